@@ -1,0 +1,212 @@
+/* srnn_b200.h - C ABI of the B200 (sm_100a) SampleRNN training-step kernels.
+ *
+ * The reference (AlomdaElmasry/samplernn_pase) has no FFI: its hot path is Python that calls
+ * torch.  This header is the boundary a maintainer of the reference would bind (ctypes stub in
+ * INTEGRATION.md); each entry cites the reference code it replaces (file:line into the
+ * reference repository).
+ *
+ * Conventions:
+ *   - every entry returns 0 on success, a positive cudaError_t, or a negative SRNN_ERR_* code;
+ *     srnn_last_error() returns a thread-local message for the last failure;
+ *   - all pointers are raw DEVICE pointers unless the name ends in _host; the caller owns all
+ *     memory including workspaces; nothing is allocated or freed by the library;
+ *   - kernels are enqueued on the passed stream (a cudaStream_t cast to void*) and the library
+ *     never synchronises;
+ *   - "bf16" buffers are __nv_bfloat16; matrices are row-major with an explicit leading
+ *     dimension in ELEMENTS; every bf16 leading dimension / batch stride must be a multiple of
+ *     8 elements (16 bytes) and every bf16 base pointer 16-byte aligned (TMA requirement).
+ */
+#ifndef SRNN_B200_H
+#define SRNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRNN_OK 0
+#define SRNN_ERR_ARG (-1)     /* bad argument (shape, alignment, null pointer) */
+#define SRNN_ERR_DEVICE (-2)  /* not an sm_100 device / driver entry point missing */
+
+#define SRNN_ABI_VERSION 1
+
+typedef void* srnn_stream_t; /* cudaStream_t */
+
+const char* srnn_last_error(void);
+int srnn_abi_version(void);
+/* sm count and compute capability of the current device */
+int srnn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Quantiser - replaces SampleRNNQuantizer (utils.py:25-73)
+ * ------------------------------------------------------------------------------------------- */
+/* quantize_ulaw (utils.py:59-65), bit-exact with the reference op chain executed by torch on
+ * CUDA.  Writes any of: int64 indices (the reference's API dtype), uint8 indices (internal,
+ * saturated at 255) ; *overflow_count is incremented for every element that maps to index >=
+ * q_levels (the reference would raise an index error downstream; SURVEY trap 3). */
+int srnn_quantize_ulaw(const float* x, int64_t n, int64_t* idx_i64, uint8_t* idx_u8, int32_t* overflow_count,
+                       srnn_stream_t stream);
+/* quantize_linear (utils.py:48-54) with per-row min/max; rows x cols input. */
+int srnn_quantize_linear(const float* x, int64_t rows, int64_t cols, int64_t* idx_i64, uint8_t* idx_u8,
+                         srnn_stream_t stream);
+/* dequantize (utils.py:56-57,67-73) through a 256(+1)-entry table: out[i] = lut[idx[i]].
+ * Exactly one of idx_i64 / idx_u8 is non-null; exactly one of out_f32 / out_bf16 is non-null. */
+int srnn_dequantize_lut(const int64_t* idx_i64, const uint8_t* idx_u8, int64_t n, const float* lut, float* out_f32,
+                        void* out_bf16, srnn_stream_t stream);
+/* One-hot rows for the sample-level contraction (model.py:192-193 restated as a one-hot x table
+ * product): onehot[i, :] = e_{idx[i]} as bf16, row length q (=256). */
+int srnn_onehot_rows(const uint8_t* idx_u8, int64_t n, int32_t q, void* onehot_bf16, srnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout / parameter preparation
+ * ------------------------------------------------------------------------------------------- */
+/* weight_norm forward (torch.nn.utils.weight_norm dim=0; model.py:135-138,183-186):
+ * v is (R, A, B) contiguous fp32, g is (R); w[r,a,b] = g[r] * v[r,a,b] / ||v[r]||.
+ * Writes bf16 copies of w in up to two GEMM layouts: element (r,a,b) goes to
+ * out + r*s[0] + a*s[1] + b*s[2].  inv_norm (R) receives 1/||v[r]|| for the backward.
+ * If g is NULL the kernel is a plain cast/permute (w = v). */
+int srnn_weight_prep(const float* v, const float* g, int32_t R, int32_t A, int32_t B, void* out1_bf16,
+                     const int64_t* s1, void* out2_bf16, const int64_t* s2, float* inv_norm, srnn_stream_t stream);
+/* weight_norm backward: dw is read at dw + r*s[0] + a*s[1] + b*s[2] (fp32, GEMM layout);
+ * dv (R,A,B) and dg (R) are written (not accumulated). If g is NULL: dv = permuted dw. */
+int srnn_weight_prep_bwd(const float* dw, const int64_t* s, const float* v, const float* g, const float* inv_norm,
+                         int32_t R, int32_t A, int32_t B, float* dv, float* dg, srnn_stream_t stream);
+/* fp32 (rows, cols) with leading dim ld_in -> bf16 (rows, cols_pad) zero padded, leading dim ld_out */
+int srnn_pad_cast_bf16(const float* in, int64_t rows, int32_t cols, int64_t ld_in, void* out_bf16, int32_t cols_pad,
+                       int64_t ld_out, srnn_stream_t stream);
+/* bf16 (rows, cols) -> fp32, out[r, c] (+)= in[r, c]  (accumulate != 0 adds) */
+int srnn_bf16_to_f32(const void* in_bf16, int64_t rows, int32_t cols, int64_t ld_in, float* out, int64_t ld_out,
+                     int32_t accumulate, srnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Conditioning mixer input (model.py:60-72): row (b,l) = [speaker_emb[spk[b]] (S) | utt[b,l] (U) | 0 pad]
+ * ------------------------------------------------------------------------------------------- */
+int srnn_mixer_input(const float* utt, const float* spk_table, const int32_t* spk_ids, int32_t batch, int32_t frames,
+                     int32_t U, int32_t S, void* out_bf16, int32_t k_pad, srnn_stream_t stream);
+/* backward of the speaker part: d_table[spk[b], s] += sum_l d_in[(b,l), s]  (d_in bf16, ld k_pad) */
+int srnn_mixer_input_bwd(const void* d_in_bf16, const int32_t* spk_ids, int32_t batch, int32_t frames, int32_t S,
+                         int32_t k_pad, float* d_table, srnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Frame tier input assembly (model.py:142-147,268-271): row (b,t) =
+ *   [ lut[xq[b, x_off + t*fs + i]] for i<fs | conds[b, t / rep, :C] | 0 pad ]   as bf16.
+ * conds is fp32 (B, L, C); rep = T / L.  If `frames` (fp32 (B,T,fs), already dequantised - the
+ * FrameLevelLayer.forward calling convention, model.py:140) is non-null it replaces the xq/lut path.
+ * ------------------------------------------------------------------------------------------- */
+int srnn_tier_input(const uint8_t* xq, int64_t xq_ld, int32_t x_off, const float* lut, const float* frames,
+                    const float* conds, int32_t batch, int32_t T, int32_t fs, int32_t L, int32_t C, void* out_bf16,
+                    int32_t k_pad, srnn_stream_t stream);
+/* dconds[b, l, c] += sum_{t in frame l} d_in[(b,t), fs + c]   (d_in bf16 with ld k_pad) */
+int srnn_tier_input_bwd(const void* d_in_bf16, int32_t batch, int32_t T, int32_t fs, int32_t L, int32_t C,
+                        int32_t k_pad, float* dconds, srnn_stream_t stream);
+
+/* Row repeat (model.py:189-191): out[(b, l*rep + i), :] = in[(b,l), :] for i < rep, bf16, and its
+ * adjoint (sum over the rep rows, fp32 accumulate into out). */
+int srnn_repeat_rows(const void* in_bf16, int64_t rows, int32_t cols, int64_t ld_in, int32_t rep, void* out_bf16,
+                     int64_t ld_out, srnn_stream_t stream);
+int srnn_repeat_rows_bwd(const void* d_out_bf16, int64_t rows, int32_t cols, int64_t ld_dout, int32_t rep,
+                         void* d_in_bf16, int64_t ld_din, srnn_stream_t stream);
+
+/* column sums of a bf16 matrix: out[c] = sum_r in[r, c]  (bias gradients); out is overwritten */
+int srnn_colsum(const void* in_bf16, int64_t rows, int32_t cols, int64_t ld, float* out, srnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * tcgen05 GEMM - replaces the cuDNN/cuBLAS calls behind model.py:48,108-109,112,146-147,153-155,
+ * 168-172,193-202 and their autograd backward.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct srnn_gemm_args {
+  /* op = 0 ("NT"): for each batch i < batch:  C_i[m,n] = epi( A_i[m,k] . B[n,k]^T )
+   *                A_i = a + i*a_batch_stride (lda), C_i = c + i*c_batch_stride (ldc), B shared.
+   * op = 1 ("TN"): C[m,n] += sum_i A_i[k,m]^T . B_i[k,n]   (fp32 atomic accumulate, split-K)
+   *                A_i = a + i*a_batch_stride + a_row_offset*lda, B_i likewise. */
+  int32_t op;
+  int32_t m, n, k, batch;
+  const void* a; int64_t lda; int64_t a_batch_stride; int32_t a_row_offset;
+  const void* b; int64_t ldb; int64_t b_batch_stride; int32_t b_row_offset;
+  void* c;       int64_t ldc; int64_t c_batch_stride;
+  int32_t c_dtype;            /* 0 = bf16, 1 = fp32 (op 1 is always fp32) */
+  int32_t n_fold;             /* op 0: if >0, element (row j, col n) is stored at row j*(N/n_fold) + n/n_fold,
+                                 col n % n_fold  (learned-upsampling layout, model.py:153-155) */
+  const float* bias;          /* [n] or NULL, added before the activation */
+  const void* aux; int64_t ldaux; int64_t aux_batch_stride;   /* bf16 [m,n] per batch or NULL */
+  int32_t aux_mode;           /* 0 none, 1 add (before activation), 2 gate: C = acc * (aux > 0) */
+  int32_t relu;               /* apply max(.,0) last */
+} srnn_gemm_args;
+
+int srnn_gemm_bf16(const srnn_gemm_args* args, srnn_stream_t stream);
+
+/* Last linear layer fused with log-softmax + NLL (model.py:202-203, runner.py:52): logits =
+ * A[m,k] . W[256,k]^T + bias never leave TMEM.
+ *   mode 0: lse[m], logp_target[m] (= logit[target] - lse) written.
+ *   mode 1: additionally the full log-probabilities logp[m,256] (fp32) are written.
+ *   mode 2: backward of mode 0: dlogits[m,n] = row_grad[m] * (onehot(target)[n] - softmax[n])  (bf16)
+ *   mode 3: backward of mode 1: dlogits[m,n] = g[m,n] - softmax[n] * sum_n g[m,n]              (bf16)
+ */
+typedef struct srnn_nll_args {
+  int32_t mode;
+  int32_t m, k;                 /* n is fixed at 256 */
+  const void* a; int64_t lda;   /* bf16 [m,k] */
+  const void* w; int64_t ldw;   /* bf16 [256,k] */
+  const float* bias;            /* [256] */
+  const uint8_t* target;        /* [m] */
+  float* lse; float* logp_target;        /* [m] (modes 0,1) */
+  float* logp; int64_t ldlogp;           /* mode 1 */
+  const float* row_grad;                 /* [m] mode 2 */
+  const float* g; int64_t ldg;           /* [m,256] mode 3 */
+  void* dlogits; int64_t lddlogits;      /* bf16 [m,256] modes 2,3 */
+} srnn_nll_args;
+
+int srnn_gemm_nll(const srnn_nll_args* args, srnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Persistent recurrent kernels - replace torch.nn.GRU (model.py:110,152) and its backward.
+ * One cooperative launch runs all `steps` timesteps; W_hh stays resident in shared memory.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct srnn_gru_args {
+  int32_t batch, steps, hidden;   /* batch <= 128, hidden % 8 == 0 */
+  const void* gi;        /* bf16 [batch*steps, 3H] = W_ih u_t + b_ih, row (b,t) = b*steps + t */
+  const void* w_hh;      /* fwd: bf16 [3H, H];  bwd: bf16 [H, 3H] (= W_hh^T) */
+  const float* b_hh;     /* [3H] (fwd) */
+  void* h_ext;           /* bf16 [batch, steps+1, H]: slot 0 holds h_init (input), slot t+1 receives h_t */
+  float* h_state;        /* fwd: fp32 [batch, H], in = h_init, out = h_T */
+  void* gates;           /* bf16 [batch*steps, 4H]: r, z, n, (W_hn h + b_hn) saved by fwd / read by bwd */
+  /* backward only */
+  const void* dh_out;    /* bf16 [batch*steps, H] : dL/dh_t from the layers above */
+  void* dgi;             /* bf16 [batch*steps, 3H] out */
+  void* dgh;             /* bf16 [batch, steps, 3H] out (also the per-step exchange buffer) */
+  float* dh0;            /* fp32 [batch, H] out: dL/dh_init */
+  uint32_t* sync;        /* >= 256 bytes, zeroed by the caller before every launch */
+} srnn_gru_args;
+
+int srnn_gru_forward(const srnn_gru_args* args, srnn_stream_t stream);
+int srnn_gru_backward(const srnn_gru_args* args, srnn_stream_t stream);
+
+/* Initial-state assembly (model.py:149-151, 239-243): h_init[b] = use_carry[b] ? carried[b] : h0;
+ * writes fp32 h_state [B,H] and, if h_ext is non-null, the bf16 slot 0 of h_ext (row stride
+ * ext_ld = (steps+1)*H). */
+int srnn_state_select(const float* carried, const float* h0, const uint8_t* use_carry, int32_t batch, int32_t hidden,
+                      float* h_state, void* h_ext_bf16, int64_t ext_ld, srnn_stream_t stream);
+/* d_h0[j] = sum_{b: !use_carry[b]} dh_init[b, j] */
+int srnn_state_select_bwd(const float* dh_init, const uint8_t* use_carry, int32_t batch, int32_t hidden, float* d_h0,
+                          srnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Loss reduction (runner.py:52 + model.py:283-284): out[0] = -sum_{valid rows} logp_target / count,
+ * out[1] = count, where row m is valid iff row_valid[m / rows_per_slot] != 0.
+ * ------------------------------------------------------------------------------------------- */
+int srnn_masked_nll_mean(const float* logp_target, const uint8_t* slot_valid, int64_t rows, int32_t rows_per_slot,
+                         float* out2, srnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * AdamClipped (optimizer.py:6-14): g = clamp(g,-1,1); Adam update, one fused pass over a flat
+ * fp32 parameter buffer.  step is 1-based; grad_scale multiplies g before the clamp (data-parallel
+ * averaging).
+ * ------------------------------------------------------------------------------------------- */
+int srnn_adam_clipped(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                      double beta1, double beta2, double eps, int32_t step, double grad_scale, srnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRNN_B200_H */

@@ -1,0 +1,575 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a.
+//
+// One persistent, warp-specialised kernel template serves every dense contraction of the
+// training step (reference: cuDNN conv1d/conv_transpose1d and cuBLAS calls behind
+// model.py:48,108-109,112,146-147,153-155,168-172,193-202 and their autograd backward):
+//
+//   op NT : C_i[m,n] = epi(A_i[m,k] . B[n,k]^T)      A, B K-major (activations x weights)
+//   op TN : C[m,n]  += sum_i A_i[k,m]^T . B_i[k,n]    A, B MN-major (weight gradients), split-K,
+//                                                      fp32 atomics
+//   NLL   : NT with N = 256 whose epilogue does log-softmax + NLL (or its backward) straight
+//           out of TMEM, so logits never reach HBM (model.py:202-203 + runner.py:52).
+//
+// Tile 128 x BN x 64 (BN = 128 or 256), bf16 operands staged by TMA with the 128-byte swizzle,
+// fp32 accumulators double-buffered in TMEM (2 x BN columns), a ring of 4 (BN=256) or 6 (BN=128)
+// smem stages.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 =
+// TMEM allocator, warps 4-7 = epilogue (one TMEM lane quadrant each).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace srnn {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 256;
+
+struct GemmParams {
+  int m, n, k, batch;
+  int a_row_offset, b_row_offset;
+  void* c;
+  long long ldc, c_batch_stride;
+  int c_dtype, n_fold;
+  const float* bias;
+  const __nv_bfloat16* aux;
+  long long ldaux, aux_batch_stride;
+  int aux_mode, relu;
+  // schedule
+  int tiles_m, tiles_n, kb_per_batch, splits, kb_per_split, total_kb, total_work;
+  // NLL epilogue
+  int nll_mode;
+  const uint8_t* target;
+  float* lse;
+  float* logp_t;
+  float* logp;
+  long long ldlogp;
+  const float* row_grad;
+  const float* g;
+  long long ldg;
+};
+
+template <int BN>
+struct SmemCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int BAR_OFF = STAGES * STAGE;
+  static constexpr int BIAS_OFF = BAR_OFF + 256;
+  static constexpr int TOTAL = BIAS_OFF + 1024 + 1024;  // + bias tile + alignment slack
+};
+
+struct Work {
+  int mt, nt, b, kb_begin, kb_end;
+};
+
+template <bool TN>
+__device__ __forceinline__ Work decode_work(const GemmParams& p, int w) {
+  Work wk;
+  if (!TN) {
+    wk.nt = w % p.tiles_n;
+    int t = w / p.tiles_n;
+    wk.b = t / p.tiles_m;
+    wk.mt = t % p.tiles_m;
+    wk.kb_begin = 0;
+    wk.kb_end = p.kb_per_batch;
+  } else {
+    int split = w % p.splits;
+    int tile = w / p.splits;
+    wk.nt = tile % p.tiles_n;
+    wk.mt = tile / p.tiles_n;
+    wk.b = 0;
+    wk.kb_begin = split * p.kb_per_split;
+    wk.kb_end = min(wk.kb_begin + p.kb_per_split, p.total_kb);
+  }
+  return wk;
+}
+
+// EPI: 0 = bias / aux / relu / store, 1 = log-softmax + NLL family, 2 = fp32 atomic accumulate
+template <int BN, bool TN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const GemmParams p) {
+  using Cfg = SmemCfg<BN>;
+  constexpr int S = Cfg::STAGES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  constexpr uint32_t IDESC = idesc_bf16(BM, BN, TN, TN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* empty = full + S;
+  uint64_t* tfull = empty + S;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sbias = reinterpret_cast<float*>(smem + Cfg::BIAS_OFF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  if constexpr (EPI == 1) {
+    for (int i = threadIdx.x; i < 256; i += GEMM_THREADS) sbias[i] = p.bias ? p.bias[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------ TMA producer ------------------------------
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const Work wk = decode_work<TN>(p, w);
+        for (int kb = wk.kb_begin; kb < wk.kb_end; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full[stage], Cfg::STAGE);
+          if (!TN) {
+            tma_load_3d(sa, &tma_a, &full[stage], kb * BK, wk.mt * BM, wk.b);
+            tma_load_2d(sb, &tma_b, &full[stage], kb * BK, wk.nt * BN);
+          } else {
+            const int bi = kb / p.kb_per_batch;
+            const int r0 = (kb - bi * p.kb_per_batch) * BK;
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_3d(sa + j * 8192, &tma_a, &full[stage], wk.mt * BM + j * 64, r0 + p.a_row_offset, bi);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_3d(sb + j * 8192, &tma_b, &full[stage], wk.nt * BN + j * 64, r0 + p.b_row_offset, bi);
+          }
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------ MMA issuer ------------------------------
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const Work wk = decode_work<TN>(p, w);
+        if (wk.kb_end <= wk.kb_begin) continue;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = wk.kb_begin; kb < wk.kb_end; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k16 = 0; k16 < BK / 16; ++k16) {
+            uint64_t ad, bd;
+            if (!TN) {
+              ad = smem_desc_sw128(a_addr + k16 * 32, 16, 1024);
+              bd = smem_desc_sw128(b_addr + k16 * 32, 16, 1024);
+            } else {
+              ad = smem_desc_sw128(a_addr + k16 * 2048, 8192, 1024);
+              bd = smem_desc_sw128(b_addr + k16 * 2048, 8192, 1024);
+            }
+            umma_bf16(d_tmem, ad, bd, IDESC, (kb > wk.kb_begin || k16 > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ------------------------------
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      const Work wk = decode_work<TN>(p, w);
+      if (wk.kb_end <= wk.kb_begin) continue;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      const int j = wk.mt * BM + q * 32 + lane;   // row within the batch (NT) / row of C (TN)
+      const bool row_ok = j < p.m;
+
+      if constexpr (EPI == 0) {
+        const int fold_rows = p.n_fold > 0 ? p.n / p.n_fold : 1;
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n0 = wk.nt * BN + c * 32;
+          if (n0 >= p.n) break;
+          uint32_t v[32];
+          tmem_ld32(t_addr + c * 32, v);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+          const bool full_chunk = n0 + 32 <= p.n;
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (full_chunk || n0 + i < p.n) f[i] += __ldg(p.bias + n0 + i);
+          }
+          if (p.aux_mode) {
+            const __nv_bfloat16* ap = p.aux + wk.b * p.aux_batch_stride + static_cast<long long>(j) * p.ldaux + n0;
+            const bool vec = full_chunk && ((reinterpret_cast<uintptr_t>(ap) & 15) == 0);
+            float a[32];
+            if (vec) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(ap) + i);
+                a[i * 8 + 0] = bf16_lo(u.x); a[i * 8 + 1] = bf16_hi(u.x);
+                a[i * 8 + 2] = bf16_lo(u.y); a[i * 8 + 3] = bf16_hi(u.y);
+                a[i * 8 + 4] = bf16_lo(u.z); a[i * 8 + 5] = bf16_hi(u.z);
+                a[i * 8 + 6] = bf16_lo(u.w); a[i * 8 + 7] = bf16_hi(u.w);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) a[i] = (n0 + i < p.n) ? __bfloat162float(ap[i]) : 0.f;
+            }
+            if (p.aux_mode == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] += a[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = a[i] > 0.f ? f[i] : 0.f;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          long long out_row = j;
+          int out_col = n0;
+          if (p.n_fold > 0) {
+            out_row = static_cast<long long>(j) * fold_rows + n0 / p.n_fold;
+            out_col = n0 % p.n_fold;
+          }
+          if (p.c_dtype == 0) {
+            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.c) + wk.b * p.c_batch_stride + out_row * p.ldc + out_col;
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 u;
+                u.x = pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1]);
+                u.y = pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3]);
+                u.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]);
+                u.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
+                reinterpret_cast<uint4*>(cp)[i] = u;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (n0 + i < p.n) cp[i] = __float2bfloat16_rn(f[i]);
+            }
+          } else {
+            float* cp = reinterpret_cast<float*>(p.c) + wk.b * p.c_batch_stride + out_row * p.ldc + out_col;
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                reinterpret_cast<float4*>(cp)[i] = make_float4(f[i * 4], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (n0 + i < p.n) cp[i] = f[i];
+            }
+          }
+        }
+      } else if constexpr (EPI == 2) {
+        float* crow = reinterpret_cast<float*>(p.c) + static_cast<long long>(j) * p.ldc;
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n0 = wk.nt * BN + c * 32;
+          if (n0 >= p.n) break;
+          uint32_t v[32];
+          tmem_ld32(t_addr + c * 32, v);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (n0 + i < p.n) atomicAdd(crow + n0 + i, __uint_as_float(v[i]));
+        }
+      } else {
+        // log-softmax + NLL family; BN == 256 == N, one thread owns one full row of logits in TMEM
+        const long long row = static_cast<long long>(wk.b) * p.m + j;
+        float mx = -INFINITY;
+        for (int c = 0; c < 8; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]) + sbias[c * 32 + i]);
+        }
+        const int tgt = row_ok ? static_cast<int>(p.target[row]) : 0;
+        float sum = 0.f, xt = 0.f;
+        for (int c = 0; c < 8; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = __uint_as_float(v[i]) + sbias[c * 32 + i];
+            sum += expf(x - mx);
+            if (c * 32 + i == tgt) xt = x;
+          }
+        }
+        const float lse = mx + logf(sum);
+        if (p.nll_mode <= 1) {
+          if (row_ok) {
+            p.lse[row] = lse;
+            p.logp_t[row] = xt - lse;
+          }
+          if (p.nll_mode == 1) {
+            for (int c = 0; c < 8; ++c) {
+              uint32_t v[32];
+              tmem_ld32(t_addr + c * 32, v);
+              tmem_ld_wait();
+              if (!row_ok) continue;
+              float* op = p.logp + row * p.ldlogp + c * 32;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 o;
+                o.x = __uint_as_float(v[i * 4 + 0]) + sbias[c * 32 + i * 4 + 0] - lse;
+                o.y = __uint_as_float(v[i * 4 + 1]) + sbias[c * 32 + i * 4 + 1] - lse;
+                o.z = __uint_as_float(v[i * 4 + 2]) + sbias[c * 32 + i * 4 + 2] - lse;
+                o.w = __uint_as_float(v[i * 4 + 3]) + sbias[c * 32 + i * 4 + 3] - lse;
+                reinterpret_cast<float4*>(op)[i] = o;
+              }
+            }
+          }
+        } else {
+          float rg = 0.f, gsum = 0.f;
+          if (row_ok) {
+            if (p.nll_mode == 2) {
+              rg = p.row_grad[row];
+            } else {
+              const float4* gp = reinterpret_cast<const float4*>(p.g + row * p.ldg);
+              for (int i = 0; i < 64; ++i) {
+                const float4 t = __ldg(gp + i);
+                gsum += (t.x + t.y) + (t.z + t.w);
+              }
+            }
+          }
+          for (int c = 0; c < 8; ++c) {
+            uint32_t v[32];
+            tmem_ld32(t_addr + c * 32, v);
+            tmem_ld_wait();
+            if (!row_ok) continue;
+            float d[32];
+            if (p.nll_mode == 2) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float pr = expf(__uint_as_float(v[i]) + sbias[c * 32 + i] - lse);
+                d[i] = rg * ((c * 32 + i == tgt ? 1.f : 0.f) - pr);
+              }
+            } else {
+              const float4* gp = reinterpret_cast<const float4*>(p.g + row * p.ldg + c * 32);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 t = __ldg(gp + i);
+                const float gv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float pr = expf(__uint_as_float(v[i * 4 + e]) + sbias[c * 32 + i * 4 + e] - lse);
+                  d[i * 4 + e] = gv[e] - pr * gsum;
+                }
+              }
+            }
+            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + c * 32;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              u.x = pack_bf16x2(d[i * 8 + 0], d[i * 8 + 1]);
+              u.y = pack_bf16x2(d[i * 8 + 2], d[i * 8 + 3]);
+              u.z = pack_bf16x2(d[i * 8 + 4], d[i * 8 + 5]);
+              u.w = pack_bf16x2(d[i * 8 + 6], d[i * 8 + 7]);
+              reinterpret_cast<uint4*>(dp)[i] = u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int BN, bool TN, int EPI>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_kernel<BN, TN, EPI>;
+  static bool configured = false;   // per instantiation
+  if (!configured) {
+    SRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemCfg<BN>::TOTAL));
+    configured = true;
+  }
+  int grid = p.total_work < sm_count() ? p.total_work : sm_count();
+  if (grid < 1) return SRNN_OK;
+  kern<<<grid, GEMM_THREADS, SmemCfg<BN>::TOTAL, stream>>>(ta, tb, p);
+  SRNN_CUDA(cudaGetLastError());
+  return SRNN_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int run_nt(const srnn_gemm_args* a, GemmParams& p, bool nll, cudaStream_t stream) {
+  SRNN_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0 && a->a_batch_stride % 8 == 0,
+                 "gemm NT: lda/ldb/a_batch_stride must be multiples of 8 elements (lda=%lld ldb=%lld abs=%lld)",
+                 (long long)a->lda, (long long)a->ldb, (long long)a->a_batch_stride);
+  SRNN_CHECK_ARG(aligned16(a->a) && aligned16(a->b), "gemm NT: operand pointers must be 16-byte aligned");
+  const int bn = (nll || a->n % 256 == 0 || a->n > 512) ? 256 : 128;
+  p.tiles_m = (a->m + BM - 1) / BM;
+  p.tiles_n = (a->n + bn - 1) / bn;
+  p.kb_per_batch = (a->k + BK - 1) / BK;
+  p.splits = 1;
+  p.kb_per_split = p.kb_per_batch;
+  p.total_kb = p.kb_per_batch;
+  p.total_work = a->batch * p.tiles_m * p.tiles_n;
+  CUtensorMap ta, tb;
+  {
+    const uint64_t dims[3] = {(uint64_t)a->k, (uint64_t)a->m, (uint64_t)a->batch};
+    const uint64_t bs = a->batch > 1 ? (uint64_t)a->a_batch_stride : (uint64_t)a->lda * (uint64_t)a->m;
+    const uint64_t strides[2] = {(uint64_t)a->lda * 2, bs * 2};
+    const uint32_t box[3] = {BK, BM, 1};
+    int rc = make_tmap_bf16(&ta, a->a, 3, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a->k, (uint64_t)a->n};
+    const uint64_t strides[1] = {(uint64_t)a->ldb * 2};
+    const uint32_t box[2] = {BK, (uint32_t)bn};
+    int rc = make_tmap_bf16(&tb, a->b, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  if (nll) return launch<256, false, 1>(ta, tb, p, stream);
+  if (bn == 256) return launch<256, false, 0>(ta, tb, p, stream);
+  return launch<128, false, 0>(ta, tb, p, stream);
+}
+
+static int run_tn(const srnn_gemm_args* a, GemmParams& p, cudaStream_t stream) {
+  SRNN_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0 && a->a_batch_stride % 8 == 0 && a->b_batch_stride % 8 == 0,
+                 "gemm TN: lda/ldb/batch strides must be multiples of 8 elements");
+  SRNN_CHECK_ARG(aligned16(a->a) && aligned16(a->b), "gemm TN: operand pointers must be 16-byte aligned");
+  SRNN_CHECK_ARG(a->c_dtype == 1 && a->n_fold == 0 && !a->bias && !a->aux && !a->relu,
+                 "gemm TN: output is fp32 atomic-accumulate only, no epilogue options");
+  const int bn = (a->n % 256 == 0 || a->n > 512) ? 256 : 128;
+  p.tiles_m = (a->m + BM - 1) / BM;
+  p.tiles_n = (a->n + bn - 1) / bn;
+  p.kb_per_batch = (a->k + BK - 1) / BK;
+  p.total_kb = p.kb_per_batch * a->batch;
+  const int tiles = p.tiles_m * p.tiles_n;
+  int splits = (2 * sm_count() + tiles - 1) / tiles;
+  if (splits > p.total_kb) splits = p.total_kb;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = (p.total_kb + splits - 1) / splits;
+  p.splits = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.total_work = tiles * p.splits;
+  CUtensorMap ta, tb;
+  {
+    const uint64_t dims[3] = {(uint64_t)a->m, (uint64_t)(a->a_row_offset + a->k), (uint64_t)a->batch};
+    const uint64_t bs = a->batch > 1 ? (uint64_t)a->a_batch_stride : (uint64_t)a->lda * dims[1];
+    const uint64_t strides[2] = {(uint64_t)a->lda * 2, bs * 2};
+    const uint32_t box[3] = {64, 64, 1};
+    int rc = make_tmap_bf16(&ta, a->a, 3, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)a->n, (uint64_t)(a->b_row_offset + a->k), (uint64_t)a->batch};
+    const uint64_t bs = a->batch > 1 ? (uint64_t)a->b_batch_stride : (uint64_t)a->ldb * dims[1];
+    const uint64_t strides[2] = {(uint64_t)a->ldb * 2, bs * 2};
+    const uint32_t box[3] = {64, 64, 1};
+    int rc = make_tmap_bf16(&tb, a->b, 3, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  if (bn == 256) return launch<256, true, 2>(ta, tb, p, stream);
+  return launch<128, true, 2>(ta, tb, p, stream);
+}
+
+}  // namespace srnn
+
+using namespace srnn;
+
+extern "C" int srnn_gemm_bf16(const srnn_gemm_args* a, srnn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SRNN_CHECK_ARG(a != nullptr, "gemm: null args");
+  SRNN_CHECK_ARG(a->m > 0 && a->n > 0 && a->k > 0 && a->batch > 0, "gemm: m,n,k,batch must be positive (%d %d %d %d)",
+                 a->m, a->n, a->k, a->batch);
+  SRNN_CHECK_ARG(a->a && a->b && a->c, "gemm: null operand");
+  GemmParams p{};
+  p.m = a->m; p.n = a->n; p.k = a->k; p.batch = a->batch;
+  p.a_row_offset = a->a_row_offset; p.b_row_offset = a->b_row_offset;
+  p.c = a->c; p.ldc = a->ldc; p.c_batch_stride = a->c_batch_stride;
+  p.c_dtype = a->c_dtype; p.n_fold = a->n_fold;
+  p.bias = a->bias;
+  p.aux = static_cast<const __nv_bfloat16*>(a->aux); p.ldaux = a->ldaux; p.aux_batch_stride = a->aux_batch_stride;
+  p.aux_mode = a->aux ? a->aux_mode : 0; p.relu = a->relu;
+  if (a->op == 0) {
+    SRNN_CHECK_ARG(a->n_fold == 0 || (a->n % a->n_fold == 0 && a->n_fold % 32 == 0 && !a->aux),
+                   "gemm NT: n_fold must divide n, be a multiple of 32, and exclude aux");
+    return run_nt(a, p, false, stream);
+  }
+  SRNN_CHECK_ARG(a->op == 1, "gemm: op must be 0 (NT) or 1 (TN)");
+  return run_tn(a, p, stream);
+}
+
+extern "C" int srnn_gemm_nll(const srnn_nll_args* a, srnn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SRNN_CHECK_ARG(a != nullptr && a->m > 0 && a->k > 0, "gemm_nll: bad shape");
+  SRNN_CHECK_ARG(a->a && a->w && a->target, "gemm_nll: null operand");
+  SRNN_CHECK_ARG(a->mode >= 0 && a->mode <= 3, "gemm_nll: mode must be 0..3");
+  if (a->mode <= 1) SRNN_CHECK_ARG(a->lse && a->logp_target, "gemm_nll: lse/logp_target required");
+  if (a->mode == 1) SRNN_CHECK_ARG(a->logp && a->ldlogp % 4 == 0, "gemm_nll: logp (ld %% 4 == 0) required for mode 1");
+  if (a->mode == 2) SRNN_CHECK_ARG(a->row_grad && a->dlogits, "gemm_nll: row_grad/dlogits required for mode 2");
+  if (a->mode == 3) SRNN_CHECK_ARG(a->g && a->dlogits && a->ldg % 4 == 0, "gemm_nll: g/dlogits required for mode 3");
+  if (a->mode >= 2) SRNN_CHECK_ARG(a->lddlogits % 8 == 0, "gemm_nll: lddlogits must be a multiple of 8");
+  srnn_gemm_args g{};
+  g.op = 0; g.m = a->m; g.n = 256; g.k = a->k; g.batch = 1;
+  g.a = a->a; g.lda = a->lda; g.b = a->w; g.ldb = a->ldw;
+  GemmParams p{};
+  p.m = a->m; p.n = 256; p.k = a->k; p.batch = 1;
+  p.bias = a->bias;
+  p.nll_mode = a->mode; p.target = a->target; p.lse = a->lse; p.logp_t = a->logp_target;
+  p.logp = a->logp; p.ldlogp = a->ldlogp; p.row_grad = a->row_grad; p.g = a->g; p.ldg = a->ldg;
+  p.c = a->dlogits; p.ldc = a->lddlogits;
+  return run_nt(&g, p, true, stream);
+}

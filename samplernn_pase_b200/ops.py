@@ -1,0 +1,297 @@
+"""Tensor-level wrappers of the C ABI: they validate dtype/device/contiguity, pass raw pointers
+and leading dimensions, and allocate outputs with torch (device memory plumbing only).
+
+All matrices are row-major.  ``bf16`` operands must have 16-byte aligned bases and leading
+dimensions that are multiples of 8 elements (TMA).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, GruArgs, NllArgs, call, ptr, stream
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+#: launches issued through this module since the last reset (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def _need(t, dtype, name):
+    if t.dtype != dtype or not t.is_cuda:
+        raise RuntimeError(f'{name}: expected a CUDA {dtype} tensor, got {t.dtype} on {t.device}')
+
+
+def _strides(s):
+    return (C.c_int64 * 3)(*s)
+
+
+# ----------------------------------------------------------------------------------------------
+# quantiser
+# ----------------------------------------------------------------------------------------------
+def quantize_ulaw(x, want_i64=True, want_u8=False, overflow=None):
+    _need(x, F32, 'quantize_ulaw x')
+    x = x.contiguous()
+    o64 = torch.empty(x.shape, dtype=torch.int64, device=x.device) if want_i64 else None
+    o8 = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_u8 else None
+    call('srnn_quantize_ulaw', ptr(x), x.numel(), ptr(o64), ptr(o8), ptr(overflow), stream())
+    _count()
+    return o64, o8
+
+
+def quantize_linear(x, want_i64=True, want_u8=False):
+    _need(x, F32, 'quantize_linear x')
+    x = x.contiguous()
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    o64 = torch.empty(x.shape, dtype=torch.int64, device=x.device) if want_i64 else None
+    o8 = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_u8 else None
+    call('srnn_quantize_linear', ptr(x), rows, cols, ptr(o64), ptr(o8), stream())
+    _count()
+    return o64, o8
+
+
+def dequantize_lut(idx, lut, out_dtype=F32):
+    _need(lut, F32, 'dequantize lut')
+    idx = idx.contiguous()
+    out = torch.empty(idx.shape, dtype=out_dtype, device=idx.device)
+    i64 = idx if idx.dtype == torch.int64 else None
+    i8 = idx if idx.dtype == torch.uint8 else None
+    if i64 is None and i8 is None:
+        raise RuntimeError('dequantize_lut: indices must be int64 or uint8')
+    call('srnn_dequantize_lut', ptr(i64), ptr(i8), idx.numel(), ptr(lut), ptr(out if out_dtype == F32 else None),
+         ptr(out if out_dtype == BF16 else None), stream())
+    _count()
+    return out
+
+
+def onehot_rows(idx_u8, q=256):
+    _need(idx_u8, torch.uint8, 'onehot idx')
+    idx_u8 = idx_u8.contiguous()
+    out = torch.empty(idx_u8.shape + (q,), dtype=BF16, device=idx_u8.device)
+    call('srnn_onehot_rows', ptr(idx_u8), idx_u8.numel(), q, ptr(out), stream())
+    _count()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter preparation
+# ----------------------------------------------------------------------------------------------
+def weight_prep(v, g, shape3, out1, s1, out2=None, s2=None, inv_norm=None):
+    """v viewed as (R,A,B) -> bf16 GEMM layouts (weight-normed when g is given)."""
+    _need(v, F32, 'weight_prep v')
+    r, a, b = shape3
+    assert v.is_contiguous() and v.numel() == r * a * b
+    call('srnn_weight_prep', ptr(v), ptr(g), r, a, b, ptr(out1), _strides(s1), ptr(out2),
+         _strides(s2) if s2 is not None else None, ptr(inv_norm), stream())
+    _count()
+
+
+def weight_prep_bwd(dw, s, v, g, inv_norm, shape3):
+    r, a, b = shape3
+    _need(dw, F32, 'weight_prep_bwd dw')
+    dv = torch.empty_like(v)
+    dg = torch.empty(r, dtype=F32, device=v.device) if g is not None else None
+    call('srnn_weight_prep_bwd', ptr(dw), _strides(s), ptr(v), ptr(g), ptr(inv_norm), r, a, b, ptr(dv), ptr(dg), stream())
+    _count()
+    return dv, dg
+
+
+def pad_cast_bf16(x, rows, cols, ld_in, out, cols_pad, ld_out):
+    _need(x, F32, 'pad_cast x')
+    call('srnn_pad_cast_bf16', ptr(x), rows, cols, ld_in, ptr(out), cols_pad, ld_out, stream())
+    _count()
+
+
+def to_bf16(x):
+    """fp32 (rows, cols) contiguous -> new bf16 tensor of the same shape."""
+    x = x.contiguous()
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    pad_cast_bf16(x, rows, cols, cols, out, cols, cols)
+    return out
+
+
+def bf16_to_f32(x, rows, cols, ld_in, out, ld_out, accumulate=False):
+    call('srnn_bf16_to_f32', ptr(x), rows, cols, ld_in, ptr(out), ld_out, int(accumulate), stream())
+    _count()
+
+
+def colsum(x, rows, cols, ld):
+    out = torch.empty(cols, dtype=F32, device=x.device)
+    call('srnn_colsum', ptr(x), rows, cols, ld, ptr(out), stream())
+    _count(2)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# operand assembly
+# ----------------------------------------------------------------------------------------------
+def mixer_input(utt, table, spk_ids, k_pad):
+    b, l, u = utt.shape
+    s = table.shape[1]
+    out = torch.empty(b * l, k_pad, dtype=BF16, device=utt.device)
+    call('srnn_mixer_input', ptr(utt), ptr(table), ptr(spk_ids), b, l, u, s, ptr(out), k_pad, stream())
+    _count()
+    return out
+
+
+def mixer_input_bwd(d_in, spk_ids, batch, frames, s, k_pad, d_table):
+    call('srnn_mixer_input_bwd', ptr(d_in), ptr(spk_ids), batch, frames, s, k_pad, ptr(d_table), stream())
+    _count()
+
+
+def tier_input(xq_u8, x_off, lut, frames, conds, batch, t, fs, k_pad):
+    l, c = conds.shape[1], conds.shape[2]
+    dev = conds.device
+    out = torch.empty(batch * t, k_pad, dtype=BF16, device=dev)
+    call('srnn_tier_input', ptr(xq_u8), xq_u8.shape[1] if xq_u8 is not None else 0, x_off, ptr(lut), ptr(frames),
+         ptr(conds), batch, t, fs, l, c, ptr(out), k_pad, stream())
+    _count()
+    return out
+
+
+def tier_input_bwd(d_in, batch, t, fs, l, c, k_pad, dconds):
+    call('srnn_tier_input_bwd', ptr(d_in), batch, t, fs, l, c, k_pad, ptr(dconds), stream())
+    _count()
+
+
+def repeat_rows(x, rows, cols, ld_in, rep, out, ld_out):
+    call('srnn_repeat_rows', ptr(x), rows, cols, ld_in, rep, ptr(out), ld_out, stream())
+    _count()
+
+
+def repeat_rows_bwd(dout, rows, cols, ld_dout, rep, din, ld_din):
+    call('srnn_repeat_rows_bwd', ptr(dout), rows, cols, ld_dout, rep, ptr(din), ld_din, stream())
+    _count()
+
+
+# ----------------------------------------------------------------------------------------------
+# GEMMs
+# ----------------------------------------------------------------------------------------------
+def gemm_nt(a, b, c, m, n, k, lda, ldb, ldc, batch=1, a_bs=0, c_bs=0, bias=None, aux=None, ldaux=0, aux_bs=0,
+            aux_mode=0, relu=False, n_fold=0):
+    """C_i[m,n] = epi(A_i[m,k] . B[n,k]^T); c.dtype selects bf16 / fp32 output."""
+    _need(a, BF16, 'gemm A')
+    _need(b, BF16, 'gemm B')
+    g = GemmArgs()
+    g.op, g.m, g.n, g.k, g.batch = 0, m, n, k, batch
+    g.a, g.lda, g.a_batch_stride, g.a_row_offset = a.data_ptr(), lda, a_bs, 0
+    g.b, g.ldb, g.b_batch_stride, g.b_row_offset = b.data_ptr(), ldb, 0, 0
+    g.c, g.ldc, g.c_batch_stride = c.data_ptr(), ldc, c_bs
+    g.c_dtype = 0 if c.dtype == BF16 else 1
+    g.n_fold = n_fold
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.aux = aux.data_ptr() if aux is not None else None
+    g.ldaux, g.aux_batch_stride, g.aux_mode = ldaux, aux_bs, aux_mode if aux is not None else 0
+    g.relu = int(relu)
+    call('srnn_gemm_bf16', C.byref(g), stream())
+    _count()
+    return c
+
+
+def gemm_tn(a, b, c, m, n, k, lda, ldb, ldc, batch=1, a_bs=0, b_bs=0, a_off=0, b_off=0):
+    """C[m,n] += sum_i A_i[k,m]^T . B_i[k,n]  (c fp32, must be initialised by the caller)."""
+    _need(a, BF16, 'gemm A')
+    _need(b, BF16, 'gemm B')
+    _need(c, F32, 'gemm C')
+    g = GemmArgs()
+    g.op, g.m, g.n, g.k, g.batch = 1, m, n, k, batch
+    g.a, g.lda, g.a_batch_stride, g.a_row_offset = a.data_ptr(), lda, a_bs, a_off
+    g.b, g.ldb, g.b_batch_stride, g.b_row_offset = b.data_ptr(), ldb, b_bs, b_off
+    g.c, g.ldc, g.c_batch_stride = c.data_ptr(), ldc, 0
+    g.c_dtype = 1
+    call('srnn_gemm_bf16', C.byref(g), stream())
+    _count()
+    return c
+
+
+def gemm_nll(mode, a, w, bias, target, m, k, lda, ldw, lse=None, logp_target=None, logp=None, row_grad=None, g=None,
+             dlogits=None):
+    n = NllArgs()
+    n.mode, n.m, n.k = mode, m, k
+    n.a, n.lda, n.w, n.ldw = a.data_ptr(), lda, w.data_ptr(), ldw
+    n.bias = bias.data_ptr() if bias is not None else None
+    n.target = target.data_ptr()
+    n.lse = lse.data_ptr() if lse is not None else None
+    n.logp_target = logp_target.data_ptr() if logp_target is not None else None
+    n.logp, n.ldlogp = (logp.data_ptr(), 256) if logp is not None else (None, 0)
+    n.row_grad = row_grad.data_ptr() if row_grad is not None else None
+    n.g, n.ldg = (g.data_ptr(), 256) if g is not None else (None, 0)
+    n.dlogits, n.lddlogits = (dlogits.data_ptr(), 256) if dlogits is not None else (None, 0)
+    call('srnn_gemm_nll', C.byref(n), stream())
+    _count()
+
+
+# ----------------------------------------------------------------------------------------------
+# recurrence
+# ----------------------------------------------------------------------------------------------
+GRU_MAX_BATCH = 128
+
+
+def _gru_call(name, batch, steps, hidden, **bufs):
+    """Runs the persistent kernel over batch groups of <= 128 rows (independent sequences)."""
+    for b0 in range(0, batch, GRU_MAX_BATCH):
+        nb = min(GRU_MAX_BATCH, batch - b0)
+        a = GruArgs()
+        a.batch, a.steps, a.hidden = nb, steps, hidden
+        for key, (t, per_row) in bufs.items():
+            if t is None:
+                setattr(a, key, None)
+            else:
+                setattr(a, key, t.data_ptr() + b0 * per_row * t.element_size())
+        sync = torch.zeros(64, dtype=torch.int32, device=bufs['h_ext'][0].device)
+        a.sync = sync.data_ptr()
+        call(name, C.byref(a), stream())
+        _count(2)
+
+
+def gru_forward(gi, w_hh, b_hh, h_ext, h_state, gates, batch, steps, hidden):
+    h = hidden
+    _gru_call('srnn_gru_forward', batch, steps, h, gi=(gi, steps * 3 * h), w_hh=(w_hh, 0), b_hh=(b_hh, 0),
+              h_ext=(h_ext, (steps + 1) * h), h_state=(h_state, h), gates=(gates, steps * 4 * h))
+
+
+def gru_backward(w_hh_t, h_ext, gates, dh_out, dgi, dgh, dh0, batch, steps, hidden):
+    h = hidden
+    _gru_call('srnn_gru_backward', batch, steps, h, w_hh=(w_hh_t, 0), h_ext=(h_ext, (steps + 1) * h),
+              gates=(gates, steps * 4 * h), dh_out=(dh_out, steps * h), dgi=(dgi, steps * 3 * h),
+              dgh=(dgh, steps * 3 * h), dh0=(dh0, h))
+
+
+def state_select(carried, h0, use_carry, batch, hidden):
+    h_state = torch.empty(batch, hidden, dtype=F32, device=h0.device)
+    call('srnn_state_select', ptr(carried), ptr(h0), ptr(use_carry), batch, hidden, ptr(h_state), None, 0, stream())
+    _count()
+    return h_state
+
+
+def state_select_bwd(dh, use_carry, batch, hidden):
+    out = torch.empty(hidden, dtype=F32, device=dh.device)
+    call('srnn_state_select_bwd', ptr(dh), ptr(use_carry), batch, hidden, ptr(out), stream())
+    _count()
+    return out
+
+
+def masked_nll_mean(logp_target, slot_valid, rows_per_slot):
+    out = torch.empty(2, dtype=F32, device=logp_target.device)
+    call('srnn_masked_nll_mean', ptr(logp_target), ptr(slot_valid), logp_target.numel(), rows_per_slot, ptr(out), stream())
+    _count(3)
+    return out
+
+
+def adam_clipped(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    call('srnn_adam_clipped', ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), float(lr),
+         float(beta1), float(beta2), float(eps), int(step), float(grad_scale), stream())
+    _count()

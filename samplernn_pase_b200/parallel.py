@@ -1,0 +1,147 @@
+"""Data-parallel training step over utterance slots.
+
+One process per GPU.  Rank g owns batch slots [g*B/G, (g+1)*B/G) for the whole run, so the carried
+hidden state of a slot never moves.  Per step the only exchange is
+  * an all-reduce(sum) of the fp32 gradients, issued per *bucket* (one bucket per top-level module,
+    in the order autograd finishes them: sample layer, tier 0, ..., top tier, mixer) from
+    post-accumulate hooks so it overlaps the rest of the backward pass, and
+  * a 2-scalar all-reduce (sum of NLL, number of valid rows) so that loss and gradient
+    normalisation equal the single-process mean over all valid rows (model.py:283-284,
+    runner.py:52) even when ranks hold different numbers of empty (reset == 2) slots.
+Clipping (optimizer.py:12) is applied after averaging, inside the fused AdamClipped kernel.
+
+Parameters and gradients live in two flat fp32 buffers (views are handed back to the modules), so
+the optimizer is one kernel launch and each bucket is one contiguous NCCL call.
+"""
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_slots(batch: int, world: int, rank: int):
+    """Contiguous, sticky slot ownership: returns (first, last+1)."""
+    if batch % world != 0:
+        raise ValueError(f'global batch {batch} must be divisible by world size {world}')
+    per = batch // world
+    return rank * per, (rank + 1) * per
+
+
+class FlatBuffers:
+    """Re-homes every parameter (and its gradient) of ``model`` into flat fp32 buffers."""
+
+    def __init__(self, model: torch.nn.Module):
+        self.params = [p for p in model.parameters()]
+        self.names = [n for n, _ in model.named_parameters()]
+        dev = self.params[0].device
+        sizes = [p.numel() for p in self.params]
+        self.offsets = [0]
+        for s in sizes:
+            self.offsets.append(self.offsets[-1] + (s + 3) // 4 * 4)          # 16-byte aligned views
+        total = self.offsets[-1]
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        for p, off in zip(self.params, self.offsets):
+            view = self.flat_param[off: off + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.flat_grad[off: off + p.numel()].view_as(p)
+        # buckets: contiguous ranges of parameters that share a top-level module prefix
+        self.buckets = []                                                      # (name, start, end, param indices)
+        cur, start, idxs = None, 0, []
+        for i, n in enumerate(self.names):
+            parts = n.split('.')
+            key = '.'.join(parts[:2]) if parts[0] == 'frames_layers' else parts[0]
+            if key != cur:
+                if cur is not None:
+                    self.buckets.append((cur, start, self.offsets[i], idxs))
+                cur, start, idxs = key, self.offsets[i], []
+            idxs.append(i)
+        self.buckets.append((cur, start, self.offsets[-1], idxs))
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+
+class DataParallelTrainer:
+    """forward + NLL + backward + bucketed all-reduce + fused AdamClipped for one rank.
+
+    ``group=None`` with an uninitialised process group runs single-process (no collectives).
+    Works with any backend; tests drive it with gloo on CPU tensors through ``reduce_only``."""
+
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, group=None):
+        self.model = model
+        self.flat = FlatBuffers(model)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.exp_avg = torch.zeros_like(self.flat.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.flat.flat_param)
+        self.steps = 0
+        self._pending: List = []
+        self._ready = None
+        self._install_hooks()
+
+    def _install_hooks(self):
+        if self.world == 1:
+            return
+        self._remaining = {}
+        owner = {}
+        for bi, (_, _, _, idxs) in enumerate(self.flat.buckets):
+            for i in idxs:
+                owner[i] = bi
+        for i, p in enumerate(self.flat.params):
+            p.register_post_accumulate_grad_hook(lambda _p, bi=owner[i]: self._param_ready(bi))
+
+    def _param_ready(self, bi):
+        self._remaining[bi] -= 1
+        if self._remaining[bi] == 0:
+            self._launch_bucket(bi)
+
+    def _launch_bucket(self, bi):
+        _, start, end, _ = self.flat.buckets[bi]
+        self._pending.append(dist.all_reduce(self.flat.flat_grad[start:end], op=dist.ReduceOp.SUM, group=self.group,
+                                             async_op=True))
+        self._launched.add(bi)
+
+    def _begin(self):
+        self._pending = []
+        self._launched = set()
+        if self.world > 1:
+            self._remaining = {bi: len(b[3]) for bi, b in enumerate(self.flat.buckets)}
+
+    def _finish_reduce(self):
+        if self.world == 1:
+            return
+        for bi in range(len(self.flat.buckets)):                               # parameters that got no gradient
+            if bi not in self._launched:
+                self._launch_bucket(bi)
+        for w in self._pending:
+            w.wait()
+
+    def reduce_only(self, stats: torch.Tensor):
+        """All-reduce whatever sits in the flat gradient buffer plus the (sum_nll, n_valid) pair."""
+        self._begin()
+        if self.world > 1:
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)
+        self._finish_reduce()
+        return stats
+
+    def step(self, x, y, utt_conds, info, reset):
+        """One training step on this rank's slots.  Returns (global mean NLL, global valid rows)."""
+        from . import ops
+        self._begin()
+        self.flat.zero_grad()
+        y_hat, tgt = self.model(x, y, utt_conds, info, reset)
+        # local SUM of the NLL; the mean's 1/N_global is folded into the optimizer's grad_scale
+        local_sum = torch.nn.functional.nll_loss(y_hat.view(-1, y_hat.size(2)), tgt.view(-1), reduction='sum')
+        stats = torch.stack([local_sum.detach(), torch.tensor(float(tgt.numel()), device=local_sum.device)])
+        local_sum.backward()
+        if self.world > 1:
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)
+        self._finish_reduce()
+        total, count = stats.tolist()
+        self.steps += 1
+        ops.adam_clipped(self.flat.flat_param, self.flat.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr,
+                         self.betas[0], self.betas[1], self.eps, self.steps, grad_scale=1.0 / max(count, 1.0))
+        return total / max(count, 1.0), int(count)

@@ -1,0 +1,370 @@
+"""Parity of each C-ABI kernel on a B200 (``-m gpu``).  Integer/byte results are bit-exact against
+the oracle; floating-point kernels are compared with a plain torch fp32 evaluation of the same op
+on the same (bf16-rounded) operands, with the tolerance written at each assert."""
+import math
+
+import pytest
+import torch
+
+from oracle import samplernn_oracle as O
+from tests.helpers import Golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+@pytest.fixture(scope='module')
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a GPU')
+    from samplernn_pase_b200 import ops as _ops
+    return _ops
+
+
+def dev(t):
+    return t.to('cuda')
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+# ------------------------------------------------------------------------------------------------
+# quantiser: bit-exact
+# ------------------------------------------------------------------------------------------------
+def test_quantize_ulaw_bit_exact_vs_reference_chain_on_cuda(ops):
+    g = torch.Generator().manual_seed(11)
+    x = torch.cat([torch.linspace(-0.99, 0.99, 2_000_003), (torch.rand(6_000_000, generator=g) * 2 - 1) * 0.99,
+                   torch.tensor([0.0, -0.0, 1e-8, -1e-8, 0.5, -0.5])]).cuda()
+    want = O.quantize_ulaw(x)                       # the reference op chain, executed by torch on CUDA
+    got64, got8 = ops.quantize_ulaw(x, want_i64=True, want_u8=True)
+    assert torch.equal(got64, want)
+    assert torch.equal(got8.long(), want)
+
+
+def test_quantize_ulaw_vs_cpu_golden(ops):
+    """CPU golden vectors (reference on CPU).  torch-CPU divides where torch-CUDA multiplies by the
+    reciprocal and uses a different logf, so a handful of boundary values may differ by one level
+    (58 of 5e7); the bound here is <= 1 level and < 1e-4 of the samples."""
+    g = Golden('quantizer')
+    got = ops.quantize_ulaw(g.t('x').cuda())[0].cpu()
+    diff = (got - g.t('idx')).abs()
+    assert int(diff.max()) <= 1
+    assert float((diff > 0).float().mean()) < 1e-4
+
+
+def test_quantize_ulaw_ragged_and_overflow(ops):
+    for n in (1, 2, 3, 5, 1023):
+        x = (torch.rand(n) * 2 - 1).mul(0.99).cuda()
+        assert torch.equal(ops.quantize_ulaw(x)[0], O.quantize_ulaw(x))
+    over = torch.zeros(1, dtype=torch.int32, device='cuda')
+    x = torch.tensor([1.0, 0.5, 1.0], device='cuda')
+    i64, u8 = ops.quantize_ulaw(x, want_u8=True, overflow=over)
+    assert i64.tolist() == [256, O.quantize_ulaw(torch.tensor([0.5]).cuda()).item(), 256]   # SURVEY trap 3
+    assert u8.tolist()[0] == 255 and int(over) == 2
+
+
+def test_quantize_linear_rows(ops):
+    x = (torch.rand(7, 4001, generator=torch.Generator().manual_seed(5)) * 2 - 1).cuda()
+    assert torch.equal(ops.quantize_linear(x)[0], O.quantize_linear(x))
+    g = Golden('quantizer')
+    got = ops.quantize_linear(g.t('x_linear').cuda().view(1, -1))[0].view(-1).cpu()
+    assert int((got - g.t('idx_linear')).abs().max()) <= 1
+
+
+def test_dequantize_and_onehot(ops):
+    from samplernn_pase_b200.utils import SampleRNNQuantizer
+    g = Golden('quantizer')
+    q = SampleRNNQuantizer(True, 256)
+    idx = torch.arange(257, device='cuda')
+    assert torch.equal(q.dequantize(idx).cpu(), g.t('dequant_table'))          # exact, incl. the lost sign
+    ql = SampleRNNQuantizer(False, 256)
+    assert torch.equal(ql.dequantize(torch.arange(256, device='cuda')).cpu(), g.t('dequant_linear_table'))
+    u8 = torch.randint(0, 256, (3, 37), dtype=torch.uint8, device='cuda')
+    oh = ops.onehot_rows(u8)
+    assert torch.equal(oh.float(), torch.nn.functional.one_hot(u8.long(), 256).float())
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+def _gemm_ref(a, b):
+    return a.float() @ b.float().t()
+
+
+@pytest.mark.parametrize('m,n,k', [(128, 256, 64), (256, 256, 128), (1000, 1024, 3072), (300, 128, 64),
+                                   (4100, 3072, 1024), (77, 32, 96), (513, 50, 64)])
+def test_gemm_nt_plain(ops, m, n, k):
+    a = rnd(m, k).to(BF16)
+    b = rnd(n, k, seed=1).to(BF16)
+    c = torch.empty(m, n, dtype=F32, device='cuda')
+    ops.gemm_nt(a, b, c, m, n, k, k, k, n)
+    ref = _gemm_ref(a, b)
+    assert rel_l2(c, ref) < 1e-5, rel_l2(c, ref)           # fp32 accumulation of exact bf16 products
+    cb = torch.empty(m, round_up8(n), dtype=BF16, device='cuda')
+    ops.gemm_nt(a, b, cb, m, n, k, k, k, round_up8(n))
+    assert rel_l2(cb[:, :n], ref) < 4e-3                   # bf16 output rounding (2^-9)
+
+
+def round_up8(n):
+    return (n + 7) // 8 * 8
+
+
+def test_gemm_nt_epilogue_bias_aux_relu_gate(ops):
+    m, n, k = 700, 512, 256
+    a, b = rnd(m, k).to(BF16), rnd(n, k, seed=1).to(BF16)
+    bias = rnd(n, seed=2)
+    aux = rnd(m, n, seed=3).to(BF16)
+    c = torch.empty(m, n, dtype=F32, device='cuda')
+    ops.gemm_nt(a, b, c, m, n, k, k, k, n, bias=bias, aux=aux, ldaux=n, aux_mode=1, relu=True)
+    ref = torch.relu(_gemm_ref(a, b) + bias + aux.float())
+    assert rel_l2(c, ref) < 1e-5
+    ops.gemm_nt(a, b, c, m, n, k, k, k, n, aux=aux, ldaux=n, aux_mode=2)
+    ref = _gemm_ref(a, b) * (aux.float() > 0)
+    assert rel_l2(c, ref) < 1e-5
+
+
+def test_gemm_nt_batched_overlapping_rows_and_strided_c(ops):
+    """The sample-level contraction: A rows are overlapping windows of a (B, W, Q) one-hot buffer."""
+    bsz, rf, r0, q, h = 3, 200, 4, 256, 64
+    w = rf + r0 - 1
+    idx = torch.randint(0, q, (bsz, w), dtype=torch.uint8, device='cuda')
+    onehot = ops.onehot_rows(idx)
+    table = rnd(h, r0 * q, seed=4).to(BF16)
+    cat = torch.zeros(bsz * rf, 3 * h, dtype=BF16, device='cuda')
+    ops.gemm_nt(onehot, table, cat, rf, h, r0 * q, q, r0 * q, 3 * h, batch=bsz, a_bs=w * q, c_bs=rf * 3 * h)
+    win = onehot.float().unfold(1, r0, 1).permute(0, 1, 3, 2).reshape(bsz * rf, r0 * q)
+    ref = win @ table.float().t()
+    assert rel_l2(cat[:, :h], ref) < 4e-3
+    assert float(cat[:, h:].abs().max()) == 0.0
+
+
+def test_gemm_nt_fold_is_the_upsample_layout(ops):
+    bsz, t, h, r = 2, 37, 64, 4
+    hall = rnd(bsz, t + 1, h).to(BF16)
+    wu = rnd(r * h, h, seed=1).to(BF16)
+    bias = rnd(r * h, seed=2)
+    up = torch.empty(bsz, t * r, h, dtype=BF16, device='cuda')
+    ops.gemm_nt(hall[:, 1:], wu, up, t, r * h, h, h, h, r * h, batch=bsz, a_bs=(t + 1) * h, c_bs=t * r * h, bias=bias)
+    ref = (hall[:, 1:].float() @ wu.float().t() + bias).reshape(bsz, t * r, h)
+    assert rel_l2(up, ref) < 4e-3
+    # n_fold: same values written with a leading dimension of 3H (straight into the concat buffer)
+    cat = torch.zeros(bsz * t * r, 3 * h, dtype=BF16, device='cuda')
+    ops.gemm_nt(hall[:, 1:], wu, cat[:, 2 * h:], t, r * h, h, h, h, 3 * h, batch=bsz, a_bs=(t + 1) * h,
+                c_bs=t * r * 3 * h, bias=bias, n_fold=h)
+    assert rel_l2(cat[:, 2 * h:], ref.reshape(-1, h)) < 4e-3
+
+
+@pytest.mark.parametrize('m,n,k', [(128, 128, 64), (256, 256, 1000), (1024, 3072, 5000), (56, 64, 333), (3072, 1024, 20000)])
+def test_gemm_tn(ops, m, n, k):
+    a = rnd(k, m).to(BF16)
+    b = rnd(k, n, seed=1).to(BF16)
+    c = torch.zeros(m, n, dtype=F32, device='cuda')
+    ops.gemm_tn(a, b, c, m, n, k, m, n, n)
+    ref = a.float().t() @ b.float()
+    assert rel_l2(c, ref) < 2e-5, rel_l2(c, ref)
+    ops.gemm_tn(a, b, c, m, n, k, m, n, n)                  # accumulates
+    assert rel_l2(c, 2 * ref) < 2e-5
+
+
+def test_gemm_tn_batched_with_row_offset(ops):
+    bsz, rf, r0, q, h = 3, 150, 4, 256, 64
+    w = rf + r0 - 1
+    idx = torch.randint(0, q, (bsz, w), dtype=torch.uint8, device='cuda')
+    onehot = ops.onehot_rows(idx)
+    de = rnd(bsz, rf, h).to(BF16)
+    g = torch.zeros(q, r0 * h, dtype=F32, device='cuda')
+    for k in range(r0):
+        ops.gemm_tn(onehot, de, g[:, k * h:], q, h, rf, q, h, r0 * h, batch=bsz, a_bs=w * q, b_bs=rf * h, a_off=k)
+    for k in range(r0):
+        ref = torch.einsum('bjq,bjo->qo', onehot[:, k:k + rf].float(), de.float())
+        assert rel_l2(g[:, k * h:(k + 1) * h], ref) < 2e-5
+
+
+@pytest.mark.parametrize('m,k', [(128, 64), (1000, 1024), (333, 32)])
+def test_gemm_nll_all_modes(ops, m, k):
+    a = rnd(m, k, scale=0.5).to(BF16)
+    w = rnd(256, k, scale=0.2, seed=1).to(BF16)
+    bias = rnd(256, seed=2)
+    tgt = torch.randint(0, 256, (m,), dtype=torch.uint8, device='cuda')
+    logits = _gemm_ref(a, w) + bias
+    logp_ref = torch.log_softmax(logits, dim=1)
+    lse = torch.empty(m, device='cuda'); lpt = torch.empty(m, device='cuda')
+    ops.gemm_nll(0, a, w, bias, tgt, m, k, k, k, lse=lse, logp_target=lpt)
+    assert float((lse - torch.logsumexp(logits, 1)).abs().max()) < 1e-4
+    assert float((lpt - logp_ref.gather(1, tgt.long()[:, None])[:, 0]).abs().max()) < 1e-4
+    logp = torch.empty(m, 256, device='cuda')
+    ops.gemm_nll(1, a, w, bias, tgt, m, k, k, k, lse=lse, logp_target=lpt, logp=logp)
+    assert float((logp - logp_ref).abs().max()) < 1e-4
+    rg = rnd(m, seed=3)
+    dl = torch.empty(m, 256, dtype=BF16, device='cuda')
+    ops.gemm_nll(2, a, w, bias, tgt, m, k, k, k, row_grad=rg, dlogits=dl)
+    ref = rg[:, None] * (torch.nn.functional.one_hot(tgt.long(), 256).float() - logp_ref.exp())
+    assert rel_l2(dl, ref) < 4e-3
+    g = rnd(m, 256, seed=4)
+    ops.gemm_nll(3, a, w, bias, tgt, m, k, k, k, g=g, dlogits=dl)
+    ref = g - logp_ref.exp() * g.sum(1, keepdim=True)
+    assert rel_l2(dl, ref) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# persistent GRU
+# ------------------------------------------------------------------------------------------------
+def _gru_ref(gi, w_hh, b_hh, h0):
+    """fp32 evaluation of the same recurrence with the matmul operand rounded to bf16 like the kernel."""
+    bsz, t, h3 = gi.shape
+    h = h3 // 3
+    hs, gates = [], []
+    cur = h0.clone()
+    for s in range(t):
+        gh = cur.to(BF16).float() @ w_hh.float().t() + b_hh
+        r = torch.sigmoid(gi[:, s, :h] + gh[:, :h])
+        z = torch.sigmoid(gi[:, s, h:2 * h] + gh[:, h:2 * h])
+        hn = gh[:, 2 * h:]
+        n = torch.tanh(gi[:, s, 2 * h:] + r * hn)
+        cur = (1 - z) * n + z * cur
+        hs.append(cur)
+        gates.append(torch.cat([r, z, n, hn], 1))
+    return torch.stack(hs, 1), torch.stack(gates, 1), cur
+
+
+@pytest.mark.parametrize('bsz,t,h', [(3, 5, 32), (8, 40, 64), (64, 33, 1024), (100, 9, 256), (130, 6, 64)])
+def test_gru_forward(ops, bsz, t, h):
+    gi = rnd(bsz, t, 3 * h).to(BF16)
+    w_hh = rnd(3 * h, h, scale=1 / math.sqrt(h), seed=1).to(BF16)
+    b_hh = rnd(3 * h, scale=0.1, seed=2)
+    h0 = rnd(bsz, h, scale=0.5, seed=3)
+    h_ext = torch.zeros(bsz, t + 1, h, dtype=BF16, device='cuda')
+    h_ext[:, 0] = h0.to(BF16)
+    h_state = h0.clone()
+    gates = torch.empty(bsz * t, 4 * h, dtype=BF16, device='cuda')
+    ops.gru_forward(gi.view(bsz * t, 3 * h), w_hh, b_hh, h_ext, h_state, gates, bsz, t, h)
+    hs, gref, hT = _gru_ref(gi.float(), w_hh, b_hh, h0)
+    assert float((h_ext[:, 1:].float() - hs).abs().max()) < 2e-2       # bf16 storage of values in (-1,1)
+    assert float((h_state - hT).abs().max()) < 1e-2
+    assert float((gates.view(bsz, t, 4 * h).float() - gref).abs().max()) < 3e-2
+
+
+@pytest.mark.parametrize('bsz,t,h', [(3, 5, 32), (8, 40, 64), (64, 17, 1024), (100, 9, 256)])
+def test_gru_backward(ops, bsz, t, h):
+    gi = rnd(bsz, t, 3 * h).to(BF16)
+    w_hh = rnd(3 * h, h, scale=1 / math.sqrt(h), seed=1).to(BF16)
+    b_hh = rnd(3 * h, scale=0.1, seed=2)
+    h0 = rnd(bsz, h, scale=0.5, seed=3)
+    dh_out = rnd(bsz, t, h, scale=0.1, seed=4).to(BF16)
+    # fp32 autograd reference of the same recurrence
+    gi_r = gi.float().requires_grad_(True)
+    h0_r = h0.clone().requires_grad_(True)
+    cur, outs = h0_r, []
+    for s in range(t):
+        gh = cur @ w_hh.float().t() + b_hh
+        r = torch.sigmoid(gi_r[:, s, :h] + gh[:, :h])
+        z = torch.sigmoid(gi_r[:, s, h:2 * h] + gh[:, h:2 * h])
+        n = torch.tanh(gi_r[:, s, 2 * h:] + r * gh[:, 2 * h:])
+        cur = (1 - z) * n + z * cur
+        outs.append(cur)
+    (torch.stack(outs, 1) * dh_out.float()).sum().backward()
+    # kernel path
+    h_ext = torch.zeros(bsz, t + 1, h, dtype=BF16, device='cuda')
+    h_ext[:, 0] = h0.to(BF16)
+    h_state = h0.clone()
+    gates = torch.empty(bsz * t, 4 * h, dtype=BF16, device='cuda')
+    ops.gru_forward(gi.view(bsz * t, 3 * h), w_hh, b_hh, h_ext, h_state, gates, bsz, t, h)
+    dgi = torch.empty(bsz * t, 3 * h, dtype=BF16, device='cuda')
+    dgh = torch.empty(bsz * t, 3 * h, dtype=BF16, device='cuda')
+    dh0 = torch.empty(bsz, h, dtype=F32, device='cuda')
+    ops.gru_backward(w_hh.t().contiguous(), h_ext, gates, dh_out.view(bsz * t, h), dgi, dgh, dh0, bsz, t, h)
+    assert rel_l2(dgi.view(bsz, t, 3 * h), gi_r.grad) < 3e-2, rel_l2(dgi.view(bsz, t, 3 * h), gi_r.grad)
+    assert rel_l2(dh0, h0_r.grad) < 3e-2, rel_l2(dh0, h0_r.grad)
+
+
+# ------------------------------------------------------------------------------------------------
+# small kernels
+# ------------------------------------------------------------------------------------------------
+def test_weight_prep_and_backward(ops):
+    r, a, b = 48, 40, 4
+    v = rnd(r, a, b).requires_grad_(True)
+    g = (rnd(r, seed=1).abs() + 0.5).requires_grad_(True)
+    w_ref = O.weight_norm(g.view(r, 1, 1), v)
+    out1 = torch.empty(b * a, r, dtype=BF16, device='cuda')          # upsample layout [(j*A + o), i]
+    out2 = torch.empty(r, b * a, dtype=BF16, device='cuda')
+    inv = torch.empty(r, device='cuda')
+    ops.weight_prep(v.detach(), g.detach(), (r, a, b), out1, (1, r, a * r), out2, (b * a, 1, a), inv)
+    want = w_ref.detach().permute(2, 1, 0).reshape(b * a, r)
+    assert rel_l2(out1, want) < 4e-3 and rel_l2(out2, want.t()) < 4e-3
+    dw = rnd(b * a, r, seed=2)
+    (w_ref.permute(2, 1, 0).reshape(b * a, r) * dw).sum().backward()
+    dv, dg = ops.weight_prep_bwd(dw, (1, r, a * r), v.detach(), g.detach(), inv, (r, a, b))
+    assert rel_l2(dv, v.grad) < 1e-5 and rel_l2(dg, g.grad) < 1e-5
+    plain = torch.empty(r, a * b, dtype=BF16, device='cuda')
+    ops.weight_prep(v.detach(), None, (r, a * b, 1), plain, (a * b, 1, 0))
+    assert torch.equal(plain, v.detach().reshape(r, a * b).to(BF16))
+
+
+def test_colsum_repeat_cast(ops):
+    x = rnd(1000, 200).to(BF16)
+    assert rel_l2(ops.colsum(x, 1000, 200, 200), x.float().sum(0)) < 1e-5
+    src = rnd(30, 64).to(BF16)
+    out = torch.zeros(30 * 5, 192, dtype=BF16, device='cuda')
+    ops.repeat_rows(src, 30, 64, 64, 5, out[:, 64:], 192)
+    assert torch.equal(out[:, 64:128], src.repeat_interleave(5, 0)) and float(out[:, :64].abs().max()) == 0
+    back = torch.empty(30, 64, dtype=BF16, device='cuda')
+    ops.repeat_rows_bwd(out[:, 64:], 30, 64, 192, 5, back, 64)
+    assert rel_l2(back, 5 * src.float()) < 4e-3
+    f = rnd(17, 50)
+    padded = torch.empty(17, 56, dtype=BF16, device='cuda')
+    ops.pad_cast_bf16(f, 17, 50, 50, padded, 56, 56)
+    assert torch.equal(padded[:, :50], f.to(BF16)) and float(padded[:, 50:].abs().max()) == 0
+
+
+def test_tier_and_mixer_inputs(ops):
+    from samplernn_pase_b200.utils import SampleRNNQuantizer
+    q = SampleRNNQuantizer(True, 256)
+    bsz, l, c, fs, fs_top, rf = 3, 5, 50, 4, 16, 80
+    t = rf // fs
+    xq = torch.randint(0, 256, (bsz, rf + fs_top - 1), dtype=torch.uint8, device='cuda')
+    conds = rnd(bsz, l, c)
+    lut = q.lut('cuda')
+    kp = 56
+    out = ops.tier_input(xq, fs_top - fs, lut, None, conds, bsz, t, fs, kp)
+    frames = lut[xq[:, fs_top - fs: fs_top - fs + rf].long()].view(bsz, t, fs)
+    want = torch.cat([frames, conds.repeat_interleave(t // l, 1), torch.zeros(bsz, t, kp - fs - c, device='cuda')], 2)
+    assert torch.equal(out.view(bsz, t, kp), want.to(BF16))
+    out2 = ops.tier_input(None, 0, None, frames.contiguous(), conds, bsz, t, fs, kp)
+    assert torch.equal(out2, out)
+    dc = torch.zeros(bsz, l, c, device='cuda')
+    ops.tier_input_bwd(out, bsz, t, fs, l, c, kp, dc)
+    assert rel_l2(dc, out.view(bsz, l, t // l, kp)[..., fs:fs + c].float().sum(2)) < 1e-5
+    table = rnd(7, 15, seed=1)
+    spk = torch.tensor([3, 0, 6], dtype=torch.int32, device='cuda')
+    utt = rnd(bsz, l, 43, seed=2)
+    mix = ops.mixer_input(utt, table, spk, 64)
+    want = torch.cat([table[spk.long()][:, None].expand(bsz, l, 15), utt, torch.zeros(bsz, l, 6, device='cuda')], 2)
+    assert torch.equal(mix.view(bsz, l, 64), want.to(BF16))
+
+
+def test_state_select_and_masked_mean(ops):
+    bsz, h = 5, 64
+    carried, h0 = rnd(bsz, h), rnd(h, seed=1)
+    use = torch.tensor([1, 0, 1, 0, 0], dtype=torch.uint8, device='cuda')
+    hs = ops.state_select(carried, h0, use, bsz, h)
+    assert torch.equal(hs, torch.where(use.bool()[:, None], carried, h0[None].expand(bsz, h)))
+    dh = rnd(bsz, h, seed=2)
+    assert rel_l2(ops.state_select_bwd(dh, use, bsz, h), dh[~use.bool()].sum(0)) < 1e-6
+    lp = -rnd(5 * 40, seed=3).abs()
+    valid = torch.tensor([1, 1, 0, 1, 0], dtype=torch.uint8, device='cuda')
+    out = ops.masked_nll_mean(lp, valid, 40)
+    keep = valid.bool().repeat_interleave(40)
+    assert abs(float(out[0]) + float(lp[keep].mean())) < 1e-5 and int(out[1]) == 120
+
+
+def test_adam_clipped_matches_reference_golden(ops):
+    g = Golden('adam_clipped')
+    for key in 'ab':
+        w = g.t(f'w0_{key}').cuda().contiguous()
+        m, v = torch.zeros_like(w), torch.zeros_like(w)
+        for s in range(3):
+            ops.adam_clipped(w, g.t(f'g{s}_{key}').cuda().contiguous(), m, v, 1e-3, 0.9, 0.999, 1e-8, s + 1)
+        assert float((w.cpu() - g.t(f'w3_{key}')).abs().max()) < 1e-6
