@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""Benchmark of the teacher-forced SampleRNN training step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A *step* is one training step on one sequential-loader chunk: forward + NLL + backward
+(+ gradient all-reduce for N > 1) + AdamClipped.  The workload is BASELINE config 2: 3-tier
+SampleRNN GRU (ratios [4,4] = frame sizes 16/4, H=1024), 64 utterance slots per GPU x chunks of
+L=1000 frames (RF = 16 000 samples = 1 s of 16 kHz audio), hidden state carried across chunks; an
+8 s utterance batch is 8 consecutive steps.  Weak scaling: every rank owns 64 slots.
+
+Printed JSON (one line, rank 0):
+  value     audio samples/s over all GPUs, inputs already resident in HBM, no host sync per step
+  e2e       the same metric through the public module API with pinned HOST buffers: H2D copies of
+            x / y / conds and the D2H read of the loss are inside the timed region
+  roofline  the dominant kernel (comb_layer forward GEMM, tcgen05) timed live with CUDA events
+  cpu_baseline  the CPU oracle port timed on this box's host cores on a bounded sample
+
+``--impl reference`` times the reference's CPU path (the oracle port; the reference is pure Python
+and cannot travel to the GPU box) on the host cores with the same metric/unit.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RATIOS, LAYERS, HIDDEN = [4, 4], [1, 1], [1024, 1024]
+SLOTS_PER_GPU, SEQ_LEN = 64, 1000
+N_SPEAKERS = 126
+METRIC = 'teacher-forced training audio samples/sec'
+WORKLOAD = ('config2: 3-tier SampleRNN GRU ratios [4,4] H=1024, 64 slots/GPU x 1 s chunks (L=1000, RF=16000) '
+            'of 8 s utterances with hidden-state carry, acoustic conds U=43, 126 speakers')
+
+
+def model_kwargs(seq_len=SEQ_LEN):
+    return dict(conds_speaker_type='embedding', conds_speaker_n=N_SPEAKERS, conds_speaker_size=15,
+                conds_utterance_type='acoustic', conds_utterance_linguistic_n=[9, 5, 4, 3],
+                conds_utterance_linguistic_emb_size=10, conds_size=50, sequence_length=seq_len, ratios=RATIOS,
+                rnn_layers=LAYERS, rnn_hidden_size=HIDDEN, q_type_ulaw=True, q_levels=256)
+
+
+def flops_per_sample_fwd():
+    """dense model FLOPs of the reference arithmetic per audio sample."""
+    h, c, q = HIDDEN[0], 50, 256
+    r0 = RATIOS[0]
+    f = 2 * (r0 * q * h + c * h + 3 * h * h + h * h + h * q)
+    fs = 1
+    for n, r in enumerate(RATIOS):
+        fs *= r
+        f += (1.0 / fs) * 2 * (fs * h + c * h + LAYERS[n] * 2 * 3 * h * h + r * h * h)
+    return f
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port)
+# --------------------------------------------------------------------------------------------------
+def cpu_reference(steps, warmup, batch=8, seq_len=64):
+    from oracle import samplernn_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = O.ModelSpec(RATIOS, LAYERS, HIDDEN, seq_len)
+    params = O.init_params(spec, conds_speaker_n=N_SPEAKERS)
+    trainer = O.CpuTrainer(spec, params)
+    wav, conds, spk = O.synthetic_utterances(spec, batch, warmup + steps)
+    times = []
+    for k in range(warmup + steps):
+        x, y, c = O.chunk_of(spec, wav, conds, k)
+        t0 = time.perf_counter()
+        trainer.step(x, y, c, spk, [1] * batch if k == 0 else [0] * batch)
+        if k >= warmup:
+            times.append(time.perf_counter() - t0)
+    per_step = batch * spec.receptive_field
+    total = sum(times)
+    return dict(value=per_step * len(times) / total, ms_per_step=1e3 * total / len(times), cores=torch.get_num_threads(),
+                sample=f'oracle port (torch CPU fp32), same model, batch {batch} x L={seq_len} (RF={spec.receptive_field}) '
+                       f'chunks with carry, {len(times)} timed steps')
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    r = cpu_reference(max(1, min(args.steps, 6)), max(1, min(args.warmup, 2)))
+    line = dict(impl='reference', metric=METRIC, value=r['value'], unit='samples/s', n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f32', data='synthetic', config=dict(workload=WORKLOAD),
+                cpu_baseline=dict(value=r['value'], unit='samples/s', cores=r['cores'], kind='port', sample=r['sample']),
+                e2e=dict(value=r['value'], unit='samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.FIELDS}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        out = self.proc.communicate()[0]
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[2:6]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch.distributed as dist
+    from oracle import samplernn_oracle as O          # synthetic workload generator + cpu_baseline leg only
+    from samplernn_pase_b200 import SampleRNNModel, ops
+    from samplernn_pase_b200.parallel import DataParallelTrainer
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run for N > 1')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    torch.manual_seed(1234)
+    model = SampleRNNModel(fused_loss=True, **model_kwargs()).to(dev)
+    trainer = DataParallelTrainer(model, lr=1e-4)
+    spec = O.ModelSpec(RATIOS, LAYERS, HIDDEN, SEQ_LEN)
+    b = SLOTS_PER_GPU
+    chunks = 8
+    wav, conds, spk = O.synthetic_utterances(spec, b, chunks, seed=4321 + rank)
+    info = [{'speaker': {'index': int(s)}} for s in spk]
+    host = []
+    for k in range(chunks):
+        x, y, c = O.chunk_of(spec, wav, conds, k)
+        host.append((x.pin_memory(), y.pin_memory(), c.pin_memory()))
+    resident = [tuple(t.to(dev) for t in h) for h in host]
+    resets = [torch.ones(b, dtype=torch.int64), torch.zeros(b, dtype=torch.int64)]
+    rf = spec.receptive_field
+    global_rows = b * rf * world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def loop(n_steps, e2e, first):
+        last = None
+        for s in range(first, first + n_steps):
+            k = s % chunks
+            reset = resets[0] if k == 0 else resets[1]
+            if e2e:
+                x, y, c = (t.to(dev, non_blocking=True) for t in host[k])
+                loss, _ = trainer.step(x, y, c, info, reset)            # reads the loss back (D2H)
+                last = loss
+            else:
+                x, y, c = resident[k]
+                last, _ = trainer.step(x, y, c, info, reset, global_count=global_rows)
+        return last
+
+    def timed(n_steps, e2e, first):
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        last = loop(n_steps, e2e, first)
+        t1.record()
+        barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), float(last)
+
+    loop(args.warmup, False, 0)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ops.launch_count = 0
+    ops.event_log = {}
+    ms, loss = timed(args.steps, False, args.warmup)
+    launches = ops.launch_count
+    events = ops.event_log
+    ops.event_log = None
+    clocks = sampler.stop() if sampler else None
+    kernel_ms = [a.elapsed_time(b_) for a, b_ in events.get('comb_layer_fwd', [])]
+    loop(1, True, args.warmup + args.steps)
+    ms_e2e, loss_e2e = timed(args.steps, True, args.warmup + args.steps + 1)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except OSError:
+            pass
+        peak = peaks.get('bf16_tflops_sustained', 1400.0)
+        m_rows, h = b * rf, HIDDEN[0]
+        gemm_flops = 2.0 * m_rows * h * 3 * h                     # comb_layer forward: (B*RF, 3H) x (3H, H)
+        avg_ms = sum(kernel_ms) / max(len(kernel_ms), 1)
+        achieved = gemm_flops / (avg_ms * 1e-3) / 1e12 if avg_ms else None
+        total = args.steps * global_rows
+        f_fwd = flops_per_sample_fwd()
+        cpu = cpu_reference(3, 1)
+        line = dict(
+            metric=METRIC, value=total / (ms * 1e-3), unit='samples/s', n_gpus=world, steps=args.steps,
+            warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+            dtype='bf16', data='synthetic',
+            config=dict(workload=WORKLOAD, slots_per_gpu=b, samples_per_step_per_gpu=b * rf, parallelism=f'dp{world}',
+                        l2_policy='inputs and activations per step (>10 GB) exceed the 126 MB L2; no flush needed',
+                        loss_mode='fused log-softmax+NLL epilogue', final_loss=loss,
+                        model_train_mflop_per_sample=3 * f_fwd / 1e6,
+                        model_tflops_achieved=3 * f_fwd * total / (ms * 1e-3) / 1e12),
+            clocks=clocks,
+            e2e=dict(value=total / (ms_e2e * 1e-3), unit='samples/s', ms_per_step=ms_e2e / args.steps,
+                     h2d_bytes_per_step=sum(t.numel() * t.element_size() for t in host[0]), d2h_bytes_per_step=8,
+                     final_loss=loss_e2e),
+            gpu_launches=launches,
+            roofline=dict(bound='tensor', kernel='gemm_kernel<256,NT,epilogue bias+relu> (comb_layer forward, tcgen05)',
+                          achieved=achieved, peak=peak, unit='TFLOP/s', frac=(achieved / peak) if achieved else None,
+                          traffic=None, launches_timed=len(kernel_ms), avg_launch_ms=avg_ms,
+                          peak_source='MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
+                          if peaks else 'fallback'),
+            cpu_baseline=dict(value=cpu['value'], unit='samples/s', cores=cpu['cores'], kind='port', sample=cpu['sample']),
+        )
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -127,9 +127,22 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+#: when a list, every C call is bracketed with CUDA events: (name, note, start, end) tuples are appended
+#: (scripts/profile_step.py); None in normal operation.
+profile_log = None
+profile_note = ''
+
+
 def call(name, *args):
     lib = load()
+    if profile_log is None:
+        check(getattr(lib, name)(*args), name)
+        return
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
     check(getattr(lib, name)(*args), name)
+    end.record()
+    profile_log.append((name, profile_note, start, end))
 
 
 def device_info():

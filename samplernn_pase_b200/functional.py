@@ -264,7 +264,8 @@ class SampleLevelFn(torch.autograd.Function):
         wcomb_t = _empty(3 * h, h, device=dev)
         ops.weight_prep(cw.contiguous(), None, (h, 3 * h, 1), wcomb, (3 * h, 1, 0), wcomb_t, (1, h, 0))
         h1 = _empty(m, h, device=dev)
-        ops.gemm_nt(cat, wcomb, h1, m, h, 3 * h, 3 * h, 3 * h, h, bias=cbias.contiguous(), relu=True)
+        with ops.timed('comb_layer_fwd'):
+            ops.gemm_nt(cat, wcomb, h1, m, h, 3 * h, 3 * h, 3 * h, h, bias=cbias.contiguous(), relu=True)
         w2 = _empty(h, h, device=dev)
         w2_t = _empty(h, h, device=dev)
         inv_2 = _empty(h, dtype=F32, device=dev)

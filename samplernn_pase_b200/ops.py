@@ -23,6 +23,29 @@ def _count(n=1):
     launch_count += n
 
 
+#: when a dict, ``timed(tag)`` brackets the enclosed launches with CUDA events on the current stream
+#: and appends (start, end) to ``event_log[tag]``; bench.py reads them after the timed region.
+event_log = None
+
+
+class timed:
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if event_log is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.end = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if event_log is not None:
+            self.end.record()
+            event_log.setdefault(self.tag, []).append((self.start, self.end))
+        return False
+
+
 def round_up(x, m):
     return (x + m - 1) // m * m
 
@@ -196,6 +219,7 @@ def gemm_nt(a, b, c, m, n, k, lda, ldb, ldc, batch=1, a_bs=0, c_bs=0, bias=None,
     g.aux = aux.data_ptr() if aux is not None else None
     g.ldaux, g.aux_batch_stride, g.aux_mode = ldaux, aux_bs, aux_mode if aux is not None else 0
     g.relu = int(relu)
+    _lib.profile_note = f'NT m={m}x{batch} n={n} k={k}'
     call('srnn_gemm_bf16', C.byref(g), stream())
     _count()
     return c
@@ -212,6 +236,7 @@ def gemm_tn(a, b, c, m, n, k, lda, ldb, ldc, batch=1, a_bs=0, b_bs=0, a_off=0, b
     g.b, g.ldb, g.b_batch_stride, g.b_row_offset = b.data_ptr(), ldb, b_bs, b_off
     g.c, g.ldc, g.c_batch_stride = c.data_ptr(), ldc, 0
     g.c_dtype = 1
+    _lib.profile_note = f'TN m={m} n={n} k={k}x{batch}'
     call('srnn_gemm_bf16', C.byref(g), stream())
     _count()
     return c
@@ -230,6 +255,7 @@ def gemm_nll(mode, a, w, bias, target, m, k, lda, ldw, lse=None, logp_target=Non
     n.row_grad = row_grad.data_ptr() if row_grad is not None else None
     n.g, n.ldg = (g.data_ptr(), 256) if g is not None else (None, 0)
     n.dlogits, n.lddlogits = (dlogits.data_ptr(), 256) if dlogits is not None else (None, 0)
+    _lib.profile_note = f'NLL mode={mode} m={m} k={k}'
     call('srnn_gemm_nll', C.byref(n), stream())
     _count()
 
@@ -253,6 +279,7 @@ def _gru_call(name, batch, steps, hidden, **bufs):
                 setattr(a, key, t.data_ptr() + b0 * per_row * t.element_size())
         sync = torch.zeros(64, dtype=torch.int32, device=bufs['h_ext'][0].device)
         a.sync = sync.data_ptr()
+        _lib.profile_note = f'B={nb} T={steps} H={hidden}'
         call(name, C.byref(a), stream())
         _count(2)
 

@@ -127,8 +127,12 @@ class DataParallelTrainer:
         self._finish_reduce()
         return stats
 
-    def step(self, x, y, utt_conds, info, reset):
-        """One training step on this rank's slots.  Returns (global mean NLL, global valid rows)."""
+    def step(self, x, y, utt_conds, info, reset, global_count=None):
+        """One training step on this rank's slots.  Returns (global mean NLL, global valid rows).
+
+        ``global_count``: the number of valid target rows over ALL ranks when the caller already knows
+        it (e.g. no empty slots); the step then needs no device->host read and the returned loss is a
+        device tensor.  Otherwise the (sum, count) pair is all-reduced and read back."""
         from . import ops
         self._begin()
         self.flat.zero_grad()
@@ -140,8 +144,13 @@ class DataParallelTrainer:
         if self.world > 1:
             dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)
         self._finish_reduce()
-        total, count = stats.tolist()
         self.steps += 1
+        if global_count is None:
+            total, count = stats.tolist()
+            loss = total / max(count, 1.0)
+        else:
+            count = float(global_count)
+            loss = stats[0] / count
         ops.adam_clipped(self.flat.flat_param, self.flat.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr,
                          self.betas[0], self.betas[1], self.eps, self.steps, grad_scale=1.0 / max(count, 1.0))
-        return total / max(count, 1.0), int(count)
+        return loss, int(count)

@@ -1,12 +1,16 @@
 """End-to-end parity of the CUDA path (through the C ABI, behind the reference's module API)
 against the golden vectors produced by the reference itself and against the CPU oracle.
 
-Tolerances (bf16 operands / fp32 accumulate; SURVEY.md 8(d) calibrated the reference's own
-bf16-autocast noise at: loss rel 7.9e-5, worst per-tensor gradient rel-L2 8.2e-2, min cosine 0.9967):
+Tolerances (bf16 operands / fp32 accumulate).  Calibration: the reference's OWN noise when it is run
+under torch bf16 autocast on exactly these golden inputs (tests/golden/calibrate_bf16.py, H=32, 48-160
+target rows, loss ~ ln 256 so gradients are small differences): loss rel up to 5.8e-4, max |dlogp|
+3.8e-2, worst per-tensor gradient rel-L2 0.09-0.13 (cos 0.992); SURVEY.md 8(d) measured 8.2e-2 / 0.9967
+at H=1024.  The bounds below are ~1.5x that noise per tensor and tighter than it everywhere else:
   * quantised targets: bit-exact;
-  * log-probabilities: max |diff| <= 0.08 nat;   loss: rel <= 5e-3;
-  * every parameter gradient: rel-L2 <= 0.12 and cosine >= 0.993 (tensors whose reference norm is
-    below 1e-7 of the largest gradient are compared in absolute terms);
+  * log-probabilities: max |diff| <= 0.04 nat;   loss: rel <= 5e-4;
+  * every parameter gradient: rel-L2 <= 0.2 and cosine >= 0.98 (tensors whose reference norm is below
+    1e-7 of the largest gradient are compared in absolute terms);
+  * all gradients concatenated: rel-L2 <= 0.1 and cosine >= 0.995;
   * carried hidden state: max |diff| <= 3e-2.
 """
 import os
@@ -62,8 +66,8 @@ def test_forward_backward_vs_reference_golden(name):
         loss = torch.nn.functional.nll_loss(y_hat.view(-1, y_hat.size(2)), yq.view(-1))
         rel = abs(float(loss) - float(c['loss'])) / abs(float(c['loss']))
         report(f'{name} chunk {k}: max|dlogp| {d:.3e}  loss {float(loss):.6f} ref {float(c["loss"]):.6f} rel {rel:.2e}')
-        assert d <= 0.08, d
-        assert rel <= 5e-3, rel
+        assert d <= 0.04, d
+        assert rel <= 5e-4, rel
         for n in range(len(model.frames_layers)):
             ref = c[f'state.{n}']
             ok = ~torch.isnan(ref)
@@ -73,15 +77,20 @@ def test_forward_backward_vs_reference_golden(name):
         if 'grad.' + next(iter(params)) in c:
             loss.backward()
             gmax = max(float(c['grad.' + pn].norm()) for pn in params)
+            all_got, all_ref = [], []
             for pn, p in params.items():
                 ref = c['grad.' + pn]
                 got = p.grad.detach().cpu() if p.grad is not None else torch.zeros_like(ref)
+                all_got.append(got.flatten()); all_ref.append(ref.flatten())
                 if float(ref.norm()) < 1e-7 * gmax:
                     assert float(got.norm()) <= 1e-4 * gmax, pn
                     continue
                 r, cs = rel_l2(got, ref), cosine(got, ref)
                 report(f'{name} chunk {k} grad {pn}: rel_l2 {r:.3e} cos {cs:.6f}')
-                assert r <= 0.12 and cs >= 0.993, (pn, r, cs)
+                assert r <= 0.2 and cs >= 0.98, (pn, r, cs)
+            r, cs = rel_l2(torch.cat(all_got), torch.cat(all_ref)), cosine(torch.cat(all_got), torch.cat(all_ref))
+            report(f'{name} chunk {k} ALL GRADS: rel_l2 {r:.3e} cos {cs:.6f}')
+            assert r <= 0.1 and cs >= 0.995, (r, cs)
 
 
 def test_fused_loss_mode_gives_the_same_scalar_and_gradients():
@@ -133,6 +142,33 @@ def test_layer_level_api_matches_oracle():
     lp = model.sample_layer(xs.cuda(), conds_ref.cuda(), upper.cuda())
     assert lp.shape == lp_ref.shape and float((lp.cpu() - lp_ref).abs().max()) < 0.08
     assert float(torch.logsumexp(lp, 2).abs().max()) < 1e-4                     # rows are normalised
+
+
+def test_medium_size_vs_cpu_oracle():
+    """More rows (2048) and H=256: the bf16 noise averages down; checked against the fp32 CPU oracle."""
+    from samplernn_pase_b200 import SampleRNNModel
+    spec = O.ModelSpec([4, 4], [1, 1], [256, 256], 16)
+    params = O.init_params(spec, conds_speaker_n=9, perturb=0.1)
+    model = SampleRNNModel('embedding', 9, 15, 'acoustic', [9, 5, 4, 3], 10, 50, 16, [4, 4], [1, 1], [256, 256], True,
+                           256).cuda()
+    model.load_state_dict(params)
+    wav, conds, spk = O.synthetic_utterances(spec, 8, 1, n_speakers=9)
+    x, y, c = O.chunk_of(spec, wav, conds, 0)
+    info = [{'speaker': {'index': int(s)}} for s in spk]
+    y_hat, yq = model(x.cuda(), y.cuda(), c.cuda(), info, torch.ones(8, dtype=torch.int64))
+    loss = torch.nn.functional.nll_loss(y_hat.view(-1, 256), yq.view(-1))
+    loss.backward()
+    p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    logp, tgt, _, _ = O.forward(p_ref, spec, x, y, c, spk, [1] * 8, fast=True)
+    ref_loss = O.nll(logp, tgt)
+    ref_loss.backward()
+    assert torch.equal(yq.cpu(), tgt)
+    assert abs(float(loss) - float(ref_loss)) <= 5e-4 * float(ref_loss)
+    got = torch.cat([p.grad.flatten().cpu() for _, p in model.named_parameters()])
+    ref = torch.cat([p_ref[n].grad.flatten() for n, _ in model.named_parameters()])
+    r, cs = rel_l2(got, ref), cosine(got, ref)
+    report(f'medium H=256 B=8 L=16: loss {float(loss):.6f} ref {float(ref_loss):.6f}; ALL GRADS rel_l2 {r:.3e} cos {cs:.6f}')
+    assert r <= 0.08 and cs >= 0.997, (r, cs)
 
 
 def test_chunked_equals_unchunked_with_carry():
