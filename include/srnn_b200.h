@@ -165,18 +165,27 @@ int srnn_gemm_nll(const srnn_nll_args* args, srnn_stream_t stream);
  * ------------------------------------------------------------------------------------------- */
 typedef struct srnn_gru_args {
   int32_t batch, steps, hidden;   /* batch <= 128, hidden % 8 == 0 */
-  const void* gi;        /* bf16 [batch*steps, 3H] = W_ih u_t + b_ih, row (b,t) = b*steps + t */
+  int32_t ext_batch;     /* rows per time slot of the TIME-major buffers (>= batch; a launch may cover a
+                            sub-range of a larger batch: pass pointers offset to its first row) */
+  const void* gi;        /* bf16 [batch*steps, 3H] = W_ih u_t + b_ih, batch-major: row (b,t) = b*steps + t */
   const void* w_hh;      /* fwd: bf16 [3H, H];  bwd: bf16 [H, 3H] (= W_hh^T) */
   const float* b_hh;     /* [3H] (fwd) */
-  void* h_ext;           /* bf16 [batch, steps+1, H]: slot 0 holds h_init (input), slot t+1 receives h_t */
+  void* h_ext;           /* bf16 [steps+1, ext_batch, H] TIME-major exchange buffer: slot 0 holds h_init
+                            (input), slot t+1 receives h_t.  One timestep is one dense block, which is what
+                            every CTA re-reads through TMA each step. */
+  void* hall;            /* fwd out (nullable): bf16 [batch*steps, H] batch-major copy of h_t (GEMM operand) */
   float* h_state;        /* fwd: fp32 [batch, H], in = h_init, out = h_T */
-  void* gates;           /* bf16 [batch*steps, 4H]: r, z, n, (W_hn h + b_hn) saved by fwd / read by bwd */
+  void* gates;           /* bf16 [batch*steps, 4H] batch-major: r, z, n, (W_hn h + b_hn); fwd writes, bwd reads */
   /* backward only */
-  const void* dh_out;    /* bf16 [batch*steps, H] : dL/dh_t from the layers above */
-  void* dgi;             /* bf16 [batch*steps, 3H] out */
-  void* dgh;             /* bf16 [batch, steps, 3H] out (also the per-step exchange buffer) */
+  const void* dh_out;    /* bf16 [batch*steps, H] batch-major: dL/dh_t from the layers above */
+  void* dgi;             /* bf16 [batch*steps, 3H] batch-major, out */
+  void* dgh;             /* bf16 [steps, ext_batch, 3H] TIME-major, out (also the per-step exchange buffer) */
   float* dh0;            /* fp32 [batch, H] out: dL/dh_init */
-  uint32_t* sync;        /* >= 256 bytes, zeroed by the caller before every launch */
+  uint32_t* sync;        /* >= 4*(hidden/8) bytes (one flag per CTA), zeroed by the caller before every launch */
+  int32_t debug_flags;   /* must be 0.  Timing experiments only (results are WRONG when set):
+                            1 = do not wait on the grid counter, 2 = skip TMA loads and MMAs,
+                            4 = skip the per-step global loads/stores of the epilogue */
+  uint64_t* debug_ts;    /* NULL, or [256][8] clock64 stamps of CTA 0's pipeline events (profiling aid) */
 } srnn_gru_args;
 
 int srnn_gru_forward(const srnn_gru_args* args, srnn_stream_t stream);

@@ -43,11 +43,11 @@ class NllArgs(C.Structure):
 
 class GruArgs(C.Structure):
     _fields_ = [
-        ('batch', C.c_int32), ('steps', C.c_int32), ('hidden', C.c_int32),
+        ('batch', C.c_int32), ('steps', C.c_int32), ('hidden', C.c_int32), ('ext_batch', C.c_int32),
         ('gi', C.c_void_p), ('w_hh', C.c_void_p), ('b_hh', C.c_void_p),
-        ('h_ext', C.c_void_p), ('h_state', C.c_void_p), ('gates', C.c_void_p),
+        ('h_ext', C.c_void_p), ('hall', C.c_void_p), ('h_state', C.c_void_p), ('gates', C.c_void_p),
         ('dh_out', C.c_void_p), ('dgi', C.c_void_p), ('dgh', C.c_void_p), ('dh0', C.c_void_p),
-        ('sync', C.c_void_p),
+        ('sync', C.c_void_p), ('debug_flags', C.c_int32), ('debug_ts', C.c_void_p),
     ]
 
 

@@ -335,34 +335,48 @@ __global__ void repeat_rows_bwd_kernel(const __nv_bfloat16* __restrict__ dout, l
   reinterpret_cast<uint4*>(din + irow * ld_din)[seg] = o;
 }
 
-// column sums: block (64, 4) covers 128 columns x one row slab; fp32 atomics into a zeroed vector
-__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ in, long long rows, int cols, long long ld,
-                              long long rows_per_block, float* __restrict__ out) {
-  __shared__ float s[4][128];
-  const int c = blockIdx.x * 128 + threadIdx.x * 2;
+// column sums: block (32, 8) covers 256 columns x one row slab; every thread keeps 4 independent
+// 16-byte loads in flight; fp32 atomics into a zeroed vector
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ in, long long rows, int cols, long long ld, long long rows_per_block,
+              float* __restrict__ out) {
+  __shared__ float s[8][257];
+  const int c = blockIdx.x * 256 + threadIdx.x * 8;
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
-  float a0 = 0.f, a1 = 0.f;
-  if (c < cols) {
-    for (long long r = r0 + threadIdx.y; r < r1; r += 4) {
-      if (c + 1 < cols) {
-        const uint32_t u = *reinterpret_cast<const uint32_t*>(in + r * ld + c);
-        a0 += bf16_lo(u);
-        a1 += bf16_hi(u);
-      } else {
-        a0 += __bfloat162float(in[r * ld + c]);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const bool vec = (c + 8 <= cols) && ((ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  if (vec) {
+    for (long long r = r0 + threadIdx.y; r < r1; r += 32) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + u * 8;
+        v[u] = rr < r1 ? __ldg(reinterpret_cast<const uint4*>(in + rr * ld + c)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[0] += bf16_lo(v[u].x); acc[1] += bf16_hi(v[u].x);
+        acc[2] += bf16_lo(v[u].y); acc[3] += bf16_hi(v[u].y);
+        acc[4] += bf16_lo(v[u].z); acc[5] += bf16_hi(v[u].z);
+        acc[6] += bf16_lo(v[u].w); acc[7] += bf16_hi(v[u].w);
       }
     }
+  } else if (c < cols) {
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8)
+      for (int j = 0; j < 8; ++j)
+        if (c + j < cols) acc[j] += __bfloat162float(in[r * ld + c + j]);
   }
-  s[threadIdx.y][threadIdx.x * 2] = a0;
-  s[threadIdx.y][threadIdx.x * 2 + 1] = a1;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[threadIdx.y][threadIdx.x * 8 + j] = acc[j];
   __syncthreads();
-  if (threadIdx.y == 0) {
-    for (int j = 0; j < 2; ++j) {
-      const int cc = threadIdx.x * 2 + j;
-      if (blockIdx.x * 128 + cc < cols)
-        atomicAdd(out + blockIdx.x * 128 + cc, s[0][cc] + s[1][cc] + s[2][cc] + s[3][cc]);
-    }
+  const int t = threadIdx.y * 32 + threadIdx.x;      // 256 threads -> 256 columns
+  const int cc = blockIdx.x * 256 + t;
+  if (cc < cols) {
+    float v = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) v += s[y][t];
+    atomicAdd(out + cc, v);
   }
 }
 
@@ -577,14 +591,14 @@ extern "C" int srnn_repeat_rows_bwd(const void* dout, int64_t rows, int32_t cols
 }
 
 extern "C" int srnn_colsum(const void* in, int64_t rows, int32_t cols, int64_t ld, float* out, srnn_stream_t s) {
-  SRNN_CHECK_ARG(in && out && rows > 0 && cols > 0 && ld % 2 == 0, "colsum: bad arguments");
+  SRNN_CHECK_ARG(in && out && rows > 0 && cols > 0, "colsum: bad arguments");
   SRNN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, ST(s)));
-  const int col_blocks = (cols + 127) / 128;
-  long long slabs = (2LL * sm_count() + col_blocks - 1) / col_blocks;
-  if (slabs > (rows + 63) / 64) slabs = (rows + 63) / 64;
+  const int col_blocks = (cols + 255) / 256;
+  long long slabs = (8LL * sm_count() + col_blocks - 1) / col_blocks;
+  if (slabs > (rows + 127) / 128) slabs = (rows + 127) / 128;
   if (slabs < 1) slabs = 1;
   const long long rpb = (rows + slabs - 1) / slabs;
-  colsum_kernel<<<dim3(col_blocks, static_cast<unsigned>(slabs)), dim3(64, 4), 0, ST(s)>>>(
+  colsum_kernel<<<dim3(col_blocks, static_cast<unsigned>(slabs)), dim3(32, 8), 0, ST(s)>>>(
       static_cast<const __nv_bfloat16*>(in), rows, cols, ld, rpb, out);
   SRNN_CUDA(cudaGetLastError());
   return SRNN_OK;

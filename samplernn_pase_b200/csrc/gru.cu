@@ -1,28 +1,45 @@
 // Persistent recurrent GRU kernels for sm_100a (replace torch.nn.GRU, model.py:110,152, and its
 // autograd backward).
 //
-// One cooperative launch runs all T timesteps of a tier.  The hidden units are partitioned over
-// G = H/U CTAs; each CTA keeps its slice of W_hh (forward: the 3U gate rows of its U units;
-// backward: its U rows of W_hh^T) resident in shared memory for the whole launch, in the
-// 128-byte-swizzled K-major layout tcgen05 consumes.  Per timestep every CTA
-//   1. waits on a grid-wide arrival counter (release/acquire through L2) for h_{t-1} (resp. the
-//      gate gradients of step t+1) of all CTAs,
-//   2. streams that [batch, K] bf16 matrix through a TMA ring and multiplies it against the
-//      resident weight slice with tcgen05.mma (M = 64 or 128 batch rows, fp32 accumulate in TMEM),
-//   3. finishes the gate math in the epilogue warps (fp32), writes its U columns of h_t (bf16
-//      exchange copy + saved gates) and arrives on the counter.
-// The fp32 recurrent state of a unit never leaves the registers of its owner thread.
+// One cooperative launch runs all T timesteps of a tier; the recurrent weights never leave shared
+// memory.  Work decomposition (H hidden units, batch rows M <= 64, K = H forward / 3H backward):
+//
+//   * the grid is H/8 CTAs grouped into thread-block clusters of C (1, 2, 4 or 8) CTAs;
+//   * a cluster owns 8*C hidden units: forward its 3*8*C gate rows of W_hh, backward its 8*C rows of
+//     W_hh^T.  Inside the cluster the reduction dimension is SPLIT: CTA rank c keeps only the K/C
+//     slice [c*K/C, (c+1)*K/C) of those rows resident (<= 48 KB, 128-byte-swizzled K-major tiles);
+//   * per timestep each CTA (1) waits on a grid-wide arrival counter (release/acquire through L2)
+//     until every CTA has published its part of h_{t-1} (backward: of the gate gradients of step
+//     t+1), (2) TMA-loads only its K slice of that [batch, K] matrix (one mbarrier, K/(64 C) boxes),
+//     (3) multiplies it with tcgen05.mma (M=64, N=8C*{3,1}, fp32 partial sums in TMEM), (4) parks the
+//     partial tile in its own shared memory, (5) after a cluster-scope mbarrier handshake sums the C
+//     partial tiles of ITS 8 units through distributed shared memory, finishes the gate math in
+//     fp32, writes its 8 columns of h_t and arrives on the grid counter.
+//
+// Why this shape (measured on B200, B=64, H=1024): with one CTA per 8 units doing the
+// whole K loop alone a step cost 8-18 us, almost all of it single-thread issue latency (64-192 tiny
+// MMAs + 16-48 TMA/mbarrier handshakes per step) - the tensor pipe was 5 % busy and L2 was 5 % busy.
+// Splitting K across the cluster divides MMAs, TMA boxes and L2->SM ingest per CTA by C at the price
+// of one cluster handshake and C*24 DSMEM loads per thread.
+//
+// The fp32 recurrent state of a unit never leaves the registers of its owner thread; the exchange
+// buffers are TIME-major so one step's matrix is one dense block.
 #include "common.cuh"
 
 namespace srnn {
 
 constexpr int GRU_THREADS = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int GRU_U = 8;           // hidden units finalised per CTA
+constexpr int GRU_M = 64;          // batch rows per launch (MMA M)
+constexpr int GRU_SLOT = GRU_M * 128;   // one [64 rows][64 bf16] K block
 
 struct GruParams {
-  int batch, steps, hidden, kblocks, ctas;
+  int batch, steps, hidden, ext_batch;
+  int kbc;                         // K blocks (of 64) per CTA
   const __nv_bfloat16* gi;
   const float* b_hh;
   __nv_bfloat16* h_ext;
+  __nv_bfloat16* hall;
   float* h_state;
   __nv_bfloat16* gates;
   const __nv_bfloat16* dh_out;
@@ -30,106 +47,147 @@ struct GruParams {
   __nv_bfloat16* dgh;
   float* dh0;
   uint32_t* sync;
+  int flags;
+  unsigned long long* ts;          // debug timestamps [256][8] of CTA 0 (nullable)
 };
 
-template <int MT>
-struct GruCfg {
-  static constexpr int U = MT == 64 ? 8 : 16;          // hidden units per CTA
-  static constexpr int RING = MT == 64 ? 8 : 4;         // TMA ring stages
-  static constexpr int SLOT_BYTES = MT * 128;           // [MT rows][64 bf16]
-};
+#define GRU_TS(slot_, step_)                                                                 \
+  do {                                                                                       \
+    if (p.ts && blockIdx.x == 0 && (step_) < 256) p.ts[(step_) * 8 + (slot_)] = clock64();   \
+  } while (0)
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// MUFU approximations (max relative error 2^-11, below the bf16 rounding of the matmul operand)
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
-template <int U>
-__device__ __forceinline__ void load_bf16_vec(const __nv_bfloat16* p, float (&out)[U]) {
-#pragma unroll
-  for (int i = 0; i < U / 8; ++i) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p + i * 8);
-    out[i * 8 + 0] = bf16_lo(u.x); out[i * 8 + 1] = bf16_hi(u.x);
-    out[i * 8 + 2] = bf16_lo(u.y); out[i * 8 + 3] = bf16_hi(u.y);
-    out[i * 8 + 4] = bf16_lo(u.z); out[i * 8 + 5] = bf16_hi(u.z);
-    out[i * 8 + 6] = bf16_lo(u.w); out[i * 8 + 7] = bf16_hi(u.w);
-  }
+__device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* p, float (&out)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  out[0] = bf16_lo(u.x); out[1] = bf16_hi(u.x);
+  out[2] = bf16_lo(u.y); out[3] = bf16_hi(u.y);
+  out[4] = bf16_lo(u.z); out[5] = bf16_hi(u.z);
+  out[6] = bf16_lo(u.w); out[7] = bf16_hi(u.w);
 }
-template <int U>
-__device__ __forceinline__ void store_bf16_vec(__nv_bfloat16* p, const float (&v)[U]) {
-#pragma unroll
-  for (int i = 0; i < U / 8; ++i) {
-    uint4 u;
-    u.x = pack_bf16x2(v[i * 8 + 0], v[i * 8 + 1]);
-    u.y = pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
-    u.z = pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]);
-    u.w = pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7]);
-    *reinterpret_cast<uint4*>(p + i * 8) = u;
-  }
-}
-template <int U>
-__device__ __forceinline__ void tmem_ld_units(uint32_t taddr, float (&out)[U]) {
-  if constexpr (U == 8) {
-    uint32_t v[8];
-    tmem_ld8(taddr, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) out[i] = __uint_as_float(v[i]);
-  } else {
-    uint32_t v[16];
-    tmem_ld16(taddr, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 16; ++i) out[i] = __uint_as_float(v[i]);
-  }
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
 }
 
-__device__ __forceinline__ void grid_wait(const uint32_t* counter, uint32_t target) {
+// Grid-wide exchange handshake: one arrival counter in L2; each CTA adds 1 (release) per published
+// timestep and the TMA warp polls it (a per-CTA flag array polled lane-parallel was measured 2.5x
+// slower: 9 000 vs 3 500 cycles from publish to release).
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void grid_wait(const uint32_t* counter, uint32_t target, bool acquire_fence) {
   uint32_t spins = 0;
-  while (ld_acquire_gpu(counter) < target) {
+  while (ld_relaxed_gpu(counter) < target) {
     if (++spins > (1u << 24)) __trap();
   }
+  // acquire pattern = relaxed polling + ONE fence (an acquire load per iteration costs a gpu-scope
+  // fence and an L1 invalidation every time round the loop)
+  if (acquire_fence) asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
-// NG = number of gate row-groups resident per CTA (3 forward: r,z,n rows of W_hh; 1 backward: rows of W_hh^T)
-template <int MT, bool BWD>
+// ---- cluster / distributed shared memory helpers ------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t remote_bar_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 26)) __trap();
+  }
+  fence_acq_rel_cluster();                           // one acquire fence after the relaxed polling
+}
+
+template <bool BWD, int C>
 __global__ void __launch_bounds__(GRU_THREADS, 1)
 gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_x, const GruParams p) {
-  using Cfg = GruCfg<MT>;
-  constexpr int U = Cfg::U;
+  constexpr int U = GRU_U;
+  constexpr int UC = U * C;                          // units owned by the cluster
   constexpr int NG = BWD ? 1 : 3;
-  constexpr int NCOLS = NG * U;                      // MMA N
-  constexpr uint32_t TMEM_COLS = NCOLS <= 32 ? 32 : 64;
-  constexpr uint32_t IDESC = idesc_bf16(MT, NCOLS, false, false);
-  constexpr int RING = Cfg::RING;
+  constexpr int NCOLS = NG * UC;                     // MMA N
+  constexpr int NCH = (NCOLS + 31) / 32;             // 32-column TMEM load chunks
+  constexpr uint32_t TMEM_COLS = NCOLS <= 32 ? 32 : (NCOLS <= 64 ? 64 : (NCOLS <= 128 ? 128 : 256));
+  constexpr uint32_t IDESC = idesc_bf16(GRU_M, NCOLS, false, false);
+  constexpr int WBLOCK = NCOLS * 128;                // resident weight bytes per K block
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int KB = p.kblocks;                          // K blocks of 64 (K = H forward, 3H backward)
-  const int wblock = NCOLS * 128;                    // bytes of the resident weight per K block
-  uint8_t* sw = smem;
-  uint8_t* ring = smem + ((KB * wblock + 1023) & ~1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + RING * Cfg::SLOT_BYTES);
+  const int KBC = p.kbc;
+  uint8_t* sw = smem;                                                   // [KBC][NCOLS rows][128 B]
+  uint8_t* hbuf = sw + KBC * WBLOCK;                                    // [KBC][64 rows][128 B]
+  float* part = reinterpret_cast<float*>(hbuf + KBC * GRU_SLOT);        // [NCOLS][64] fp32 partial tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part + NCOLS * GRU_M);
   uint64_t* wfull = bars;
   uint64_t* full = bars + 1;
-  uint64_t* empty = full + RING;
-  uint64_t* acc_full = empty + RING;
-  uint64_t* acc_empty = acc_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  uint64_t* acc_full = bars + 2;
+  uint64_t* part_ready = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int H = p.hidden, T = p.steps, B = p.batch;
-  const int u0 = blockIdx.x * U;
+  const int H = p.hidden, T = p.steps, B = p.batch, EB = p.ext_batch;
+  const uint32_t crank = C > 1 ? cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / C;
+  const int u0 = blockIdx.x * U;                     // first unit finalised by this CTA
+  const int kb0 = static_cast<int>(crank) * KBC;     // first K block of this CTA's slice
   const uint32_t G = gridDim.x;
+  const int rounds = BWD ? T + 1 : T;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_w);
     tma_prefetch_desc(&tma_x);
     mbar_init(wfull, 1);
-    for (int s = 0; s < RING; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
+    mbar_init(full, 1);
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 4);
+    mbar_init(part_ready, C);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -139,87 +197,149 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (C > 1) cluster_sync_all();                     // every CTA's barriers exist before remote arrivals
   const uint32_t tmem_base = *tmem_slot;
 
-  // number of matmul rounds: forward T (round s consumes h_{s-1} = slot s); backward T (rounds 1..T
-  // consume the gate gradients of step T-s; round 0 has no recurrent input)
   if (warp == 0) {
+    // ------------------------------ TMA producer (whole warp polls, lane 0 issues) ------------
     if (lane == 0) {
-      // resident weights
-      mbar_expect_tx(wfull, static_cast<uint32_t>(KB * wblock));
-      for (int kb = 0; kb < KB; ++kb)
+      mbar_expect_tx(wfull, static_cast<uint32_t>(KBC * WBLOCK));
+      for (int kb = 0; kb < KBC; ++kb)
         for (int g = 0; g < NG; ++g)
-          tma_load_2d(sw + kb * wblock + g * U * 128, &tma_w, wfull, kb * 64, (BWD ? 0 : g * H) + u0);
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t slot_bytes = static_cast<uint32_t>(B) * 128u;
-      const int rounds = BWD ? T + 1 : T;
+          tma_load_2d(sw + kb * WBLOCK + g * UC * 128, &tma_w, wfull, (kb0 + kb) * 64,
+                      (BWD ? 0 : g * H) + cluster_id * UC);
+    }
+    const uint32_t bytes = static_cast<uint32_t>(KBC) * static_cast<uint32_t>(B) * 128u;
+    if (lane == 0) {
       for (int s = 0; s < rounds; ++s) {
-        if (BWD && s == 0) continue;
-        if (s > 0) {
-          grid_wait(p.sync, G * static_cast<uint32_t>(s));
-          fence_proxy_async_all();
+        if (BWD && s == 0) continue;                 // the last timestep has no recurrent input
+        if (s > 0 && !(p.flags & 1)) {
+          grid_wait(p.sync, G * static_cast<uint32_t>(s), !(p.flags & 8));
+          GRU_TS(0, s);
         }
-        const int slot = BWD ? (T - s) : s;        // time slot of the exchange buffer to read
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], slot_bytes);
-          tma_load_3d(ring + stage * Cfg::SLOT_BYTES, &tma_x, &full[stage], kb * 64, slot, 0);
-          if (++stage == RING) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
+        asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy writes -> TMA reads
+        const int slot = BWD ? (T - s) : s;          // time slot of the exchange buffer
+        mbar_expect_tx(full, bytes);
+        for (int kb = 0; kb < KBC; ++kb) tma_load_3d(hbuf + kb * GRU_SLOT, &tma_x, full, (kb0 + kb) * 64, 0, slot);
+        GRU_TS(1, s);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
+      // ------------------------------ MMA issuer ------------------------------
       mbar_wait(wfull, 0);
-      int stage = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      const int rounds = BWD ? T + 1 : T;
+      const uint64_t a_base = smem_desc_sw128(smem_u32(hbuf), 16, 1024);
+      const uint64_t b_base = smem_desc_sw128(smem_u32(sw), 16, 1024);
+      uint32_t phase = 0;
       for (int s = 0; s < rounds; ++s) {
         if (BWD && s == 0) continue;
-        mbar_wait(acc_empty, acc_phase ^ 1);
+        mbar_wait(full, phase);
+        phase ^= 1;
+        GRU_TS(2, s);
         tc_fence_after();
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(ring + stage * Cfg::SLOT_BYTES);
-          const uint32_t b_addr = smem_u32(sw + kb * wblock);
+        for (int kb = 0; kb < KBC; ++kb) {
 #pragma unroll
           for (int k16 = 0; k16 < 4; ++k16) {
-            umma_bf16(tmem_base, smem_desc_sw128(a_addr + k16 * 32, 16, 1024),
-                      smem_desc_sw128(b_addr + k16 * 32, 16, 1024), IDESC, (kb > 0 || k16 > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty[stage]);
-          if (++stage == RING) {
-            stage = 0;
-            phase ^= 1;
+            umma_bf16(tmem_base, a_base + ((kb * GRU_SLOT + k16 * 32) >> 4),
+                      b_base + ((kb * WBLOCK + k16 * 32) >> 4), IDESC, (kb | k16) ? 1u : 0u);
           }
         }
         umma_commit(acc_full);
-        acc_phase ^= 1;
+        GRU_TS(3, s);
       }
     }
     __syncwarp();
   } else {
-    // ------------------------------ epilogue: gate math ------------------------------
-    const int q = warp & 3;                           // TMEM lane quadrant of this warp
-    int row;
-    bool row_ok;
-    if (MT == 128) {
-      row = q * 32 + lane;
-      row_ok = row < B;
-    } else {
-      row = q * 16 + lane;                            // M=64: rows 16q..16q+15 live in lanes 32q..32q+15
-      row_ok = lane < 16 && row < B;
-    }
+    // ------------------------------ epilogue ------------------------------
+    const int q = warp & 3;                          // TMEM lane quadrant of this warp
+    const int row = q * 16 + lane;                   // M=64: rows 16q..16q+15 live in lanes 32q..32q+15
+    const bool lane_ok = lane < 16;
+    const bool row_ok = lane_ok && row < B;
+    const bool io = row_ok && !(p.flags & 4);
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    uint32_t acc_phase = 0;
+    const uint32_t part_addr = smem_u32(part);
+    const uint32_t ready_addr = smem_u32(part_ready);
+    uint32_t acc_phase = 0, part_phase = 0;
 
-    if (!BWD) {
+    // TMEM partial tile -> this CTA's smem (layout [dst rank][gate][row][8 units], so that a
+    // consumer reads its 8 units of a row with two 16-byte DSMEM loads), cluster handshake, then the
+    // DSMEM sum over the C source ranks.
+    auto exchange = [&](float (&out)[NG * U], int dbg_step) {
+      mbar_wait(acc_full, acc_phase);
+      acc_phase ^= 1;
+      if (warp == 2 && lane == 0) GRU_TS(4, dbg_step);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < NCH; c0 += 3) {            // <= 96 columns in flight, ONE wait per batch
+        uint32_t v[3][32];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          if (c0 + j < NCH) tmem_ld32(t_addr + (c0 + j) * 32, v[j]);
+        tmem_ld_wait();
+        if (lane_ok) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            if (c0 + j < NCH) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {             // groups of 8 columns = one (gate, dst rank) pair
+                const int col = (c0 + j) * 32 + e * 8;
+                if (col < NCOLS) {
+                  const int g = col / UC, dst = (col % UC) / U;
+                  float4* dp = reinterpret_cast<float4*>(part + (((dst * NG + g) * GRU_M + row) * U));
+                  dp[0] = make_float4(__uint_as_float(v[j][e * 8 + 0]), __uint_as_float(v[j][e * 8 + 1]),
+                                      __uint_as_float(v[j][e * 8 + 2]), __uint_as_float(v[j][e * 8 + 3]));
+                  dp[1] = make_float4(__uint_as_float(v[j][e * 8 + 4]), __uint_as_float(v[j][e * 8 + 5]),
+                                      __uint_as_float(v[j][e * 8 + 6]), __uint_as_float(v[j][e * 8 + 7]));
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+        fence_acq_rel_cluster();                       // one release fence, then relaxed remote arrivals
+#pragma unroll
+        for (int r = 0; r < C; ++r) mbar_arrive_cluster_relaxed(mapa(ready_addr, static_cast<uint32_t>(r)));
+        GRU_TS(7, dbg_step);
+      }
+      mbar_wait_cluster(part_ready, part_phase);
+      part_phase ^= 1;
+      if (warp == 2 && lane == 0) GRU_TS(5, dbg_step);
+#pragma unroll
+      for (int i = 0; i < NG * U; ++i) out[i] = 0.f;
+      if (lane_ok) {
+        float4 v[C][NG][2];
+#pragma unroll
+        for (int r = 0; r < C; ++r) {
+          const uint32_t base = mapa(part_addr, static_cast<uint32_t>(r));
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            const int off = ((static_cast<int>(crank) * NG + g) * GRU_M + row) * U;
+            if (static_cast<uint32_t>(r) == crank) {            // own partial: plain shared-memory loads
+              v[r][g][0] = *reinterpret_cast<const float4*>(part + off);
+              v[r][g][1] = *reinterpret_cast<const float4*>(part + off + 4);
+            } else {
+              v[r][g][0] = ld_dsmem_v4(base + static_cast<uint32_t>(off * 4));
+              v[r][g][1] = ld_dsmem_v4(base + static_cast<uint32_t>(off * 4 + 16));
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < C; ++r)
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            out[g * U + 0] += v[r][g][0].x; out[g * U + 1] += v[r][g][0].y;
+            out[g * U + 2] += v[r][g][0].z; out[g * U + 3] += v[r][g][0].w;
+            out[g * U + 4] += v[r][g][1].x; out[g * U + 5] += v[r][g][1].y;
+            out[g * U + 6] += v[r][g][1].z; out[g * U + 7] += v[r][g][1].w;
+          }
+      }
+    };
+
+    if constexpr (!BWD) {
       float h[U], bhr[U], bhz[U], bhn[U];
 #pragma unroll
       for (int i = 0; i < U; ++i) {
@@ -231,46 +351,40 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       for (int t = 0; t < T; ++t) {
         const long long rt = static_cast<long long>(row) * T + t;
         float gr[U], gz[U], gn[U];
-        if (row_ok) {
-          const __nv_bfloat16* gp = p.gi + rt * 3 * H + u0;
-          load_bf16_vec<U>(gp, gr);
-          load_bf16_vec<U>(gp + H, gz);
-          load_bf16_vec<U>(gp + 2 * H, gn);
-        }
-        mbar_wait(acc_full, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
-        float dr[U], dz[U], dn[U];
-        tmem_ld_units<U>(t_addr, dr);
-        tmem_ld_units<U>(t_addr + U, dz);
-        tmem_ld_units<U>(t_addr + 2 * U, dn);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty);
-        if (row_ok) {
-          float r[U], z[U], n[U], hn[U];
 #pragma unroll
-          for (int i = 0; i < U; ++i) {
-            r[i] = sigmoidf_(gr[i] + dr[i] + bhr[i]);
-            z[i] = sigmoidf_(gz[i] + dz[i] + bhz[i]);
-            hn[i] = dn[i] + bhn[i];
-            n[i] = tanhf(gn[i] + r[i] * hn[i]);
-            h[i] = (1.f - z[i]) * n[i] + z[i] * h[i];
-          }
-          store_bf16_vec<U>(p.h_ext + (static_cast<long long>(row) * (T + 1) + t + 1) * H + u0, h);
-          if (p.gates) {
-            __nv_bfloat16* sp = p.gates + rt * 4 * H + u0;
-            store_bf16_vec<U>(sp, r);
-            store_bf16_vec<U>(sp + H, z);
-            store_bf16_vec<U>(sp + 2 * H, n);
-            store_bf16_vec<U>(sp + 3 * H, hn);
-          }
+        for (int i = 0; i < U; ++i) gr[i] = gz[i] = gn[i] = 0.f;
+        if (io) {
+          const __nv_bfloat16* gp = p.gi + rt * 3 * H + u0;
+          load_bf16x8(gp, gr);
+          load_bf16x8(gp + H, gz);
+          load_bf16x8(gp + 2 * H, gn);
         }
+        float acc[3 * U];
+        exchange(acc, t);
+        float r[U], z[U], n[U], hn[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          r[i] = sigmoid_fast(gr[i] + acc[i] + bhr[i]);
+          z[i] = sigmoid_fast(gz[i] + acc[U + i] + bhz[i]);
+          hn[i] = acc[2 * U + i] + bhn[i];
+          n[i] = tanh_fast(gn[i] + r[i] * hn[i]);
+          h[i] = (1.f - z[i]) * n[i] + z[i] * h[i];
+        }
+        if (io) store_bf16x8(p.h_ext + (static_cast<long long>(t + 1) * EB + row) * H + u0, h);
         // publish h_t: all epilogue threads' stores -> one release arrival per CTA
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (warp == 2 && lane == 0) {
-          __threadfence();
+          GRU_TS(6, t);
           red_release_gpu_add(p.sync, 1u);
+        }
+        // the batch-major copy of h_t (GEMM operand) and the saved gates are off the critical path
+        if (p.hall && io) store_bf16x8(p.hall + rt * H + u0, h);
+        if (p.gates && io) {
+          __nv_bfloat16* sp = p.gates + rt * 4 * H + u0;
+          store_bf16x8(sp, r);
+          store_bf16x8(sp + H, z);
+          store_bf16x8(sp + 2 * H, n);
+          store_bf16x8(sp + 3 * H, hn);
         }
       }
       if (row_ok) {
@@ -285,27 +399,21 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         const int t = T - 1 - s;
         const long long rt = static_cast<long long>(row) * T + t;
         float dh[U], r[U], z[U], n[U], hn[U], hp[U];
-        if (row_ok && t >= 0) {
-          load_bf16_vec<U>(p.dh_out + rt * H + u0, dh);
+#pragma unroll
+        for (int i = 0; i < U; ++i) dh[i] = r[i] = z[i] = n[i] = hn[i] = hp[i] = 0.f;
+        if (io && t >= 0) {
+          load_bf16x8(p.dh_out + rt * H + u0, dh);
           const __nv_bfloat16* sp = p.gates + rt * 4 * H + u0;
-          load_bf16_vec<U>(sp, r);
-          load_bf16_vec<U>(sp + H, z);
-          load_bf16_vec<U>(sp + 2 * H, n);
-          load_bf16_vec<U>(sp + 3 * H, hn);
-          load_bf16_vec<U>(p.h_ext + (static_cast<long long>(row) * (T + 1) + t) * H + u0, hp);
+          load_bf16x8(sp, r);
+          load_bf16x8(sp + H, z);
+          load_bf16x8(sp + 2 * H, n);
+          load_bf16x8(sp + 3 * H, hn);
+          load_bf16x8(p.h_ext + (static_cast<long long>(t) * EB + row) * H + u0, hp);
         }
         float d[U];
 #pragma unroll
         for (int i = 0; i < U; ++i) d[i] = 0.f;
-        if (s > 0) {
-          mbar_wait(acc_full, acc_phase);
-          acc_phase ^= 1;
-          tc_fence_after();
-          tmem_ld_units<U>(t_addr, d);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty);
-        }
+        if (s > 0) exchange(d, s);
         if (t < 0) {
           if (row_ok) {
 #pragma unroll
@@ -313,34 +421,33 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           }
           break;
         }
-        if (row_ok) {
-          float gr[U], gz[U], gn[U], ghn[U];
+        float gr[U], gz[U], gn[U], ghn[U];
 #pragma unroll
-          for (int i = 0; i < U; ++i) {
-            const float dht = dh[i] + carry[i] + d[i];
-            const float dn_ = dht * (1.f - z[i]);
-            const float dz_ = dht * (hp[i] - n[i]);
-            carry[i] = dht * z[i];
-            const float dn_pre = dn_ * (1.f - n[i] * n[i]);
-            const float dr_ = dn_pre * hn[i];
-            gr[i] = dr_ * r[i] * (1.f - r[i]);
-            gz[i] = dz_ * z[i] * (1.f - z[i]);
-            gn[i] = dn_pre;
-            ghn[i] = dn_pre * r[i];
-          }
-          __nv_bfloat16* gip = p.dgi + rt * 3 * H + u0;
-          store_bf16_vec<U>(gip, gr);
-          store_bf16_vec<U>(gip + H, gz);
-          store_bf16_vec<U>(gip + 2 * H, gn);
-          __nv_bfloat16* ghp = p.dgh + rt * 3 * H + u0;
-          store_bf16_vec<U>(ghp, gr);
-          store_bf16_vec<U>(ghp + H, gz);
-          store_bf16_vec<U>(ghp + 2 * H, ghn);
+        for (int i = 0; i < U; ++i) {
+          const float dht = dh[i] + carry[i] + d[i];
+          const float dn_ = dht * (1.f - z[i]);
+          const float dz_ = dht * (hp[i] - n[i]);
+          carry[i] = dht * z[i];
+          const float dn_pre = dn_ * (1.f - n[i] * n[i]);
+          const float dr_ = dn_pre * hn[i];
+          gr[i] = dr_ * r[i] * (1.f - r[i]);
+          gz[i] = dz_ * z[i] * (1.f - z[i]);
+          gn[i] = dn_pre;
+          ghn[i] = dn_pre * r[i];
+        }
+        if (io) {
+          __nv_bfloat16* ghp = p.dgh + (static_cast<long long>(t) * EB + row) * 3 * H + u0;   // exchanged
+          store_bf16x8(ghp, gr);
+          store_bf16x8(ghp + H, gz);
+          store_bf16x8(ghp + 2 * H, ghn);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && lane == 0) {
-          __threadfence();
-          red_release_gpu_add(p.sync, 1u);
+        if (warp == 2 && lane == 0) red_release_gpu_add(p.sync, 1u);
+        if (io) {                                               // dgi is only read after the kernel
+          __nv_bfloat16* gip = p.dgi + rt * 3 * H + u0;
+          store_bf16x8(gip, gr);
+          store_bf16x8(gip + H, gz);
+          store_bf16x8(gip + 2 * H, gn);
         }
       }
     }
@@ -348,47 +455,89 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
 
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();                     // nobody exits while a peer may still read its smem
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int MT, bool BWD>
-static int launch_gru(const srnn_gru_args* a, cudaStream_t stream) {
-  using Cfg = GruCfg<MT>;
-  constexpr int U = Cfg::U;
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <bool BWD, int C>
+static size_t gru_smem_bytes(int kbc) {
+  const int ncols = (BWD ? 1 : 3) * GRU_U * C;
+  return static_cast<size_t>(kbc) * ncols * 128 + static_cast<size_t>(kbc) * GRU_SLOT +
+         static_cast<size_t>(ncols) * GRU_M * 4 + 256 + 1024;
+}
+
+// Can H/8 CTAs in clusters of C all be resident at once (they spin on one another)?
+template <bool BWD, int C>
+static bool gru_fits(int H, int kbc) {
+  auto kern = gru_kernel<BWD, C>;
+  const size_t smem = gru_smem_bytes<BWD, C>(kbc);
+  if (smem > 227 * 1024) return false;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  const int ctas = H / GRU_U;
+  if (C == 1) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GRU_THREADS, smem) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return per_sm * sm_count() >= ctas;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(GRU_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return clusters * C >= ctas;
+}
+
+template <bool BWD, int C>
+static int launch_gru(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   const int H = a->hidden, T = a->steps, B = a->batch;
-  SRNN_CHECK_ARG(H % U == 0, "gru: hidden (%d) must be a multiple of %d for batch tile %d", H, U, MT);
-  const int ctas = H / U;
-  SRNN_CHECK_ARG(ctas <= sm_count(), "gru: hidden/%d = %d CTAs exceeds the SM count %d", U, ctas, sm_count());
   const int K = BWD ? 3 * H : H;
-  const int KB = (K + 63) / 64;
-  const int ncols = (BWD ? 1 : 3) * U;
-  const size_t wbytes = ((size_t)KB * ncols * 128 + 1023) & ~(size_t)1023;
-  const size_t smem = wbytes + (size_t)Cfg::RING * Cfg::SLOT_BYTES + 512 + 1024;
-  SRNN_CHECK_ARG(smem <= 227 * 1024, "gru: resident weight slice does not fit shared memory (%zu bytes)", smem);
+  const int ctas = H / GRU_U;
+  const size_t smem = gru_smem_bytes<BWD, C>(kbc);
 
   CUtensorMap tw, tx;
   {
     // forward: W_hh [3H, H] rows = gate rows; backward: W_hh^T [H, 3H] rows = units
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)(BWD ? H : 3 * H)};
     const uint64_t strides[1] = {(uint64_t)K * 2};
-    const uint32_t box[2] = {64, (uint32_t)U};
+    const uint32_t box[2] = {64, (uint32_t)(GRU_U * C)};
     int rc = make_tmap_bf16(&tw, a->w_hh, 2, dims, strides, box, true);
     if (rc) return rc;
   }
   {
-    // exchange buffer: forward h_ext [B, T+1, H]; backward dgh [B, T, 3H]
+    // exchange buffer, TIME-major: forward h_ext [T+1, EB, H]; backward dgh [T, EB, 3H]
     const uint64_t slots = BWD ? (uint64_t)T : (uint64_t)T + 1;
-    const uint64_t dims[3] = {(uint64_t)K, slots, (uint64_t)B};
-    const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)K * 2 * slots};
-    const uint32_t box[3] = {64, 1, (uint32_t)B};
+    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)B, slots};
+    const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)K * 2 * (uint64_t)a->ext_batch};
+    const uint32_t box[3] = {64, (uint32_t)B, 1};
     int rc = make_tmap_bf16(&tx, BWD ? (const void*)a->dgh : (const void*)a->h_ext, 3, dims, strides, box, true);
     if (rc) return rc;
   }
   GruParams p{};
-  p.batch = B; p.steps = T; p.hidden = H; p.kblocks = KB; p.ctas = ctas;
+  p.batch = B; p.steps = T; p.hidden = H; p.ext_batch = a->ext_batch; p.kbc = kbc;
   p.gi = static_cast<const __nv_bfloat16*>(a->gi);
   p.b_hh = a->b_hh;
   p.h_ext = static_cast<__nv_bfloat16*>(a->h_ext);
+  p.hall = static_cast<__nv_bfloat16*>(a->hall);
   p.h_state = a->h_state;
   p.gates = static_cast<__nv_bfloat16*>(a->gates);
   p.dh_out = static_cast<const __nv_bfloat16*>(a->dh_out);
@@ -396,12 +545,87 @@ static int launch_gru(const srnn_gru_args* a, cudaStream_t stream) {
   p.dgh = static_cast<__nv_bfloat16*>(a->dgh);
   p.dh0 = a->dh0;
   p.sync = a->sync;
+  p.flags = a->debug_flags;
+  p.ts = reinterpret_cast<unsigned long long*>(a->debug_ts);
 
-  auto kern = gru_kernel<MT, BWD>;
+  auto kern = gru_kernel<BWD, C>;
   SRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  void* args[] = {(void*)&tw, (void*)&tx, (void*)&p};
-  SRNN_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(ctas), dim3(GRU_THREADS), args, smem, stream));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(GRU_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  attrs[na].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident: they spin on one another
+  attrs[na].val.cooperative = 1;
+  ++na;
+  if (C > 1) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = C;
+    attrs[na].val.clusterDim.y = 1;
+    attrs[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = na;
+  SRNN_CUDA(cudaLaunchKernelEx(&cfg, kern, tw, tx, p));
   return SRNN_OK;
+}
+
+// Largest cluster size whose K split is whole K blocks, whose units tile H and whose slice fits smem.
+template <bool BWD>
+static int pick_cluster(int H, int* kbc_out) {
+  const int K = BWD ? 3 * H : H;
+  const int kb_total = (K + 63) / 64;
+  // measured (B=64, H=1024): forward 6.2 us/step at C=2 vs 6.8 at C=4 (DSMEM exchange volume grows
+  // with C); backward needs C>=4 for the 3H-wide slice to fit shared memory
+  const int fwd_order[4] = {2, 4, 8, 1};
+  const int bwd_order[4] = {4, 8, 2, 1};
+  for (int i = 0; i < 4; ++i) {
+    const int c = BWD ? bwd_order[i] : fwd_order[i];
+    if (kb_total % c != 0 || H % (GRU_U * c) != 0) continue;
+    const int kbc = kb_total / c;
+    bool fits = false;
+    switch (c) {
+      case 8: fits = gru_fits<BWD, 8>(H, kbc); break;
+      case 4: fits = gru_fits<BWD, 4>(H, kbc); break;
+      case 2: fits = gru_fits<BWD, 2>(H, kbc); break;
+      default: fits = gru_fits<BWD, 1>(H, kbc); break;
+    }
+    if (!fits) continue;
+    *kbc_out = kbc;
+    return c;
+  }
+  return 0;
+}
+
+template <bool BWD>
+static int dispatch_gru(const srnn_gru_args* a, cudaStream_t stream) {
+  static int cached_h = -1, cached_c = 0, cached_kbc = 0;      // per instantiation (fwd / bwd)
+  if (cached_h != a->hidden) {
+    cached_c = pick_cluster<BWD>(a->hidden, &cached_kbc);
+    cached_h = a->hidden;
+  }
+  int kbc = cached_kbc;
+  int c = cached_c;
+  if (a->debug_flags >> 8) {                         // experiments: force a cluster size (bits 8..)
+    const int forced = a->debug_flags >> 8;
+    const int kb_total = ((BWD ? 3 : 1) * a->hidden + 63) / 64;
+    if (kb_total % forced == 0 && a->hidden % (GRU_U * forced) == 0) {
+      c = forced;
+      kbc = kb_total / forced;
+    }
+  }
+  SRNN_CHECK_ARG(c > 0, "gru: no cluster decomposition fits hidden=%d", a->hidden);
+  SRNN_CHECK_ARG(a->hidden / GRU_U <= sm_count(), "gru: hidden/8 = %d CTAs exceeds the SM count %d", a->hidden / GRU_U,
+                 sm_count());
+  switch (c) {
+    case 8: return launch_gru<BWD, 8>(a, kbc, stream);
+    case 4: return launch_gru<BWD, 4>(a, kbc, stream);
+    case 2: return launch_gru<BWD, 2>(a, kbc, stream);
+    default: return launch_gru<BWD, 1>(a, kbc, stream);
+  }
 }
 
 }  // namespace srnn
@@ -410,10 +634,12 @@ using namespace srnn;
 
 static int check_common(const srnn_gru_args* a) {
   SRNN_CHECK_ARG(a != nullptr, "gru: null args");
-  SRNN_CHECK_ARG(a->batch > 0 && a->batch <= 128, "gru: batch must be in 1..128 (got %d); split larger batches", a->batch);
+  SRNN_CHECK_ARG(a->batch > 0 && a->batch <= GRU_M, "gru: batch must be in 1..64 (got %d); split larger batches",
+                 a->batch);
   SRNN_CHECK_ARG(a->steps > 0 && a->hidden > 0 && a->hidden % 8 == 0, "gru: bad steps/hidden (%d, %d)", a->steps,
                  a->hidden);
   SRNN_CHECK_ARG(a->w_hh && a->h_ext && a->gates && a->sync, "gru: null buffer");
+  SRNN_CHECK_ARG(a->ext_batch >= a->batch, "gru: ext_batch (%d) must be >= batch (%d)", a->ext_batch, a->batch);
   return SRNN_OK;
 }
 
@@ -421,14 +647,12 @@ extern "C" int srnn_gru_forward(const srnn_gru_args* a, srnn_stream_t stream) {
   int rc = check_common(a);
   if (rc) return rc;
   SRNN_CHECK_ARG(a->gi && a->b_hh && a->h_state, "gru_forward: null buffer");
-  if (a->batch <= 64) return launch_gru<64, false>(a, static_cast<cudaStream_t>(stream));
-  return launch_gru<128, false>(a, static_cast<cudaStream_t>(stream));
+  return dispatch_gru<false>(a, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int srnn_gru_backward(const srnn_gru_args* a, srnn_stream_t stream) {
   int rc = check_common(a);
   if (rc) return rc;
   SRNN_CHECK_ARG(a->dh_out && a->dgi && a->dgh && a->dh0, "gru_backward: null buffer");
-  if (a->batch <= 64) return launch_gru<64, true>(a, static_cast<cudaStream_t>(stream));
-  return launch_gru<128, true>(a, static_cast<cudaStream_t>(stream));
+  return dispatch_gru<true>(a, static_cast<cudaStream_t>(stream));
 }

@@ -123,7 +123,7 @@ class FrameTierFn(torch.autograd.Function):
         ops.gemm_nt(ain, wcat, u, b * t, h, kp, kp, kp, h, bias=(xb + cb), aux=upper, ldaux=h, aux_mode=1)
 
         saved_layers = []
-        x_l, x_ld, x_bs, x_batched = u, h, 0, False
+        x_l = u                                                # (B*T, H) batch-major input of layer 0
         hn = _empty(layers, b, h, dtype=F32, device=dev)
         for i in range(layers):
             w_ih, w_hh, b_ih, b_hh = rnn[4 * i: 4 * i + 4]
@@ -134,19 +134,16 @@ class FrameTierFn(torch.autograd.Function):
             ops.weight_prep(w_ih.contiguous(), None, (3 * h, h, 1), wih, (h, 1, 0), wih_t, (1, 3 * h, 0))
             ops.weight_prep(w_hh.contiguous(), None, (3 * h, h, 1), whh, (h, 1, 0), whh_t, (1, 3 * h, 0))
             gi = _empty(b * t, 3 * h, device=dev)
-            if x_batched:
-                ops.gemm_nt(x_l, wih, gi, t, 3 * h, h, x_ld, h, 3 * h, batch=b, a_bs=x_bs, c_bs=t * 3 * h,
-                            bias=b_ih.contiguous())
-            else:
-                ops.gemm_nt(x_l, wih, gi, b * t, 3 * h, h, x_ld, h, 3 * h, bias=b_ih.contiguous())
-            h_ext = _empty(b, t + 1, h, device=dev)
+            ops.gemm_nt(x_l, wih, gi, b * t, 3 * h, h, h, h, 3 * h, bias=b_ih.contiguous())
+            h_ext = _empty(t + 1, b, h, device=dev)            # time-major exchange buffer, slot 0 = h_init
+            hall = _empty(b * t, h, device=dev)                # batch-major copy for the GEMMs
             h_state = h_init[i].contiguous().clone()
-            ops.pad_cast_bf16(h_state, b, h, h, h_ext, h, (t + 1) * h)
+            ops.pad_cast_bf16(h_state, b, h, h, h_ext, h, h)
             gates = _empty(b * t, 4 * h, device=dev)
-            ops.gru_forward(gi, whh, b_hh.contiguous(), h_ext, h_state, gates, b, t, h)
+            ops.gru_forward(gi, whh, b_hh.contiguous(), h_ext, hall, h_state, gates, b, t, h)
             hn[i] = h_state
-            saved_layers.append((wih_t, whh_t, h_ext, gates, x_l, x_ld, x_bs, x_batched))
-            x_l, x_ld, x_bs, x_batched = h_ext[:, 1:], h, (t + 1) * h, True
+            saved_layers.append((wih_t, whh_t, h_ext, hall, gates, x_l))
+            x_l = hall
 
         # learned upsampling as one GEMM: out[(b,t), j*H+o] = sum_i h[b,t,i] Wu[i,o,j] + bias[o,j]
         wu = _empty(r * h, h, device=dev)
@@ -154,8 +151,7 @@ class FrameTierFn(torch.autograd.Function):
         inv_u = _empty(h, dtype=F32, device=dev)
         ops.weight_prep(uv, ug, (h, h, r), wu, (1, h, h * h), wu_t, (r * h, 1, h), inv_norm=inv_u)
         up = _empty(b, t * r, h, device=dev)
-        ops.gemm_nt(x_l, wu, up, t, r * h, h, x_ld, h, r * h, batch=b, a_bs=x_bs, c_bs=t * r * h,
-                    bias=ub.t().contiguous().view(-1))
+        ops.gemm_nt(x_l, wu, up, b * t, r * h, h, h, h, r * h, bias=ub.t().contiguous().view(-1))
 
         ctx.dims = (b, t, l, c, h, fs, r, kp, cp, layers, upper is not None)
         ctx.saved_layers = saved_layers
@@ -169,11 +165,11 @@ class FrameTierFn(torch.autograd.Function):
         b, t, l, c, h, fs, r, kp, cp, layers, has_upper = ctx.dims
         dev = dup.device
         dup = dup.contiguous()            # (B, T*r, H) == (B*T, r*H)
-        last_h_ext = ctx.saved_layers[-1][2]
+        last_hall = ctx.saved_layers[-1][3]
         # upsample
         d_ub = ops.colsum(dup, b * t, r * h, r * h).view(r, h).t().contiguous()
         dwu = _zeros(r * h, h, device=dev)
-        ops.gemm_tn(dup, last_h_ext[:, 1:], dwu, r * h, h, t, r * h, h, h, batch=b, a_bs=t * r * h, b_bs=(t + 1) * h)
+        ops.gemm_tn(dup, last_hall, dwu, r * h, h, b * t, r * h, h, h)
         d_uv, d_ug = ops.weight_prep_bwd(dwu, (1, h, h * h), uv, ug, inv_u, (h, h, r))
         dh_out = _empty(b * t, h, device=dev)
         ops.gemm_nt(dup, wu_t, dh_out, b * t, h, r * h, r * h, r * h, h)
@@ -181,19 +177,16 @@ class FrameTierFn(torch.autograd.Function):
         rnn_grads = [None] * (4 * layers)
         dh0 = _empty(layers, b, h, dtype=F32, device=dev)
         for i in reversed(range(layers)):
-            wih_t, whh_t, h_ext, gates, x_l, x_ld, x_bs, x_batched = ctx.saved_layers[i]
-            dgi = _empty(b * t, 3 * h, device=dev)
-            dgh = _empty(b * t, 3 * h, device=dev)
+            wih_t, whh_t, h_ext, hall, gates, x_l = ctx.saved_layers[i]
+            dgi = _empty(b * t, 3 * h, device=dev)             # batch-major
+            dgh = _empty(t * b, 3 * h, device=dev)             # time-major (exchange buffer)
             dh0_i = _empty(b, h, dtype=F32, device=dev)
             ops.gru_backward(whh_t, h_ext, gates, dh_out, dgi, dgh, dh0_i, b, t, h)
             dh0[i] = dh0_i
-            dwhh = _zeros(3 * h, h, device=dev)
-            ops.gemm_tn(dgh, h_ext, dwhh, 3 * h, h, t, 3 * h, h, h, batch=b, a_bs=t * 3 * h, b_bs=(t + 1) * h)
+            dwhh = _zeros(3 * h, h, device=dev)                # both operands time-major: rows (t, b)
+            ops.gemm_tn(dgh, h_ext, dwhh, 3 * h, h, t * b, 3 * h, h, h)
             dwih = _zeros(3 * h, h, device=dev)
-            if x_batched:
-                ops.gemm_tn(dgi, x_l, dwih, 3 * h, h, t, 3 * h, x_ld, h, batch=b, a_bs=t * 3 * h, b_bs=x_bs)
-            else:
-                ops.gemm_tn(dgi, x_l, dwih, 3 * h, h, b * t, 3 * h, x_ld, h)
+            ops.gemm_tn(dgi, x_l, dwih, 3 * h, h, b * t, 3 * h, h, h)
             rnn_grads[4 * i: 4 * i + 4] = [dwih, dwhh, ops.colsum(dgi, b * t, 3 * h, 3 * h),
                                            ops.colsum(dgh, b * t, 3 * h, 3 * h)]
             dx = _empty(b * t, h, device=dev)

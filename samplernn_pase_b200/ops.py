@@ -263,38 +263,45 @@ def gemm_nll(mode, a, w, bias, target, m, k, lda, ldw, lse=None, logp_target=Non
 # ----------------------------------------------------------------------------------------------
 # recurrence
 # ----------------------------------------------------------------------------------------------
-GRU_MAX_BATCH = 128
+GRU_MAX_BATCH = 64
+gru_debug_flags = 0      # timing experiments only (scripts/gru_microbench.py)
+gru_debug_ts = None      # int64 [256, 8] tensor receiving CTA 0's pipeline timestamps
 
 
 def _gru_call(name, batch, steps, hidden, **bufs):
-    """Runs the persistent kernel over batch groups of <= 128 rows (independent sequences)."""
+    """Runs the persistent kernel over batch groups of <= 128 rows (independent sequences).
+    ``bufs``: field -> (tensor, elements per batch row); time-major buffers advance by one row."""
     for b0 in range(0, batch, GRU_MAX_BATCH):
         nb = min(GRU_MAX_BATCH, batch - b0)
         a = GruArgs()
-        a.batch, a.steps, a.hidden = nb, steps, hidden
+        a.batch, a.steps, a.hidden, a.ext_batch = nb, steps, hidden, batch
         for key, (t, per_row) in bufs.items():
             if t is None:
                 setattr(a, key, None)
             else:
                 setattr(a, key, t.data_ptr() + b0 * per_row * t.element_size())
-        sync = torch.zeros(64, dtype=torch.int32, device=bufs['h_ext'][0].device)
+        sync = torch.zeros(256, dtype=torch.int32, device=bufs['h_ext'][0].device)
         a.sync = sync.data_ptr()
+        a.debug_flags = gru_debug_flags
+        a.debug_ts = gru_debug_ts.data_ptr() if gru_debug_ts is not None else None
         _lib.profile_note = f'B={nb} T={steps} H={hidden}'
         call(name, C.byref(a), stream())
         _count(2)
 
 
-def gru_forward(gi, w_hh, b_hh, h_ext, h_state, gates, batch, steps, hidden):
+def gru_forward(gi, w_hh, b_hh, h_ext, hall, h_state, gates, batch, steps, hidden):
+    """h_ext: bf16 [steps+1, batch, H] time-major (slot 0 = initial state); hall: bf16 [batch*steps, H]."""
     h = hidden
     _gru_call('srnn_gru_forward', batch, steps, h, gi=(gi, steps * 3 * h), w_hh=(w_hh, 0), b_hh=(b_hh, 0),
-              h_ext=(h_ext, (steps + 1) * h), h_state=(h_state, h), gates=(gates, steps * 4 * h))
+              h_ext=(h_ext, h), hall=(hall, steps * h), h_state=(h_state, h), gates=(gates, steps * 4 * h))
 
 
 def gru_backward(w_hh_t, h_ext, gates, dh_out, dgi, dgh, dh0, batch, steps, hidden):
+    """dgh: bf16 [steps, batch, 3H] time-major; dgi: bf16 [batch*steps, 3H] batch-major."""
     h = hidden
-    _gru_call('srnn_gru_backward', batch, steps, h, w_hh=(w_hh_t, 0), h_ext=(h_ext, (steps + 1) * h),
+    _gru_call('srnn_gru_backward', batch, steps, h, w_hh=(w_hh_t, 0), h_ext=(h_ext, h),
               gates=(gates, steps * 4 * h), dh_out=(dh_out, steps * h), dgi=(dgi, steps * 3 * h),
-              dgh=(dgh, steps * 3 * h), dh0=(dh0, h))
+              dgh=(dgh, 3 * h), dh0=(dh0, h))
 
 
 def state_select(carried, h0, use_carry, batch, hidden):

@@ -1,0 +1,71 @@
+"""Timing decomposition of the persistent GRU kernels (CUDA events, us per timestep).
+python scripts/gru_microbench.py [--batch 64] [--steps 1000] [--hidden 1024] [--flags 0,1,2,3,4,7]"""
+import argparse
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from samplernn_pase_b200 import ops    # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--batch', type=int, default=64)
+ap.add_argument('--steps', type=int, default=1000)
+ap.add_argument('--hidden', type=int, default=1024)
+ap.add_argument('--flags', default='0,1024,512,256,1,4')   # bits 8.. force a cluster size
+ap.add_argument('--reps', type=int, default=3)
+a = ap.parse_args()
+b, t, h = a.batch, a.steps, a.hidden
+bf = torch.bfloat16
+gi = torch.randn(b * t, 3 * h, device='cuda').to(bf)
+w = (torch.randn(3 * h, h, device='cuda') / math.sqrt(h)).to(bf)
+wt = w.t().contiguous()
+b_hh = torch.zeros(3 * h, device='cuda')
+h_ext = torch.zeros(t + 1, b, h, dtype=bf, device='cuda')
+hall = torch.zeros(b * t, h, dtype=bf, device='cuda')
+gates = torch.empty(b * t, 4 * h, dtype=bf, device='cuda')
+dh_out = (torch.randn(b * t, h, device='cuda') * 0.1).to(bf)
+dgi = torch.empty(b * t, 3 * h, dtype=bf, device='cuda')
+dgh = torch.empty(b * t, 3 * h, dtype=bf, device='cuda')
+dh0 = torch.empty(b, h, device='cuda')
+
+
+def run(kind):
+    if kind == 'fwd':
+        ops.gru_forward(gi, w, b_hh, h_ext, hall, torch.zeros(b, h, device='cuda'), gates, b, t, h)
+    else:
+        ops.gru_backward(wt, h_ext, gates, dh_out, dgi, dgh, dh0, b, t, h)
+
+
+for flags in [int(f) for f in a.flags.split(',')]:
+    ops.gru_debug_flags = flags
+    for kind in ('fwd', 'bwd'):
+        try:
+            run(kind)
+        except RuntimeError as e:
+            print(f'flags={flags} {kind}: {str(e)[-80:]}')
+            continue
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(a.reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); run(kind); e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        print(f'flags={flags} {kind}: {best:8.3f} ms  {1e3 * best / t:6.2f} us/step   (B={b} T={t} H={h})')
+ops.gru_debug_flags = 0
+# pipeline timestamps of CTA 0 (forward): cycles relative to the end of the grid wait
+ts = torch.zeros(256, 8, dtype=torch.int64, device='cuda')
+ops.gru_debug_ts = ts
+run('fwd')
+torch.cuda.synchronize()
+ops.gru_debug_ts = None
+t_ = ts.cpu()
+names = ['wait_done', 'tma_issued', 'mma_full', 'mma_commit', 'epi_acc_full', 'epi_arrived', 'epi_part_rdy', 'epi_publish']
+order = [0, 1, 2, 3, 4, 7, 5, 6]
+print('step  ' + '  '.join(f'{n:>12s}' for n in names) + '   next_wait_done')
+for s_ in range(20, 28):
+    base = int(t_[s_, 0])
+    print(f'{s_:4d}  ' + '  '.join(f'{int(t_[s_, i]) - base:12d}' for i in order) + f'   {int(t_[s_ + 1, 0]) - base:10d}')

@@ -236,13 +236,15 @@ def test_gru_forward(ops, bsz, t, h):
     w_hh = rnd(3 * h, h, scale=1 / math.sqrt(h), seed=1).to(BF16)
     b_hh = rnd(3 * h, scale=0.1, seed=2)
     h0 = rnd(bsz, h, scale=0.5, seed=3)
-    h_ext = torch.zeros(bsz, t + 1, h, dtype=BF16, device='cuda')
-    h_ext[:, 0] = h0.to(BF16)
+    h_ext = torch.zeros(t + 1, bsz, h, dtype=BF16, device='cuda')      # time-major exchange buffer
+    h_ext[0] = h0.to(BF16)
+    hall = torch.zeros(bsz, t, h, dtype=BF16, device='cuda')
     h_state = h0.clone()
     gates = torch.empty(bsz * t, 4 * h, dtype=BF16, device='cuda')
-    ops.gru_forward(gi.view(bsz * t, 3 * h), w_hh, b_hh, h_ext, h_state, gates, bsz, t, h)
+    ops.gru_forward(gi.view(bsz * t, 3 * h), w_hh, b_hh, h_ext, hall, h_state, gates, bsz, t, h)
     hs, gref, hT = _gru_ref(gi.float(), w_hh, b_hh, h0)
-    assert float((h_ext[:, 1:].float() - hs).abs().max()) < 2e-2       # bf16 storage of values in (-1,1)
+    assert float((hall.float() - hs).abs().max()) < 2e-2               # bf16 storage of values in (-1,1)
+    assert torch.equal(h_ext[1:].transpose(0, 1), hall)                # both copies of h_t agree
     assert float((h_state - hT).abs().max()) < 1e-2
     assert float((gates.view(bsz, t, 4 * h).float() - gref).abs().max()) < 3e-2
 
@@ -267,11 +269,11 @@ def test_gru_backward(ops, bsz, t, h):
         outs.append(cur)
     (torch.stack(outs, 1) * dh_out.float()).sum().backward()
     # kernel path
-    h_ext = torch.zeros(bsz, t + 1, h, dtype=BF16, device='cuda')
-    h_ext[:, 0] = h0.to(BF16)
+    h_ext = torch.zeros(t + 1, bsz, h, dtype=BF16, device='cuda')
+    h_ext[0] = h0.to(BF16)
     h_state = h0.clone()
     gates = torch.empty(bsz * t, 4 * h, dtype=BF16, device='cuda')
-    ops.gru_forward(gi.view(bsz * t, 3 * h), w_hh, b_hh, h_ext, h_state, gates, bsz, t, h)
+    ops.gru_forward(gi.view(bsz * t, 3 * h), w_hh, b_hh, h_ext, None, h_state, gates, bsz, t, h)
     dgi = torch.empty(bsz * t, 3 * h, dtype=BF16, device='cuda')
     dgh = torch.empty(bsz * t, 3 * h, dtype=BF16, device='cuda')
     dh0 = torch.empty(bsz, h, dtype=F32, device='cuda')
