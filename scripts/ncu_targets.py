@@ -1,0 +1,54 @@
+"""Launches the hot kernels once each at BASELINE config-2 row counts so that `ncu --set full` can
+capture them in isolation (the persistent cluster GRU kernels are excluded: ncu cannot replay a
+cooperative cluster launch - it reports LaunchFailed).  Prints CUDA-event times as a plain run."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from samplernn_pase_b200 import ops   # noqa: E402
+
+bf = torch.bfloat16
+m, h, q = int(os.environ.get('ROWS', 1024000)), 1024, 256
+dev = 'cuda'
+
+
+def timed(name, fn, flops=None, nbytes=None):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    extra = f'{flops / ms / 1e9:8.1f} TFLOP/s' if flops else f'{nbytes / ms / 1e6:8.1f} GB/s'
+    print(f'{name:34s} {ms:8.3f} ms  {extra}')
+
+
+cat = torch.randn(m, 3 * h, device=dev).to(bf)
+w = (torch.randn(h, 3 * h, device=dev) * 0.02).to(bf)
+bias = torch.zeros(h, device=dev)
+h1 = torch.empty(m, h, dtype=bf, device=dev)
+timed('NT comb fwd  m x 1024 x 3072', lambda: ops.gemm_nt(cat, w, h1, m, h, 3 * h, 3 * h, 3 * h, h, bias=bias, relu=True),
+      flops=2.0 * m * h * 3 * h)
+w2 = (torch.randn(h, h, device=dev) * 0.03).to(bf)
+h2 = torch.empty(m, h, dtype=bf, device=dev)
+timed('NT expand    m x 1024 x 1024', lambda: ops.gemm_nt(h1, w2, h2, m, h, h, h, h, h, bias=bias, relu=True),
+      flops=2.0 * m * h * h)
+timed('NT dgrad+gate m x 1024 x 1024', lambda: ops.gemm_nt(h1, w2, h2, m, h, h, h, h, h, aux=h1, ldaux=h, aux_mode=2),
+      flops=2.0 * m * h * h)
+dw = torch.zeros(h, 3 * h, device=dev)
+timed('TN wgrad 1024 x 3072 x m', lambda: ops.gemm_tn(h1, cat, dw, h, 3 * h, m, h, 3 * h, 3 * h), flops=2.0 * m * h * 3 * h)
+w3 = (torch.randn(q, h, device=dev) * 0.03).to(bf)
+b3 = torch.zeros(q, device=dev)
+tgt = torch.randint(0, 256, (m,), dtype=torch.uint8, device=dev)
+lse = torch.empty(m, device=dev); lpt = torch.empty(m, device=dev)
+timed('NLL fwd (logits stay in TMEM)', lambda: ops.gemm_nll(0, h2, w3, b3, tgt, m, h, h, h, lse=lse, logp_target=lpt),
+      flops=2.0 * m * q * h)
+rg = torch.full((m,), -1.0 / m, device=dev)
+dl = torch.empty(m, q, dtype=bf, device=dev)
+timed('NLL bwd (dlogits bf16)', lambda: ops.gemm_nll(2, h2, w3, b3, tgt, m, h, h, h, row_grad=rg, dlogits=dl),
+      flops=2.0 * m * q * h)
+x = (torch.rand(64 * 16015, device=dev) * 2 - 1) * 0.99
+timed('quantize_ulaw 64 x 16015', lambda: ops.quantize_ulaw(x, want_i64=True, want_u8=True), nbytes=x.numel() * (4 + 8 + 1))
+timed('colsum m x 1024 bf16', lambda: ops.colsum(h1, m, h, h), nbytes=m * h * 2)
+idx = torch.randint(0, 256, (64, 16003), dtype=torch.uint8, device=dev)
+timed('onehot_rows 64 x 16003 x 256', lambda: ops.onehot_rows(idx), nbytes=idx.numel() * 513)
