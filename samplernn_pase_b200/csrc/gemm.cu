@@ -23,7 +23,10 @@ namespace srnn {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 256;
+// warps 0-3: TMA / MMA / TMEM alloc / spare; then 4 (NLL epilogue: one thread owns a whole row) or 8
+// epilogue warps (two per TMEM lane quadrant, each taking half of the tile's columns)
+template <int EPI>
+__host__ __device__ constexpr int gemm_threads() { return EPI == 1 ? 256 : 384; }
 
 struct GemmParams {
   int m, n, k, batch;
@@ -88,13 +91,16 @@ __device__ __forceinline__ Work decode_work(const GemmParams& p, int w) {
 
 // EPI: 0 = bias / aux / relu / store, 1 = log-softmax + NLL family, 2 = fp32 atomic accumulate
 template <int BN, bool TN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const GemmParams p) {
   using Cfg = SmemCfg<BN>;
   constexpr int S = Cfg::STAGES;
   constexpr uint32_t TMEM_COLS = 2 * BN;
   constexpr uint32_t IDESC = idesc_bf16(BM, BN, TN, TN);
+  constexpr int THREADS = gemm_threads<EPI>();
+  constexpr int EPI_WARPS = THREADS / 32 - 4;
+  constexpr int CHUNKS_PER_WARP = (BN / 32) / (EPI_WARPS / 4);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -119,7 +125,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -128,7 +134,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tmem_relinquish();
   }
   if constexpr (EPI == 1) {
-    for (int i = threadIdx.x; i < 256; i += GEMM_THREADS) sbias[i] = p.bias ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < 256; i += THREADS) sbias[i] = p.bias ? p.bias[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -213,6 +219,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
     const int q = warp & 3;
+    const int c_begin = ((warp - 4) >> 2) * CHUNKS_PER_WARP;   // this warp's share of the tile's columns
+    const int c_end = c_begin + CHUNKS_PER_WARP;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
@@ -226,7 +234,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
       if constexpr (EPI == 0) {
         const int fold_rows = p.n_fold > 0 ? p.n / p.n_fold : 1;
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
           const int n0 = wk.nt * BN + c * 32;
           if (n0 >= p.n) break;
           uint32_t v[32];
@@ -309,7 +317,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
       } else if constexpr (EPI == 2) {
         float* crow = reinterpret_cast<float*>(p.c) + static_cast<long long>(j) * p.ldc;
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
           const int n0 = wk.nt * BN + c * 32;
           if (n0 >= p.n) break;
           uint32_t v[32];
@@ -445,7 +453,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   }
   int grid = p.total_work < sm_count() ? p.total_work : sm_count();
   if (grid < 1) return SRNN_OK;
-  kern<<<grid, GEMM_THREADS, SmemCfg<BN>::TOTAL, stream>>>(ta, tb, p);
+  kern<<<grid, gemm_threads<EPI>(), SmemCfg<BN>::TOTAL, stream>>>(ta, tb, p);
   SRNN_CUDA(cudaGetLastError());
   return SRNN_OK;
 }

@@ -123,6 +123,14 @@ __device__ __forceinline__ float4 ld_dsmem_v4(uint32_t addr) {
                : "memory");
   return v;
 }
+// Push 16 bytes into a peer CTA's shared memory; the peer's mbarrier receives complete_tx(16), so the
+// consumer needs no fence: waiting on its own barrier makes the data visible (like a TMA load).
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float a, float b, float c, float d,
+                                            uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(remote_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(remote_bar)
+               : "memory");
+}
 __device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t remote_bar_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
@@ -187,7 +195,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
     mbar_init(wfull, 1);
     mbar_init(full, 1);
     mbar_init(acc_full, 1);
-    mbar_init(part_ready, C);
+    mbar_init(part_ready, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -262,10 +270,27 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
     const uint32_t ready_addr = smem_u32(part_ready);
     uint32_t acc_phase = 0, part_phase = 0;
 
-    // TMEM partial tile -> this CTA's smem (layout [dst rank][gate][row][8 units], so that a
-    // consumer reads its 8 units of a row with two 16-byte DSMEM loads), cluster handshake, then the
-    // DSMEM sum over the C source ranks.
+    // Cluster reduction, push model: every rank sends, for each destination rank, the 8 columns of
+    // that rank's units straight into the destination's shared memory with st.async (layout
+    // recv[src rank][gate][row][8 units]); the bytes complete on the destination's mbarrier, so there
+    // is no staging buffer, no cluster-scope fence and no remote-load latency on the critical path.
+    // WAR safety: a peer pushes step t+1 only after the grid barrier of step t, i.e. after this CTA
+    // has consumed step t.
+    constexpr uint32_t RECV_BYTES = C * NG * GRU_M * U * 4;
     auto exchange = [&](float (&out)[NG * U], int dbg_step) {
+      if constexpr (C == 1) {                          // no peers: the accumulator columns are the result
+        mbar_wait(acc_full, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(t_addr, v);
+        tmem_ld_wait();
+        tc_fence_before();
+#pragma unroll
+        for (int i = 0; i < NG * U; ++i) out[i] = __uint_as_float(v[i]);
+        return;
+      }
+      if (warp == 2 && lane == 0) mbar_expect_tx(part_ready, RECV_BYTES);
       mbar_wait(acc_full, acc_phase);
       acc_phase ^= 1;
       if (warp == 2 && lane == 0) GRU_TS(4, dbg_step);
@@ -286,11 +311,13 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
                 const int col = (c0 + j) * 32 + e * 8;
                 if (col < NCOLS) {
                   const int g = col / UC, dst = (col % UC) / U;
-                  float4* dp = reinterpret_cast<float4*>(part + (((dst * NG + g) * GRU_M + row) * U));
-                  dp[0] = make_float4(__uint_as_float(v[j][e * 8 + 0]), __uint_as_float(v[j][e * 8 + 1]),
-                                      __uint_as_float(v[j][e * 8 + 2]), __uint_as_float(v[j][e * 8 + 3]));
-                  dp[1] = make_float4(__uint_as_float(v[j][e * 8 + 4]), __uint_as_float(v[j][e * 8 + 5]),
-                                      __uint_as_float(v[j][e * 8 + 6]), __uint_as_float(v[j][e * 8 + 7]));
+                  const uint32_t off = static_cast<uint32_t>((((crank * NG + g) * GRU_M + row) * U) * 4);
+                  const uint32_t ra = mapa(part_addr + off, static_cast<uint32_t>(dst));
+                  const uint32_t rb = mapa(ready_addr, static_cast<uint32_t>(dst));
+                  st_async_v4(ra, __uint_as_float(v[j][e * 8 + 0]), __uint_as_float(v[j][e * 8 + 1]),
+                              __uint_as_float(v[j][e * 8 + 2]), __uint_as_float(v[j][e * 8 + 3]), rb);
+                  st_async_v4(ra + 16, __uint_as_float(v[j][e * 8 + 4]), __uint_as_float(v[j][e * 8 + 5]),
+                              __uint_as_float(v[j][e * 8 + 6]), __uint_as_float(v[j][e * 8 + 7]), rb);
                 }
               }
             }
@@ -298,43 +325,21 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         }
       }
       tc_fence_before();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (warp == 2 && lane == 0) {
-        fence_acq_rel_cluster();                       // one release fence, then relaxed remote arrivals
-#pragma unroll
-        for (int r = 0; r < C; ++r) mbar_arrive_cluster_relaxed(mapa(ready_addr, static_cast<uint32_t>(r)));
-        GRU_TS(7, dbg_step);
-      }
-      mbar_wait_cluster(part_ready, part_phase);
+      if (warp == 2 && lane == 0) GRU_TS(7, dbg_step);
+      mbar_wait(part_ready, part_phase);
       part_phase ^= 1;
       if (warp == 2 && lane == 0) GRU_TS(5, dbg_step);
 #pragma unroll
       for (int i = 0; i < NG * U; ++i) out[i] = 0.f;
       if (lane_ok) {
-        float4 v[C][NG][2];
-#pragma unroll
-        for (int r = 0; r < C; ++r) {
-          const uint32_t base = mapa(part_addr, static_cast<uint32_t>(r));
-#pragma unroll
-          for (int g = 0; g < NG; ++g) {
-            const int off = ((static_cast<int>(crank) * NG + g) * GRU_M + row) * U;
-            if (static_cast<uint32_t>(r) == crank) {            // own partial: plain shared-memory loads
-              v[r][g][0] = *reinterpret_cast<const float4*>(part + off);
-              v[r][g][1] = *reinterpret_cast<const float4*>(part + off + 4);
-            } else {
-              v[r][g][0] = ld_dsmem_v4(base + static_cast<uint32_t>(off * 4));
-              v[r][g][1] = ld_dsmem_v4(base + static_cast<uint32_t>(off * 4 + 16));
-            }
-          }
-        }
 #pragma unroll
         for (int r = 0; r < C; ++r)
 #pragma unroll
           for (int g = 0; g < NG; ++g) {
-            out[g * U + 0] += v[r][g][0].x; out[g * U + 1] += v[r][g][0].y;
-            out[g * U + 2] += v[r][g][0].z; out[g * U + 3] += v[r][g][0].w;
-            out[g * U + 4] += v[r][g][1].x; out[g * U + 5] += v[r][g][1].y;
-            out[g * U + 6] += v[r][g][1].z; out[g * U + 7] += v[r][g][1].w;
+            const float4* rp = reinterpret_cast<const float4*>(part + ((r * NG + g) * GRU_M + row) * U);
+            const float4 a = rp[0], b = rp[1];
+            out[g * U + 0] += a.x; out[g * U + 1] += a.y; out[g * U + 2] += a.z; out[g * U + 3] += a.w;
+            out[g * U + 4] += b.x; out[g * U + 5] += b.y; out[g * U + 6] += b.z; out[g * U + 7] += b.w;
           }
       }
     };

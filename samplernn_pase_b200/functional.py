@@ -18,6 +18,23 @@ def _empty(*shape, dtype=BF16, device=None):
 
 
 # ----------------------------------------------------------------------------------------------
+# sum of the negative log-likelihoods (runner.py:52 with reduction='sum') on our own reduction kernel
+# ----------------------------------------------------------------------------------------------
+class NegSumFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logp_target):
+        flat = logp_target.contiguous().view(-1)
+        one = torch.ones(1, dtype=torch.uint8, device=flat.device)
+        out = ops.masked_nll_mean(flat, one, flat.numel())          # [-mean, count]
+        ctx.shape = logp_target.shape
+        return out[0] * out[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        return (-g).expand(ctx.shape).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
 # CondsMixer (model.py:60-65): conds = Linear([speaker_emb | utt])
 # ----------------------------------------------------------------------------------------------
 class CondsMixFn(torch.autograd.Function):
@@ -94,7 +111,7 @@ class FrameTierFn(torch.autograd.Function):
     h_n (layers,B,H) fp32, not differentiable - the reference detaches it, model.py:276)."""
 
     @staticmethod
-    def forward(ctx, xq_u8, x_off, lut, frames, conds, upper, h_init, fs, ratio,
+    def forward(ctx, xq_u8, x_off, lut, frames, conds, upper, h_init, fs, ratio, into_cat,
                 xg, xv, xb, cg, cv, cb, ug, uv, ub, *rnn):
         dev = conds.device
         b, l, c = conds.shape
@@ -150,8 +167,15 @@ class FrameTierFn(torch.autograd.Function):
         wu_t = _empty(h, r * h, device=dev)
         inv_u = _empty(h, dtype=F32, device=dev)
         ops.weight_prep(uv, ug, (h, h, r), wu, (1, h, h * h), wu_t, (r * h, 1, h), inv_norm=inv_u)
-        up = _empty(b, t * r, h, device=dev)
-        ops.gemm_nt(x_l, wu, up, b * t, r * h, h, h, h, r * h, bias=ub.t().contiguous().view(-1))
+        if into_cat and h % 32 == 0:
+            # lowest tier: write the upsampled conditioning straight into column block [2H,3H) of the
+            # sample-level concat buffer (model.py:196-199) - the returned tensor is a strided view of it
+            cat = _empty(b * t * r, 3 * h, device=dev)
+            up = cat[:, 2 * h:].view(b, t * r, h)
+            ops.gemm_nt(x_l, wu, up, b * t, r * h, h, h, h, 3 * h, bias=ub.t().contiguous().view(-1), n_fold=h)
+        else:
+            up = _empty(b, t * r, h, device=dev)
+            ops.gemm_nt(x_l, wu, up, b * t, r * h, h, h, h, r * h, bias=ub.t().contiguous().view(-1))
 
         ctx.dims = (b, t, l, c, h, fs, r, kp, cp, layers, upper is not None)
         ctx.saved_layers = saved_layers
@@ -205,7 +229,7 @@ class FrameTierFn(torch.autograd.Function):
             dconds = _zeros(b, l, c, device=dev)
             ops.tier_input_bwd(dc_rows, b, t, 0, l, c, cp, dconds)
         d_upper = du.view(b, t, h) if has_upper else None
-        return (None, None, None, None, dconds, d_upper, dh0, None, None,
+        return (None, None, None, None, dconds, d_upper, dh0, None, None, None,
                 d_xg.view_as(xg), d_xv, d_bias, d_cg.view_as(cg), d_cv, d_bias.clone(),
                 d_ug.view_as(ug), d_uv, d_ub, *rnn_grads)
 
@@ -239,7 +263,13 @@ class SampleLevelFn(torch.autograd.Function):
         table = _empty(h, r0 * q, device=dev)
         for k in range(r0):
             ops.gemm_nt(we[:, k * q:], e_b, table[:, k * q:], h, q, q, r0 * q, q, r0 * q)
-        cat = _empty(m, 3 * h, device=dev)
+        shared_cat = (upper.dim() == 3 and upper.stride(2) == 1 and upper.stride(1) == 3 * h and
+                      upper.stride(0) == rf * 3 * h and upper.storage_offset() == 2 * h and
+                      upper.untyped_storage().nbytes() >= m * 3 * h * 2)
+        if shared_cat:      # the tier below already wrote column block [2H,3H) of this buffer
+            cat = torch.as_strided(upper, (m, 3 * h), (3 * h, 1), 0)
+        else:
+            cat = _empty(m, 3 * h, device=dev)
         ops.gemm_nt(onehot, table, cat, rf, h, r0 * q, q, r0 * q, 3 * h, batch=b, a_bs=w * q, c_bs=rf * 3 * h)
 
         # conditioning at frame rate, then repeated FS times into the concat buffer
@@ -251,7 +281,8 @@ class SampleLevelFn(torch.autograd.Function):
         c_frame = _empty(b * l, h, device=dev)
         ops.gemm_nt(conds_b, wcs, c_frame, b * l, h, cp, cp, cp, h, bias=csb.contiguous())
         ops.repeat_rows(c_frame, b * l, h, h, fsz, cat[:, h:], 3 * h)
-        cat[:, 2 * h:] = upper.reshape(m, h)
+        if not shared_cat:
+            cat[:, 2 * h:] = upper.reshape(m, h)
 
         wcomb = _empty(h, 3 * h, device=dev)
         wcomb_t = _empty(3 * h, h, device=dev)

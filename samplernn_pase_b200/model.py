@@ -145,9 +145,9 @@ class FrameLevelLayer(torch.nn.Module):
         self.rnn = _RnnParams(h, rnn_layers)
         self.upsample = _normed(_uniform_(torch.empty(h, h, ratio), math.sqrt(6.0 / h)))          # model.py:124-126
 
-    def _tier(self, xq_u8, x_off, lut, frames, conds, upper, h_init):
+    def _tier(self, xq_u8, x_off, lut, frames, conds, upper, h_init, into_cat=False):
         return FrameTierFn.apply(
-            xq_u8, x_off, lut, frames, conds, upper, h_init, self.input_samples, self.ratio,
+            xq_u8, x_off, lut, frames, conds, upper, h_init, self.input_samples, self.ratio, into_cat,
             self.x_expand.weight_g, self.x_expand.weight_v, self.x_expand.bias,
             self.conds_expand.weight_g, self.conds_expand.weight_v, self.conds_expand.bias,
             self.upsample.weight_g, self.upsample.weight_v, self.upsample_bias, *self.rnn.flat(self.rnn_layers))
@@ -264,7 +264,8 @@ class SampleRNNModel(torch.nn.Module):
             use = [1 if (r == 0 and valid[i] and self._state[n] is not None) else 0 for i, r in enumerate(reset_l)]
             use_t = torch.tensor(use, dtype=torch.uint8).to(dev, non_blocking=True)
             h_init = layer.initial_state(self._state[n] if any(use) else None, use_t)
-            upper, hn = layer._tier(xq8, fs_top - layer.input_samples, lut, None, conds, upper, h_init)
+            upper, hn = layer._tier(xq8, fs_top - layer.input_samples, lut, None, conds, upper, h_init,
+                                    into_cat=(n == 0))
             self._state[n] = hn.detach()
             self._state_valid[n] = [r in (0, 1) for r in reset_l]               # model.py:245-250
 

@@ -138,7 +138,11 @@ class DataParallelTrainer:
         self.flat.zero_grad()
         y_hat, tgt = self.model(x, y, utt_conds, info, reset)
         # local SUM of the NLL; the mean's 1/N_global is folded into the optimizer's grad_scale
-        local_sum = torch.nn.functional.nll_loss(y_hat.view(-1, y_hat.size(2)), tgt.view(-1), reduction='sum')
+        if y_hat.size(2) == 1:      # fused-loss mode: y_hat already holds log p(target)
+            from .functional import NegSumFn
+            local_sum = NegSumFn.apply(y_hat)
+        else:
+            local_sum = torch.nn.functional.nll_loss(y_hat.view(-1, y_hat.size(2)), tgt.view(-1), reduction='sum')
         stats = torch.stack([local_sum.detach(), torch.tensor(float(tgt.numel()), device=local_sum.device)])
         local_sum.backward()
         if self.world > 1:
