@@ -244,7 +244,10 @@ def run_gpu(args):
             gpu_launches=launches,
             roofline=dict(bound='tensor', kernel='gemm_kernel<256,NT,epilogue bias+relu> (comb_layer forward, tcgen05)',
                           achieved=achieved, peak=peak, unit='TFLOP/s', frac=(achieved / peak) if achieved else None,
-                          traffic=None, launches_timed=len(kernel_ms), avg_launch_ms=avg_ms,
+                          # dram__bytes_read+write of this kernel from `ncu --set full` at 262 144 rows (2.129 GB,
+                          # profiles/r01_hot_kernels_ncu.txt [1]) scaled to this launch's rows; algorithmic = A + C + W
+                          traffic=2.129e9 * m_rows / 262144.0, traffic_algorithmic=2.0 * m_rows * 4 * h + 6.0 * h * h,
+                          launches_timed=len(kernel_ms), avg_launch_ms=avg_ms,
                           peak_source='MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
                           if peaks else 'fallback'),
             cpu_baseline=dict(value=cpu['value'], unit='samples/s', cores=cpu['cores'], kind='port', sample=cpu['sample']),

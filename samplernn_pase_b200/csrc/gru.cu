@@ -28,7 +28,8 @@
 
 namespace srnn {
 
-constexpr int GRU_THREADS = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int GRU_THREADS = 224;   // warp 0 TMA, warps 1 and 6 MMA issuers, warps 2-5 epilogue
+constexpr int GRU_MMA_WARPS = 2;   // tcgen05.mma issue is ~60 cycles per instruction from one thread
 constexpr int GRU_U = 8;           // hidden units finalised per CTA
 constexpr int GRU_M = 64;          // batch rows per launch (MMA M)
 constexpr int GRU_SLOT = GRU_M * 128;   // one [64 rows][64 bf16] K block
@@ -161,8 +162,12 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
   constexpr int UC = U * C;                          // units owned by the cluster
   constexpr int NG = BWD ? 1 : 3;
   constexpr int NCOLS = NG * UC;                     // MMA N
-  constexpr int NCH = (NCOLS + 31) / 32;             // 32-column TMEM load chunks
-  constexpr uint32_t TMEM_COLS = NCOLS <= 32 ? 32 : (NCOLS <= 64 ? 64 : (NCOLS <= 128 ? 128 : 256));
+  constexpr int NB = (NCOLS + 31) / 32;              // 32-column TMEM load batches per partial
+  // one partial accumulator per issuing warp: partial w lives at columns [w*NCOLS, (w+1)*NCOLS); the
+  // epilogue reads whole 32-column chunks, so the allocation covers the over-read of the last chunk
+  constexpr int TMEM_NEED = (GRU_MMA_WARPS - 1) * NCOLS + NB * 32;
+  constexpr uint32_t TMEM_COLS = TMEM_NEED <= 32 ? 32 : (TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 :
+                                 (TMEM_NEED <= 256 ? 256 : 512)));
   constexpr uint32_t IDESC = idesc_bf16(GRU_M, NCOLS, false, false);
   constexpr int WBLOCK = NCOLS * 128;                // resident weight bytes per K block
 
@@ -194,7 +199,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
     tma_prefetch_desc(&tma_x);
     mbar_init(wfull, 1);
     mbar_init(full, 1);
-    mbar_init(acc_full, 1);
+    mbar_init(acc_full, GRU_MMA_WARPS);
     mbar_init(part_ready, 1);
     fence_barrier_init();
   }
@@ -233,9 +238,11 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 6) {
     if (lane == 0) {
-      // ------------------------------ MMA issuer ------------------------------
+      // ------------------------------ MMA issuers: K steps dealt round-robin to 2 threads, each with
+      // its own partial accumulator (summed by the epilogue) --------------------
+      const int mw = warp == 1 ? 0 : 1;
       mbar_wait(wfull, 0);
       const uint64_t a_base = smem_desc_sw128(smem_u32(hbuf), 16, 1024);
       const uint64_t b_base = smem_desc_sw128(smem_u32(sw), 16, 1024);
@@ -244,17 +251,17 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         if (BWD && s == 0) continue;
         mbar_wait(full, phase);
         phase ^= 1;
-        GRU_TS(2, s);
+        if (mw == 0) GRU_TS(2, s);
         tc_fence_after();
         for (int kb = 0; kb < KBC; ++kb) {
 #pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16) {
-            umma_bf16(tmem_base, a_base + ((kb * GRU_SLOT + k16 * 32) >> 4),
-                      b_base + ((kb * WBLOCK + k16 * 32) >> 4), IDESC, (kb | k16) ? 1u : 0u);
+          for (int k16 = mw; k16 < 4; k16 += GRU_MMA_WARPS) {
+            umma_bf16(tmem_base + mw * NCOLS, a_base + ((kb * GRU_SLOT + k16 * 32) >> 4),
+                      b_base + ((kb * WBLOCK + k16 * 32) >> 4), IDESC, (kb > 0 || k16 >= GRU_MMA_WARPS) ? 1u : 0u);
           }
         }
         umma_commit(acc_full);
-        GRU_TS(3, s);
+        if (mw == 0) GRU_TS(3, s);
       }
     }
     __syncwarp();
@@ -282,12 +289,19 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         mbar_wait(acc_full, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32(t_addr, v);
+        static_assert(NCOLS <= 32, "C == 1: one 32-column chunk per partial");
+        uint32_t v[GRU_MMA_WARPS][32];
+#pragma unroll
+        for (int pw = 0; pw < GRU_MMA_WARPS; ++pw) tmem_ld32(t_addr + pw * NCOLS, v[pw]);
         tmem_ld_wait();
         tc_fence_before();
 #pragma unroll
-        for (int i = 0; i < NG * U; ++i) out[i] = __uint_as_float(v[i]);
+        for (int i = 0; i < NG * U; ++i) {
+          float acc = 0.f;
+#pragma unroll
+          for (int pw = 0; pw < GRU_MMA_WARPS; ++pw) acc += __uint_as_float(v[pw][i]);
+          out[i] = acc;
+        }
         return;
       }
       if (warp == 2 && lane == 0) mbar_expect_tx(part_ready, RECV_BYTES);
@@ -296,30 +310,29 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       if (warp == 2 && lane == 0) GRU_TS(4, dbg_step);
       tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < NCH; c0 += 3) {            // <= 96 columns in flight, ONE wait per batch
-        uint32_t v[3][32];
+      for (int bi = 0; bi < NB; ++bi) {                // 32 result columns per batch, ONE wait per batch
+        uint32_t v[GRU_MMA_WARPS][32];
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
-          if (c0 + j < NCH) tmem_ld32(t_addr + (c0 + j) * 32, v[j]);
+        for (int pw = 0; pw < GRU_MMA_WARPS; ++pw) tmem_ld32(t_addr + pw * NCOLS + bi * 32, v[pw]);
         tmem_ld_wait();
         if (lane_ok) {
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            if (c0 + j < NCH) {
+          for (int e = 0; e < 4; ++e) {                 // groups of 8 columns = one (gate, dst rank) pair
+            const int col = bi * 32 + e * 8;
+            if (col < NCOLS) {
+              float f[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {             // groups of 8 columns = one (gate, dst rank) pair
-                const int col = (c0 + j) * 32 + e * 8;
-                if (col < NCOLS) {
-                  const int g = col / UC, dst = (col % UC) / U;
-                  const uint32_t off = static_cast<uint32_t>((((crank * NG + g) * GRU_M + row) * U) * 4);
-                  const uint32_t ra = mapa(part_addr + off, static_cast<uint32_t>(dst));
-                  const uint32_t rb = mapa(ready_addr, static_cast<uint32_t>(dst));
-                  st_async_v4(ra, __uint_as_float(v[j][e * 8 + 0]), __uint_as_float(v[j][e * 8 + 1]),
-                              __uint_as_float(v[j][e * 8 + 2]), __uint_as_float(v[j][e * 8 + 3]), rb);
-                  st_async_v4(ra + 16, __uint_as_float(v[j][e * 8 + 4]), __uint_as_float(v[j][e * 8 + 5]),
-                              __uint_as_float(v[j][e * 8 + 6]), __uint_as_float(v[j][e * 8 + 7]), rb);
-                }
+              for (int i = 0; i < 8; ++i) {
+                f[i] = 0.f;
+#pragma unroll
+                for (int pw = 0; pw < GRU_MMA_WARPS; ++pw) f[i] += __uint_as_float(v[pw][e * 8 + i]);
               }
+              const int g = col / UC, dst = (col % UC) / U;
+              const uint32_t off = static_cast<uint32_t>((((crank * NG + g) * GRU_M + row) * U) * 4);
+              const uint32_t ra = mapa(part_addr + off, static_cast<uint32_t>(dst));
+              const uint32_t rb = mapa(ready_addr, static_cast<uint32_t>(dst));
+              st_async_v4(ra, f[0], f[1], f[2], f[3], rb);
+              st_async_v4(ra + 16, f[4], f[5], f[6], f[7], rb);
             }
           }
         }
