@@ -139,8 +139,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 def run_gpu(args):
     import torch.distributed as dist
-    from oracle import samplernn_oracle as O          # synthetic workload generator + cpu_baseline leg only
-    from samplernn_pase_b200 import SampleRNNModel, ops
+    from samplernn_pase_b200 import SampleRNNModel, ops, synthetic
     from samplernn_pase_b200.parallel import DataParallelTrainer
 
     rank = int(os.environ.get('RANK', '0'))
@@ -156,18 +155,18 @@ def run_gpu(args):
     torch.manual_seed(1234)
     model = SampleRNNModel(fused_loss=True, **model_kwargs()).to(dev)
     trainer = DataParallelTrainer(model, lr=1e-4)
-    spec = O.ModelSpec(RATIOS, LAYERS, HIDDEN, SEQ_LEN)
+    fs = int(model.frame_size)
+    rf = int(model.receptive_field)
     b = SLOTS_PER_GPU
     chunks = 8
-    wav, conds, spk = O.synthetic_utterances(spec, b, chunks, seed=4321 + rank)
+    wav, conds, spk = synthetic.synthetic_utterances(fs, rf, SEQ_LEN, b, chunks, seed=4321 + rank, n_speakers=N_SPEAKERS)
     info = [{'speaker': {'index': int(s)}} for s in spk]
     host = []
     for k in range(chunks):
-        x, y, c = O.chunk_of(spec, wav, conds, k)
+        x, y, c = synthetic.chunk_of(fs, rf, SEQ_LEN, wav, conds, k)
         host.append((x.pin_memory(), y.pin_memory(), c.pin_memory()))
     resident = [tuple(t.to(dev) for t in h) for h in host]
     resets = [torch.ones(b, dtype=torch.int64), torch.zeros(b, dtype=torch.int64)]
-    rf = spec.receptive_field
     global_rows = b * rf * world
 
     def barrier():

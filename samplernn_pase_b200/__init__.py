@@ -3,7 +3,7 @@
 
 Importing the package does not touch CUDA; the first kernel call loads ``libsrnn_b200.so`` and
 raises if it is missing (there is no CPU or eager fallback)."""
-from . import _lib, ops                                                        # noqa: F401
+from . import _lib, ops, synthetic                                             # noqa: F401
 from .model import CondsMixer, FrameLevelLayer, SampleLevelLayer, SampleRNNModel  # noqa: F401
 from .optimizer import AdamClipped                                             # noqa: F401
 from .utils import SampleRNNQuantizer                                          # noqa: F401

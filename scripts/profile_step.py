@@ -9,8 +9,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench                                                  # noqa: E402
-from oracle import samplernn_oracle as O                      # noqa: E402  (workload generator only)
-from samplernn_pase_b200 import SampleRNNModel, _lib, ops     # noqa: E402
+from samplernn_pase_b200 import SampleRNNModel, _lib, ops, synthetic   # noqa: E402
 from samplernn_pase_b200.parallel import DataParallelTrainer  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -21,12 +20,12 @@ a = ap.parse_args()
 torch.manual_seed(1234)
 model = SampleRNNModel(fused_loss=True, **bench.model_kwargs(a.seq_len)).cuda()
 trainer = DataParallelTrainer(model)
-spec = O.ModelSpec(bench.RATIOS, bench.LAYERS, bench.HIDDEN, a.seq_len)
-wav, conds, spk = O.synthetic_utterances(spec, a.batch, a.steps + 2)
+fs, rf = int(model.frame_size), int(model.receptive_field)
+wav, conds, spk = synthetic.synthetic_utterances(fs, rf, a.seq_len, a.batch, a.steps + 2)
 info = [{'speaker': {'index': int(s)}} for s in spk]
-rows = a.batch * spec.receptive_field
+rows = a.batch * rf
 for k in range(a.steps + 2):
-    x, y, c = (t.cuda() for t in O.chunk_of(spec, wav, conds, k))
+    x, y, c = (t.cuda() for t in synthetic.chunk_of(fs, rf, a.seq_len, wav, conds, k))
     if k == 2:
         torch.cuda.synchronize()
         _lib.profile_log = []
