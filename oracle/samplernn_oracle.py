@@ -322,12 +322,21 @@ def forward(p: Params, spec: ModelSpec, x: Tensor, y: Tensor, utt_conds: Tensor,
     call so every chunk starts from ``rnn_h0``); ``carry=True`` is the documented intent
     (O-B, README.md:17-21).  Returns (log-probs of valid slots, targets of valid slots,
     new CarryState, dict of intermediates)."""
+    xq = quantize(x, spec.ulaw, spec.q_levels)                                       # model.py:260
+    yq = quantize(y, spec.ulaw, spec.q_levels)
+    return forward_indices(p, spec, xq, yq, utt_conds, speaker_ids, reset, state, carry, speaker_vectors, fast)
+
+
+def forward_indices(p: Params, spec: ModelSpec, xq: Tensor, yq: Tensor, utt_conds: Tensor, speaker_ids: Tensor,
+                    reset: Sequence[int], state: Optional[CarryState] = None, carry: bool = True,
+                    speaker_vectors: Optional[Tensor] = None, fast: bool = False):
+    """``forward`` after the quantiser (model.py:263-287): takes the int64 indices directly.  Used to
+    teacher-force a *generated* index sequence (SURVEY probe P8)."""
     reset = [int(r) for r in reset]
     if state is None or not carry:
         state = CarryState()
     new_state = CarryState()
-    xq = quantize(x, spec.ulaw, spec.q_levels)                                       # model.py:260
-    yq = quantize(y, spec.ulaw, spec.q_levels)
+    x, y = xq, yq
     conds = conds_mixer(p, utt_conds, speaker_ids, spec.kind, speaker_vectors)       # model.py:263
     fs_top = spec.frame_size
     rf = y.shape[1]

@@ -172,6 +172,34 @@ def test_medium_size_vs_cpu_oracle():
     assert r <= 0.08 and cs >= 0.997, (r, cs)
 
 
+def test_generation_is_consistent_with_teacher_forcing():
+    """SURVEY probe P8: the log-probabilities each generated sample was drawn from must equal the
+    teacher-forced log-probabilities of the generated sequence (RNG streams need not match the reference).
+    Checked against the CPU oracle's forward on the generated indices."""
+    from samplernn_pase_b200 import SampleRNNModel
+    spec = O.ModelSpec([2, 2, 3], [1, 2, 1], [64, 64, 64], 3)
+    params = O.init_params(spec, conds_speaker_n=5, perturb=0.1)
+    model = SampleRNNModel('embedding', 5, 15, 'acoustic', [9, 5, 4, 3], 10, 50, 3, [2, 2, 3], [1, 2, 1], [64, 64, 64],
+                           True, 256).cuda()
+    model.load_state_dict(params)
+    bsz, t, fs = 3, 3, 12
+    utt = torch.randn(bsz, t, 43, generator=torch.Generator().manual_seed(3))
+    info = [{'speaker': {'index': i}} for i in range(bsz)]
+    gen = torch.Generator(device='cuda').manual_seed(5)
+    y, logp = model.test(utt.cuda(), info, return_logp=True, generator=gen)
+    assert y.shape == (bsz, (t + 1) * fs) and y.dtype == torch.int64
+    assert bool((y[:, :fs] == 128).all())                                      # FS leading quantize_zero()
+    y = y.cpu()
+    rf = t * fs
+    ref = O.forward_indices(params, spec, y[:, :rf + fs - 1], y[:, fs:fs + rf], utt, torch.arange(bsz), [1] * bsz)[0]
+    assert logp.shape == ref.shape
+    d = float((logp.cpu() - ref).abs().max())
+    report(f'generation vs teacher forcing (3 tiers, H=64, {rf} samples): max|dlogp| {d:.3e}')
+    assert d <= 0.05, d
+    single = model.test(utt[:1].cuda(), info[0])                               # the reference's calling convention
+    assert single.shape == (1, (t + 1) * fs)
+
+
 def test_chunked_equals_unchunked_with_carry():
     """Size-independent property (SURVEY probe P2): K chunks with carry == one long forward."""
     from samplernn_pase_b200 import SampleRNNModel
