@@ -186,6 +186,12 @@ typedef struct srnn_gru_args {
                             1 = do not wait on the grid counter, 2 = skip TMA loads and MMAs,
                             4 = skip the per-step global loads/stores of the epilogue */
   uint64_t* debug_ts;    /* NULL, or [256][8] clock64 stamps of CTA 0's pipeline events (profiling aid) */
+  /* LSTM extension (cell = 1; no reference counterpart, torch.nn.LSTM semantics, gates i,f,g,o): every
+   * "3H" above becomes 4H, `gates` is [batch*steps, 5H] (i, f, g, o, c_t). */
+  int32_t cell;          /* 0 = GRU (reference), 1 = LSTM */
+  float* c_state;        /* LSTM fwd: fp32 [batch, H] cell state, in = c_init, out = c_T */
+  const float* c_init;   /* LSTM bwd: the cell state the forward started from */
+  float* dc0;            /* LSTM bwd out: dL/dc_init */
 } srnn_gru_args;
 
 int srnn_gru_forward(const srnn_gru_args* args, srnn_stream_t stream);

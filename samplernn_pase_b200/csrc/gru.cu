@@ -47,6 +47,9 @@ struct GruParams {
   __nv_bfloat16* dgi;
   __nv_bfloat16* dgh;
   float* dh0;
+  float* c_state;                  // LSTM: fp32 [batch, H] cell state, in = c_init, out = c_T
+  const float* c_init;             // LSTM backward: the cell state the forward started from
+  float* dc0;                      // LSTM backward: dL/dc_init
   uint32_t* sync;
   int flags;
   unsigned long long* ts;          // debug timestamps [256][8] of CTA 0 (nullable)
@@ -155,12 +158,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   fence_acq_rel_cluster();                           // one acquire fence after the relaxed polling
 }
 
-template <bool BWD, int C>
+// LSTM = false: GRU (gates r,z,n; 3H pre-activations).  LSTM = true: LSTM (gates i,f,g,o; 4H), an
+// extension with no reference counterpart (BASELINE config 3; torch.nn.LSTM semantics, see oracle).
+template <bool BWD, int C, bool LSTM>
 __global__ void __launch_bounds__(GRU_THREADS, 1)
 gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_x, const GruParams p) {
   constexpr int U = GRU_U;
   constexpr int UC = U * C;                          // units owned by the cluster
-  constexpr int NG = BWD ? 1 : 3;
+  constexpr int GATES = LSTM ? 4 : 3;
+  constexpr int NG = BWD ? 1 : GATES;
   constexpr int NCOLS = NG * UC;                     // MMA N
   constexpr int NB = (NCOLS + 31) / 32;              // 32-column TMEM load batches per partial
   // one partial accumulator per issuing warp: partial w lives at columns [w*NCOLS, (w+1)*NCOLS); the
@@ -220,7 +226,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       for (int kb = 0; kb < KBC; ++kb)
         for (int g = 0; g < NG; ++g)
           tma_load_2d(sw + kb * WBLOCK + g * UC * 128, &tma_w, wfull, (kb0 + kb) * 64,
-                      (BWD ? 0 : g * H) + cluster_id * UC);
+                      (BWD ? 0 : g * H) + cluster_id * UC);   // gate g rows of W_hh (fwd)
     }
     const uint32_t bytes = static_cast<uint32_t>(KBC) * static_cast<uint32_t>(B) * 128u;
     if (lane == 0) {
@@ -357,7 +363,132 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       }
     };
 
-    if constexpr (!BWD) {
+    if constexpr (!BWD && LSTM) {
+      // ---------------- LSTM forward: c' = f c + i g,  h' = o tanh(c') ----------------
+      float h[U], c[U], bi[U], bf[U], bg[U], bo[U];
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        h[i] = row_ok ? p.h_state[static_cast<long long>(row) * H + u0 + i] : 0.f;
+        c[i] = row_ok ? p.c_state[static_cast<long long>(row) * H + u0 + i] : 0.f;
+        bi[i] = p.b_hh[u0 + i];
+        bf[i] = p.b_hh[H + u0 + i];
+        bg[i] = p.b_hh[2 * H + u0 + i];
+        bo[i] = p.b_hh[3 * H + u0 + i];
+      }
+      for (int t = 0; t < T; ++t) {
+        const long long rt = static_cast<long long>(row) * T + t;
+        float xi[U], xf[U], xg[U], xo[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) xi[i] = xf[i] = xg[i] = xo[i] = 0.f;
+        if (io) {
+          const __nv_bfloat16* gp = p.gi + rt * 4 * H + u0;
+          load_bf16x8(gp, xi);
+          load_bf16x8(gp + H, xf);
+          load_bf16x8(gp + 2 * H, xg);
+          load_bf16x8(gp + 3 * H, xo);
+        }
+        float acc[4 * U];
+        exchange(acc, t);
+        float gi_[U], gf_[U], gg_[U], go_[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          gi_[i] = sigmoid_fast(xi[i] + acc[i] + bi[i]);
+          gf_[i] = sigmoid_fast(xf[i] + acc[U + i] + bf[i]);
+          gg_[i] = tanh_fast(xg[i] + acc[2 * U + i] + bg[i]);
+          go_[i] = sigmoid_fast(xo[i] + acc[3 * U + i] + bo[i]);
+          c[i] = gf_[i] * c[i] + gi_[i] * gg_[i];
+          h[i] = go_[i] * tanh_fast(c[i]);
+        }
+        if (io) store_bf16x8(p.h_ext + (static_cast<long long>(t + 1) * EB + row) * H + u0, h);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 2 && lane == 0) red_release_gpu_add(p.sync, 1u);
+        if (p.hall && io) store_bf16x8(p.hall + rt * H + u0, h);
+        if (p.gates && io) {                           // saved for backward: i, f, g, o, c_t  (5H per row)
+          __nv_bfloat16* sp = p.gates + rt * 5 * H + u0;
+          store_bf16x8(sp, gi_);
+          store_bf16x8(sp + H, gf_);
+          store_bf16x8(sp + 2 * H, gg_);
+          store_bf16x8(sp + 3 * H, go_);
+          store_bf16x8(sp + 4 * H, c);
+        }
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          p.h_state[static_cast<long long>(row) * H + u0 + i] = h[i];
+          p.c_state[static_cast<long long>(row) * H + u0 + i] = c[i];
+        }
+      }
+    } else if constexpr (BWD && LSTM) {
+      // ---------------- LSTM backward ----------------
+      float carry_c[U];
+#pragma unroll
+      for (int i = 0; i < U; ++i) carry_c[i] = 0.f;
+      for (int s = 0; s <= T; ++s) {
+        const int t = T - 1 - s;
+        const long long rt = static_cast<long long>(row) * T + t;
+        float dh[U], gi_[U], gf_[U], gg_[U], go_[U], ct[U], cp[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) dh[i] = gi_[i] = gf_[i] = gg_[i] = go_[i] = ct[i] = cp[i] = 0.f;
+        if (io && t >= 0) {
+          load_bf16x8(p.dh_out + rt * H + u0, dh);
+          const __nv_bfloat16* sp = p.gates + rt * 5 * H + u0;
+          load_bf16x8(sp, gi_);
+          load_bf16x8(sp + H, gf_);
+          load_bf16x8(sp + 2 * H, gg_);
+          load_bf16x8(sp + 3 * H, go_);
+          load_bf16x8(sp + 4 * H, ct);
+          if (t > 0) {
+            load_bf16x8(p.gates + (rt - 1) * 5 * H + 4 * H + u0, cp);
+          } else {
+#pragma unroll
+            for (int i = 0; i < U; ++i) cp[i] = p.c_init[static_cast<long long>(row) * H + u0 + i];
+          }
+        }
+        float d[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) d[i] = 0.f;
+        if (s > 0) exchange(d, s);
+        if (t < 0) {
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+              p.dh0[static_cast<long long>(row) * H + u0 + i] = d[i];
+              p.dc0[static_cast<long long>(row) * H + u0 + i] = carry_c[i];
+            }
+          }
+          break;
+        }
+        float pi[U], pf[U], pg[U], po[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          const float dht = dh[i] + d[i];
+          const float tc = tanh_fast(ct[i]);
+          const float dc = dht * go_[i] * (1.f - tc * tc) + carry_c[i];
+          carry_c[i] = dc * gf_[i];
+          pi[i] = dc * gg_[i] * gi_[i] * (1.f - gi_[i]);
+          pf[i] = dc * cp[i] * gf_[i] * (1.f - gf_[i]);
+          pg[i] = dc * gi_[i] * (1.f - gg_[i] * gg_[i]);
+          po[i] = dht * tc * go_[i] * (1.f - go_[i]);
+        }
+        if (io) {
+          __nv_bfloat16* ghp = p.dgh + (static_cast<long long>(t) * EB + row) * 4 * H + u0;   // exchanged
+          store_bf16x8(ghp, pi);
+          store_bf16x8(ghp + H, pf);
+          store_bf16x8(ghp + 2 * H, pg);
+          store_bf16x8(ghp + 3 * H, po);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 2 && lane == 0) red_release_gpu_add(p.sync, 1u);
+        if (io) {                                               // same values, batch-major, for the GEMMs
+          __nv_bfloat16* gip = p.dgi + rt * 4 * H + u0;
+          store_bf16x8(gip, pi);
+          store_bf16x8(gip + H, pf);
+          store_bf16x8(gip + 2 * H, pg);
+          store_bf16x8(gip + 3 * H, po);
+        }
+      }
+    } else if constexpr (!BWD) {
       float h[U], bhr[U], bhz[U], bhn[U];
 #pragma unroll
       for (int i = 0; i < U; ++i) {
@@ -480,18 +611,18 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <bool BWD, int C>
+template <bool BWD, int C, bool LSTM>
 static size_t gru_smem_bytes(int kbc) {
-  const int ncols = (BWD ? 1 : 3) * GRU_U * C;
+  const int ncols = (BWD ? 1 : (LSTM ? 4 : 3)) * GRU_U * C;
   return static_cast<size_t>(kbc) * ncols * 128 + static_cast<size_t>(kbc) * GRU_SLOT +
          static_cast<size_t>(ncols) * GRU_M * 4 + 256 + 1024;
 }
 
 // Can H/8 CTAs in clusters of C all be resident at once (they spin on one another)?
-template <bool BWD, int C>
+template <bool BWD, int C, bool LSTM>
 static bool gru_fits(int H, int kbc) {
-  auto kern = gru_kernel<BWD, C>;
-  const size_t smem = gru_smem_bytes<BWD, C>(kbc);
+  auto kern = gru_kernel<BWD, C, LSTM>;
+  const size_t smem = gru_smem_bytes<BWD, C, LSTM>(kbc);
   if (smem > 227 * 1024) return false;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     cudaGetLastError();
@@ -525,17 +656,18 @@ static bool gru_fits(int H, int kbc) {
   return clusters * C >= ctas;
 }
 
-template <bool BWD, int C>
+template <bool BWD, int C, bool LSTM>
 static int launch_gru(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
+  constexpr int GATES = LSTM ? 4 : 3;
   const int H = a->hidden, T = a->steps, B = a->batch;
-  const int K = BWD ? 3 * H : H;
+  const int K = BWD ? GATES * H : H;
   const int ctas = H / GRU_U;
-  const size_t smem = gru_smem_bytes<BWD, C>(kbc);
+  const size_t smem = gru_smem_bytes<BWD, C, LSTM>(kbc);
 
   CUtensorMap tw, tx;
   {
     // forward: W_hh [3H, H] rows = gate rows; backward: W_hh^T [H, 3H] rows = units
-    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)(BWD ? H : 3 * H)};
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)(BWD ? H : GATES * H)};
     const uint64_t strides[1] = {(uint64_t)K * 2};
     const uint32_t box[2] = {64, (uint32_t)(GRU_U * C)};
     int rc = make_tmap_bf16(&tw, a->w_hh, 2, dims, strides, box, true);
@@ -562,11 +694,14 @@ static int launch_gru(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   p.dgi = static_cast<__nv_bfloat16*>(a->dgi);
   p.dgh = static_cast<__nv_bfloat16*>(a->dgh);
   p.dh0 = a->dh0;
+  p.c_state = a->c_state;
+  p.c_init = a->c_init;
+  p.dc0 = a->dc0;
   p.sync = a->sync;
   p.flags = a->debug_flags;
   p.ts = reinterpret_cast<unsigned long long*>(a->debug_ts);
 
-  auto kern = gru_kernel<BWD, C>;
+  auto kern = gru_kernel<BWD, C, LSTM>;
   SRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ctas);
@@ -592,9 +727,9 @@ static int launch_gru(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
 }
 
 // Largest cluster size whose K split is whole K blocks, whose units tile H and whose slice fits smem.
-template <bool BWD>
+template <bool BWD, bool LSTM>
 static int pick_cluster(int H, int* kbc_out) {
-  const int K = BWD ? 3 * H : H;
+  const int K = BWD ? (LSTM ? 4 : 3) * H : H;
   const int kb_total = (K + 63) / 64;
   // measured (B=64, H=1024): forward 6.2 us/step at C=2 vs 6.8 at C=4 (DSMEM exchange volume grows
   // with C); backward needs C>=4 for the 3H-wide slice to fit shared memory
@@ -606,10 +741,10 @@ static int pick_cluster(int H, int* kbc_out) {
     const int kbc = kb_total / c;
     bool fits = false;
     switch (c) {
-      case 8: fits = gru_fits<BWD, 8>(H, kbc); break;
-      case 4: fits = gru_fits<BWD, 4>(H, kbc); break;
-      case 2: fits = gru_fits<BWD, 2>(H, kbc); break;
-      default: fits = gru_fits<BWD, 1>(H, kbc); break;
+      case 8: fits = gru_fits<BWD, 8, LSTM>(H, kbc); break;
+      case 4: fits = gru_fits<BWD, 4, LSTM>(H, kbc); break;
+      case 2: fits = gru_fits<BWD, 2, LSTM>(H, kbc); break;
+      default: fits = gru_fits<BWD, 1, LSTM>(H, kbc); break;
     }
     if (!fits) continue;
     *kbc_out = kbc;
@@ -618,18 +753,18 @@ static int pick_cluster(int H, int* kbc_out) {
   return 0;
 }
 
-template <bool BWD>
+template <bool BWD, bool LSTM>
 static int dispatch_gru(const srnn_gru_args* a, cudaStream_t stream) {
   static int cached_h = -1, cached_c = 0, cached_kbc = 0;      // per instantiation (fwd / bwd)
   if (cached_h != a->hidden) {
-    cached_c = pick_cluster<BWD>(a->hidden, &cached_kbc);
+    cached_c = pick_cluster<BWD, LSTM>(a->hidden, &cached_kbc);
     cached_h = a->hidden;
   }
   int kbc = cached_kbc;
   int c = cached_c;
   if (a->debug_flags >> 8) {                         // experiments: force a cluster size (bits 8..)
     const int forced = a->debug_flags >> 8;
-    const int kb_total = ((BWD ? 3 : 1) * a->hidden + 63) / 64;
+    const int kb_total = ((BWD ? (LSTM ? 4 : 3) : 1) * a->hidden + 63) / 64;
     if (kb_total % forced == 0 && a->hidden % (GRU_U * forced) == 0) {
       c = forced;
       kbc = kb_total / forced;
@@ -639,10 +774,10 @@ static int dispatch_gru(const srnn_gru_args* a, cudaStream_t stream) {
   SRNN_CHECK_ARG(a->hidden / GRU_U <= sm_count(), "gru: hidden/8 = %d CTAs exceeds the SM count %d", a->hidden / GRU_U,
                  sm_count());
   switch (c) {
-    case 8: return launch_gru<BWD, 8>(a, kbc, stream);
-    case 4: return launch_gru<BWD, 4>(a, kbc, stream);
-    case 2: return launch_gru<BWD, 2>(a, kbc, stream);
-    default: return launch_gru<BWD, 1>(a, kbc, stream);
+    case 8: return launch_gru<BWD, 8, LSTM>(a, kbc, stream);
+    case 4: return launch_gru<BWD, 4, LSTM>(a, kbc, stream);
+    case 2: return launch_gru<BWD, 2, LSTM>(a, kbc, stream);
+    default: return launch_gru<BWD, 1, LSTM>(a, kbc, stream);
   }
 }
 
@@ -658,6 +793,7 @@ static int check_common(const srnn_gru_args* a) {
                  a->hidden);
   SRNN_CHECK_ARG(a->w_hh && a->h_ext && a->gates && a->sync, "gru: null buffer");
   SRNN_CHECK_ARG(a->ext_batch >= a->batch, "gru: ext_batch (%d) must be >= batch (%d)", a->ext_batch, a->batch);
+  SRNN_CHECK_ARG(a->cell == 0 || a->cell == 1, "gru: cell must be 0 (GRU) or 1 (LSTM)");
   return SRNN_OK;
 }
 
@@ -665,12 +801,20 @@ extern "C" int srnn_gru_forward(const srnn_gru_args* a, srnn_stream_t stream) {
   int rc = check_common(a);
   if (rc) return rc;
   SRNN_CHECK_ARG(a->gi && a->b_hh && a->h_state, "gru_forward: null buffer");
-  return dispatch_gru<false>(a, static_cast<cudaStream_t>(stream));
+  if (a->cell == 1) {
+    SRNN_CHECK_ARG(a->c_state, "lstm forward: c_state required");
+    return dispatch_gru<false, true>(a, static_cast<cudaStream_t>(stream));
+  }
+  return dispatch_gru<false, false>(a, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int srnn_gru_backward(const srnn_gru_args* a, srnn_stream_t stream) {
   int rc = check_common(a);
   if (rc) return rc;
   SRNN_CHECK_ARG(a->dh_out && a->dgi && a->dgh && a->dh0, "gru_backward: null buffer");
-  return dispatch_gru<true>(a, static_cast<cudaStream_t>(stream));
+  if (a->cell == 1) {
+    SRNN_CHECK_ARG(a->c_init && a->dc0, "lstm backward: c_init and dc0 required");
+    return dispatch_gru<true, true>(a, static_cast<cudaStream_t>(stream));
+  }
+  return dispatch_gru<true, false>(a, static_cast<cudaStream_t>(stream));
 }

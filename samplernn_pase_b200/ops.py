@@ -268,13 +268,13 @@ gru_debug_flags = 0      # timing experiments only (scripts/gru_microbench.py)
 gru_debug_ts = None      # int64 [256, 8] tensor receiving CTA 0's pipeline timestamps
 
 
-def _gru_call(name, batch, steps, hidden, **bufs):
-    """Runs the persistent kernel over batch groups of <= 128 rows (independent sequences).
+def _gru_call(name, batch, steps, hidden, cell=0, **bufs):
+    """Runs the persistent kernel over slot groups of <= 64 rows (independent sequences).
     ``bufs``: field -> (tensor, elements per batch row); time-major buffers advance by one row."""
     for b0 in range(0, batch, GRU_MAX_BATCH):
         nb = min(GRU_MAX_BATCH, batch - b0)
         a = GruArgs()
-        a.batch, a.steps, a.hidden, a.ext_batch = nb, steps, hidden, batch
+        a.batch, a.steps, a.hidden, a.ext_batch, a.cell = nb, steps, hidden, batch, cell
         for key, (t, per_row) in bufs.items():
             if t is None:
                 setattr(a, key, None)
@@ -284,7 +284,7 @@ def _gru_call(name, batch, steps, hidden, **bufs):
         a.sync = sync.data_ptr()
         a.debug_flags = gru_debug_flags
         a.debug_ts = gru_debug_ts.data_ptr() if gru_debug_ts is not None else None
-        _lib.profile_note = f'B={nb} T={steps} H={hidden}'
+        _lib.profile_note = f'B={nb} T={steps} H={hidden}' + (' lstm' if cell else '')
         call(name, C.byref(a), stream())
         _count(2)
 
@@ -302,6 +302,22 @@ def gru_backward(w_hh_t, h_ext, gates, dh_out, dgi, dgh, dh0, batch, steps, hidd
     _gru_call('srnn_gru_backward', batch, steps, h, w_hh=(w_hh_t, 0), h_ext=(h_ext, h),
               gates=(gates, steps * 4 * h), dh_out=(dh_out, steps * h), dgi=(dgi, steps * 3 * h),
               dgh=(dgh, 3 * h), dh0=(dh0, h))
+
+
+def lstm_forward(gi, w_hh, b_hh, h_ext, hall, h_state, c_state, gates, batch, steps, hidden):
+    """LSTM extension: gi [batch*steps, 4H], w_hh [4H, H], gates [batch*steps, 5H] (i,f,g,o,c)."""
+    h = hidden
+    _gru_call('srnn_gru_forward', batch, steps, h, cell=1, gi=(gi, steps * 4 * h), w_hh=(w_hh, 0), b_hh=(b_hh, 0),
+              h_ext=(h_ext, h), hall=(hall, steps * h), h_state=(h_state, h), c_state=(c_state, h),
+              gates=(gates, steps * 5 * h))
+
+
+def lstm_backward(w_hh_t, h_ext, gates, c_init, dh_out, dgi, dgh, dh0, dc0, batch, steps, hidden):
+    """w_hh_t [H, 4H]; dgh [steps, batch, 4H] time-major; dgi [batch*steps, 4H] batch-major."""
+    h = hidden
+    _gru_call('srnn_gru_backward', batch, steps, h, cell=1, w_hh=(w_hh_t, 0), h_ext=(h_ext, h),
+              gates=(gates, steps * 5 * h), c_init=(c_init, h), dh_out=(dh_out, steps * h),
+              dgi=(dgi, steps * 4 * h), dgh=(dgh, 4 * h), dh0=(dh0, h), dc0=(dc0, h))
 
 
 def state_select(carried, h0, use_carry, batch, hidden):

@@ -282,6 +282,45 @@ def test_gru_backward(ops, bsz, t, h):
     assert rel_l2(dh0, h0_r.grad) < 3e-2, rel_l2(dh0, h0_r.grad)
 
 
+@pytest.mark.parametrize('bsz,t,h', [(3, 5, 32), (8, 20, 64), (64, 17, 1024), (70, 6, 128)])
+def test_lstm_forward_backward(ops, bsz, t, h):
+    """LSTM extension (BASELINE config 3; no reference counterpart): torch.nn.LSTM semantics, checked
+    against an fp32 autograd evaluation of the same recurrence."""
+    gi = rnd(bsz, t, 4 * h).to(BF16)
+    w_hh = rnd(4 * h, h, scale=1 / math.sqrt(h), seed=1).to(BF16)
+    b_hh = rnd(4 * h, scale=0.1, seed=2)
+    h0 = rnd(bsz, h, scale=0.5, seed=3)
+    c0 = rnd(bsz, h, scale=0.5, seed=5)
+    dh_out = rnd(bsz, t, h, scale=0.1, seed=4).to(BF16)
+    gi_r = gi.float().requires_grad_(True)
+    h0_r, c0_r = h0.clone().requires_grad_(True), c0.clone().requires_grad_(True)
+    hh, cc, outs = h0_r, c0_r, []
+    for s in range(t):
+        g = gi_r[:, s] + hh @ w_hh.float().t() + b_hh
+        i_, f_, g_, o_ = torch.sigmoid(g[:, :h]), torch.sigmoid(g[:, h:2 * h]), torch.tanh(g[:, 2 * h:3 * h]), torch.sigmoid(g[:, 3 * h:])
+        cc = f_ * cc + i_ * g_
+        hh = o_ * torch.tanh(cc)
+        outs.append(hh)
+    ref_out = torch.stack(outs, 1)
+    (ref_out * dh_out.float()).sum().backward()
+    h_ext = torch.zeros(t + 1, bsz, h, dtype=BF16, device='cuda')
+    h_ext[0] = h0.to(BF16)
+    hall = torch.zeros(bsz, t, h, dtype=BF16, device='cuda')
+    h_state, c_state = h0.clone(), c0.clone()
+    gates = torch.empty(bsz * t, 5 * h, dtype=BF16, device='cuda')
+    ops.lstm_forward(gi.view(bsz * t, 4 * h), w_hh, b_hh, h_ext, hall, h_state, c_state, gates, bsz, t, h)
+    assert float((hall.float() - ref_out.detach()).abs().max()) < 3e-2
+    assert float((h_state - hh.detach()).abs().max()) < 2e-2 and float((c_state - cc.detach()).abs().max()) < 3e-2
+    dgi = torch.empty(bsz * t, 4 * h, dtype=BF16, device='cuda')
+    dgh = torch.empty(t * bsz, 4 * h, dtype=BF16, device='cuda')
+    dh0 = torch.empty(bsz, h, dtype=F32, device='cuda')
+    dc0 = torch.empty(bsz, h, dtype=F32, device='cuda')
+    ops.lstm_backward(w_hh.t().contiguous(), h_ext, gates, c0, dh_out.view(bsz * t, h), dgi, dgh, dh0, dc0, bsz, t, h)
+    assert rel_l2(dgi.view(bsz, t, 4 * h), gi_r.grad) < 3e-2, rel_l2(dgi.view(bsz, t, 4 * h), gi_r.grad)
+    assert rel_l2(dh0, h0_r.grad) < 3e-2 and rel_l2(dc0, c0_r.grad) < 3e-2
+    assert torch.equal(dgh.view(t, bsz, 4 * h).transpose(0, 1).contiguous().view(bsz * t, 4 * h), dgi)
+
+
 # ------------------------------------------------------------------------------------------------
 # small kernels
 # ------------------------------------------------------------------------------------------------

@@ -172,6 +172,35 @@ def test_medium_size_vs_cpu_oracle():
     assert r <= 0.08 and cs >= 0.997, (r, cs)
 
 
+def test_config4_shape_three_tiers_large_batch_vs_cpu_oracle():
+    """BASELINE config 4 shape at reduced width: 3 frame tiers (ratios [4,4,4]), more slots than one
+    recurrent launch holds (B=70 > 64 -> slot groups), two chunks with carry, against the CPU oracle."""
+    from samplernn_pase_b200 import SampleRNNModel
+    spec = O.ModelSpec([4, 4, 4], [1, 1, 1], [64, 64, 64], 2)
+    params = O.init_params(spec, conds_speaker_n=11, perturb=0.1)
+    model = SampleRNNModel('embedding', 11, 15, 'acoustic', [9, 5, 4, 3], 10, 50, 2, [4, 4, 4], [1, 1, 1], [64, 64, 64],
+                           True, 256, fused_loss=True).cuda()
+    model.load_state_dict(params)
+    bsz = 70
+    wav, conds, spk = O.synthetic_utterances(spec, bsz, 2, n_speakers=11)
+    info = [{'speaker': {'index': int(s)}} for s in spk]
+    state = None
+    for k in range(2):
+        x, y, c = O.chunk_of(spec, wav, conds, k)
+        reset = [1] * bsz if k == 0 else [0] * bsz
+        y_hat, tgt = model(x.cuda(), y.cuda(), c.cuda(), info, torch.tensor(reset))
+        loss = torch.nn.functional.nll_loss(y_hat.view(-1, y_hat.size(2)), tgt.view(-1))
+        logp, yq, state, _ = O.forward(params, spec, x, y, c, spk, reset, state, fast=True)
+        ref = O.nll(logp, yq)
+        got_lp = y_hat[:, :, 0].cpu()
+        want_lp = logp.gather(2, yq[:, :, None])[:, :, 0]
+        d = float((got_lp - want_lp).abs().max())
+        report(f'config4-shape chunk {k}: loss {float(loss):.6f} ref {float(ref):.6f} max|dlogp_target| {d:.3e}')
+        assert abs(float(loss) - float(ref)) <= 5e-4 * float(ref) and d <= 0.05
+        for n in range(3):
+            assert float((model._state[n].cpu() - state.h[n]).abs().max()) <= 3e-2
+
+
 def test_generation_is_consistent_with_teacher_forcing():
     """SURVEY probe P8: the log-probabilities each generated sample was drawn from must equal the
     teacher-forced log-probabilities of the generated sequence (RNG streams need not match the reference).
