@@ -111,11 +111,13 @@ class FrameTierFn(torch.autograd.Function):
     h_n (layers,B,H) fp32, not differentiable - the reference detaches it, model.py:276)."""
 
     @staticmethod
-    def forward(ctx, xq_u8, x_off, lut, frames, conds, upper, h_init, fs, ratio, into_cat,
+    def forward(ctx, xq_u8, x_off, lut, frames, conds, upper, h_init, fs, ratio, into_cat, c_init,
                 xg, xv, xb, cg, cv, cb, ug, uv, ub, *rnn):
         dev = conds.device
         b, l, c = conds.shape
         layers, _, h = h_init.shape
+        lstm = c_init is not None                      # LSTM extension (BASELINE config 3), else GRU
+        ng = 4 if lstm else 3
         if frames is not None:
             frames = frames.contiguous()
             t = frames.shape[1]
@@ -142,24 +144,33 @@ class FrameTierFn(torch.autograd.Function):
         saved_layers = []
         x_l = u                                                # (B*T, H) batch-major input of layer 0
         hn = _empty(layers, b, h, dtype=F32, device=dev)
+        cn = _empty(layers, b, h, dtype=F32, device=dev) if lstm else _empty(0, dtype=F32, device=dev)
         for i in range(layers):
             w_ih, w_hh, b_ih, b_hh = rnn[4 * i: 4 * i + 4]
-            wih = _empty(3 * h, h, device=dev)
-            wih_t = _empty(h, 3 * h, device=dev)
-            whh = _empty(3 * h, h, device=dev)
-            whh_t = _empty(h, 3 * h, device=dev)
-            ops.weight_prep(w_ih.contiguous(), None, (3 * h, h, 1), wih, (h, 1, 0), wih_t, (1, 3 * h, 0))
-            ops.weight_prep(w_hh.contiguous(), None, (3 * h, h, 1), whh, (h, 1, 0), whh_t, (1, 3 * h, 0))
-            gi = _empty(b * t, 3 * h, device=dev)
-            ops.gemm_nt(x_l, wih, gi, b * t, 3 * h, h, h, h, 3 * h, bias=b_ih.contiguous())
+            wih = _empty(ng * h, h, device=dev)
+            wih_t = _empty(h, ng * h, device=dev)
+            whh = _empty(ng * h, h, device=dev)
+            whh_t = _empty(h, ng * h, device=dev)
+            ops.weight_prep(w_ih.contiguous(), None, (ng * h, h, 1), wih, (h, 1, 0), wih_t, (1, ng * h, 0))
+            ops.weight_prep(w_hh.contiguous(), None, (ng * h, h, 1), whh, (h, 1, 0), whh_t, (1, ng * h, 0))
+            gi = _empty(b * t, ng * h, device=dev)
+            ops.gemm_nt(x_l, wih, gi, b * t, ng * h, h, h, h, ng * h, bias=b_ih.contiguous())
             h_ext = _empty(t + 1, b, h, device=dev)            # time-major exchange buffer, slot 0 = h_init
             hall = _empty(b * t, h, device=dev)                # batch-major copy for the GEMMs
             h_state = h_init[i].contiguous().clone()
             ops.pad_cast_bf16(h_state, b, h, h, h_ext, h, h)
-            gates = _empty(b * t, 4 * h, device=dev)
-            ops.gru_forward(gi, whh, b_hh.contiguous(), h_ext, hall, h_state, gates, b, t, h)
+            c0_i = None
+            if lstm:
+                gates = _empty(b * t, 5 * h, device=dev)
+                c0_i = c_init[i].contiguous()
+                c_state = c0_i.clone()
+                ops.lstm_forward(gi, whh, b_hh.contiguous(), h_ext, hall, h_state, c_state, gates, b, t, h)
+                cn[i] = c_state
+            else:
+                gates = _empty(b * t, 4 * h, device=dev)
+                ops.gru_forward(gi, whh, b_hh.contiguous(), h_ext, hall, h_state, gates, b, t, h)
             hn[i] = h_state
-            saved_layers.append((wih_t, whh_t, h_ext, hall, gates, x_l))
+            saved_layers.append((wih_t, whh_t, h_ext, hall, gates, x_l, c0_i))
             x_l = hall
 
         # learned upsampling as one GEMM: out[(b,t), j*H+o] = sum_i h[b,t,i] Wu[i,o,j] + bias[o,j]
@@ -177,16 +188,17 @@ class FrameTierFn(torch.autograd.Function):
             up = _empty(b, t * r, h, device=dev)
             ops.gemm_nt(x_l, wu, up, b * t, r * h, h, h, h, r * h, bias=ub.t().contiguous().view(-1))
 
-        ctx.dims = (b, t, l, c, h, fs, r, kp, cp, layers, upper is not None)
+        ctx.dims = (b, t, l, c, h, fs, r, kp, cp, layers, upper is not None, lstm)
         ctx.saved_layers = saved_layers
         ctx.save_for_backward(ain, wct, wu_t, inv_x, inv_c, inv_u, xg, xv, cg, cv, ug, uv)
-        ctx.mark_non_differentiable(hn)
-        return up, hn
+        ctx.mark_non_differentiable(hn, cn)
+        return up, hn, cn
 
     @staticmethod
-    def backward(ctx, dup, _dhn):
+    def backward(ctx, dup, _dhn, _dcn):
         ain, wct, wu_t, inv_x, inv_c, inv_u, xg, xv, cg, cv, ug, uv = ctx.saved_tensors
-        b, t, l, c, h, fs, r, kp, cp, layers, has_upper = ctx.dims
+        b, t, l, c, h, fs, r, kp, cp, layers, has_upper, lstm = ctx.dims
+        ng = 4 if lstm else 3
         dev = dup.device
         dup = dup.contiguous()            # (B, T*r, H) == (B*T, r*H)
         last_hall = ctx.saved_layers[-1][3]
@@ -200,21 +212,27 @@ class FrameTierFn(torch.autograd.Function):
 
         rnn_grads = [None] * (4 * layers)
         dh0 = _empty(layers, b, h, dtype=F32, device=dev)
+        dc0 = _empty(layers, b, h, dtype=F32, device=dev) if lstm else None
         for i in reversed(range(layers)):
-            wih_t, whh_t, h_ext, hall, gates, x_l = ctx.saved_layers[i]
-            dgi = _empty(b * t, 3 * h, device=dev)             # batch-major
-            dgh = _empty(t * b, 3 * h, device=dev)             # time-major (exchange buffer)
+            wih_t, whh_t, h_ext, hall, gates, x_l, c0_i = ctx.saved_layers[i]
+            dgi = _empty(b * t, ng * h, device=dev)            # batch-major
+            dgh = _empty(t * b, ng * h, device=dev)            # time-major (exchange buffer)
             dh0_i = _empty(b, h, dtype=F32, device=dev)
-            ops.gru_backward(whh_t, h_ext, gates, dh_out, dgi, dgh, dh0_i, b, t, h)
+            if lstm:
+                dc0_i = _empty(b, h, dtype=F32, device=dev)
+                ops.lstm_backward(whh_t, h_ext, gates, c0_i, dh_out, dgi, dgh, dh0_i, dc0_i, b, t, h)
+                dc0[i] = dc0_i
+            else:
+                ops.gru_backward(whh_t, h_ext, gates, dh_out, dgi, dgh, dh0_i, b, t, h)
             dh0[i] = dh0_i
-            dwhh = _zeros(3 * h, h, device=dev)                # both operands time-major: rows (t, b)
-            ops.gemm_tn(dgh, h_ext, dwhh, 3 * h, h, t * b, 3 * h, h, h)
-            dwih = _zeros(3 * h, h, device=dev)
-            ops.gemm_tn(dgi, x_l, dwih, 3 * h, h, b * t, 3 * h, h, h)
-            rnn_grads[4 * i: 4 * i + 4] = [dwih, dwhh, ops.colsum(dgi, b * t, 3 * h, 3 * h),
-                                           ops.colsum(dgh, b * t, 3 * h, 3 * h)]
+            dwhh = _zeros(ng * h, h, device=dev)               # both operands time-major: rows (t, b)
+            ops.gemm_tn(dgh, h_ext, dwhh, ng * h, h, t * b, ng * h, h, h)
+            dwih = _zeros(ng * h, h, device=dev)
+            ops.gemm_tn(dgi, x_l, dwih, ng * h, h, b * t, ng * h, h, h)
+            rnn_grads[4 * i: 4 * i + 4] = [dwih, dwhh, ops.colsum(dgi, b * t, ng * h, ng * h),
+                                           ops.colsum(dgh, b * t, ng * h, ng * h)]
             dx = _empty(b * t, h, device=dev)
-            ops.gemm_nt(dgi, wih_t, dx, b * t, h, 3 * h, 3 * h, 3 * h, h)
+            ops.gemm_nt(dgi, wih_t, dx, b * t, h, ng * h, ng * h, ng * h, h)
             dh_out = dx
         du = dh_out                       # (B*T, H): gradient of u, hence also of `upper`
         d_bias = ops.colsum(du, b * t, h, h)
@@ -229,7 +247,7 @@ class FrameTierFn(torch.autograd.Function):
             dconds = _zeros(b, l, c, device=dev)
             ops.tier_input_bwd(dc_rows, b, t, 0, l, c, cp, dconds)
         d_upper = du.view(b, t, h) if has_upper else None
-        return (None, None, None, None, dconds, d_upper, dh0, None, None, None,
+        return (None, None, None, None, dconds, d_upper, dh0, None, None, None, dc0,
                 d_xg.view_as(xg), d_xv, d_bias, d_cg.view_as(cg), d_cv, d_bias.clone(),
                 d_ug.view_as(ug), d_uv, d_ub, *rnn_grads)
 

@@ -143,6 +143,8 @@ def generate(model, utt_conds, info, return_logp=False, generator=None):
     lut = q.lut(dev)
     total = (t + 1) * fs_top
     y = torch.full((b, total), q.quantize_zero(), dtype=torch.uint8, device=dev)
+    if any(layer.rnn_cell != 'gru' for layer in model.frames_layers):
+        raise NotImplementedError('generation is implemented for GRU tiers (the reference cell)')
     tiers = [TierWeights(layer, c) for layer in model.frames_layers]
     sw = SampleWeights(model.sample_layer, c)
     states = [w.h0[:, None, :].expand(-1, b, -1).contiguous() for w in tiers]  # learnable h0 (model.py:111)

@@ -78,10 +78,17 @@ class CondsMixer(torch.nn.Module):
 
     def speaker_ids(self, info, device):
         """model.py:67-72: empty slots (info None) use speaker 0."""
-        if self.conds_speaker_type != 'embedding':
-            raise NotImplementedError("conds_speaker_type='pase' raises in the reference too (model.py:73-74)")
         ids = [it['speaker']['index'] if it is not None else 0 for it in info]
         return torch.tensor(ids, dtype=torch.int32).to(device, non_blocking=True)
+
+    def speaker_vectors(self, info, device):
+        """``conds_speaker_type='pase'``: the reference raises (model.py:73-74); this extension (BASELINE
+        config 3, oracle variant O-D, parity unpinned) takes a pre-computed PASE speaker vector of width
+        ``conds_speaker_size`` from ``info[i]['speaker']['pase']`` in place of the embedding row (zeros for
+        an empty slot)."""
+        rows = [torch.as_tensor(it['speaker']['pase'], dtype=torch.float32) if it is not None
+                else torch.zeros(self.conds_speaker_size) for it in info]
+        return torch.stack(rows).to(device, non_blocking=True)
 
     def _expand_linguistic(self, utt):
         """model.py:76-93.  Index gathers + concat (data movement; the tables' gradients flow
@@ -97,9 +104,14 @@ class CondsMixer(torch.nn.Module):
         return torch.cat(parts, dim=2)
 
     def forward(self, utt_conds, info):
-        ids = self.speaker_ids(info, utt_conds.device)
-        return CondsMixFn.apply(self._expand_linguistic(utt_conds), ids, self.speaker_embedding.weight,
-                                self.conds_mix.weight, self.conds_mix.bias)
+        if self.conds_speaker_type == 'pase':
+            table = self.speaker_vectors(info, utt_conds.device)               # one row per slot
+            ids = torch.arange(len(info), dtype=torch.int32, device=utt_conds.device)
+        else:
+            table = self.speaker_embedding.weight
+            ids = self.speaker_ids(info, utt_conds.device)
+        return CondsMixFn.apply(self._expand_linguistic(utt_conds), ids, table, self.conds_mix.weight,
+                                self.conds_mix.bias)
 
 
 class _RnnParams(torch.nn.Module):
@@ -130,30 +142,37 @@ class _RnnParams(torch.nn.Module):
 class FrameLevelLayer(torch.nn.Module):
     """model.py:96-156."""
 
-    def __init__(self, input_samples, conds_size, ratio, rnn_layers, rnn_hidden_size):
+    def __init__(self, input_samples, conds_size, ratio, rnn_layers, rnn_hidden_size, rnn_cell='gru'):
         super().__init__()
         self.input_samples = input_samples
         self.ratio = ratio
         self.rnn_layers = rnn_layers
         self.rnn_hidden_size = rnn_hidden_size
+        self.rnn_cell = rnn_cell                      # 'lstm' is an extension (the reference has GRU only)
         h = rnn_hidden_size
         self.rnn_h0 = torch.nn.Parameter(torch.zeros(rnn_layers, h))
+        if rnn_cell == 'lstm':
+            self.rnn_c0 = torch.nn.Parameter(torch.zeros(rnn_layers, h))
         self.upsample_bias = torch.nn.Parameter(torch.zeros(h, ratio))
         kaiming = lambda shape, fan_in: _uniform_(torch.empty(shape), math.sqrt(6.0 / fan_in))   # noqa: E731
         self.x_expand = _normed(kaiming((h, input_samples, 1), input_samples), torch.zeros(h))   # model.py:119,121
         self.conds_expand = _normed(kaiming((h, conds_size, 1), conds_size), torch.zeros(h))     # model.py:120,122
-        self.rnn = _RnnParams(h, rnn_layers)
+        self.rnn = _RnnParams(h, rnn_layers, gates=4 if rnn_cell == 'lstm' else 3)
         self.upsample = _normed(_uniform_(torch.empty(h, h, ratio), math.sqrt(6.0 / h)))          # model.py:124-126
 
-    def _tier(self, xq_u8, x_off, lut, frames, conds, upper, h_init, into_cat=False):
+    def _tier(self, xq_u8, x_off, lut, frames, conds, upper, h_init, into_cat=False, c_init=None):
+        """-> (upsampled, h_n, c_n); c_n is an empty tensor for GRU tiers."""
         return FrameTierFn.apply(
-            xq_u8, x_off, lut, frames, conds, upper, h_init, self.input_samples, self.ratio, into_cat,
+            xq_u8, x_off, lut, frames, conds, upper, h_init, self.input_samples, self.ratio, into_cat, c_init,
             self.x_expand.weight_g, self.x_expand.weight_v, self.x_expand.bias,
             self.conds_expand.weight_g, self.conds_expand.weight_v, self.conds_expand.bias,
             self.upsample.weight_g, self.upsample.weight_v, self.upsample_bias, *self.rnn.flat(self.rnn_layers))
 
     def initial_state(self, carried, use_carry):
         return StateSelectFn.apply(self.rnn_h0, carried, use_carry)
+
+    def initial_cell(self, carried, use_carry):
+        return StateSelectFn.apply(self.rnn_c0, carried, use_carry)
 
     def forward(self, x, conds, upper_conditioning, rnn_state):
         """Reference calling convention: ``x`` (B,T,fs) dequantised floats, ``rnn_state`` a list
@@ -167,7 +186,9 @@ class FrameLevelLayer(torch.nn.Module):
             carried = torch.stack([s if s is not None else zero for s in rnn_state], dim=1).contiguous()
         h_init = self.initial_state(carried, use)
         upper = upper_conditioning.to(torch.bfloat16) if upper_conditioning is not None else None
-        up, hn = self._tier(None, 0, None, x.float(), conds.float(), upper, h_init)
+        if self.rnn_cell == 'lstm':
+            raise NotImplementedError('the per-layer list-of-states API exists for GRU tiers (the reference cell)')
+        up, hn, _ = self._tier(None, 0, None, x.float(), conds.float(), upper, h_init)
         return up.float(), hn
 
 
@@ -210,7 +231,8 @@ class SampleRNNModel(torch.nn.Module):
 
     def __init__(self, conds_speaker_type, conds_speaker_n, conds_speaker_size, conds_utterance_type,
                  conds_utterance_linguistic_n, conds_utterance_linguistic_emb_size, conds_size, sequence_length, ratios,
-                 rnn_layers, rnn_hidden_size, q_type_ulaw, q_levels, fused_loss=False, reference_as_written=False):
+                 rnn_layers, rnn_hidden_size, q_type_ulaw, q_levels, fused_loss=False, reference_as_written=False,
+                 rnn_cell='gru'):
         super().__init__()
         self.frame_size = np.prod(ratios)
         self.receptive_field = np.prod(ratios) * sequence_length
@@ -222,13 +244,15 @@ class SampleRNNModel(torch.nn.Module):
         self.frames_layers = torch.nn.ModuleList()
         frame_sizes = [int(v) for v in np.cumprod(ratios)]
         for n, fs in enumerate(frame_sizes):
-            self.frames_layers.append(FrameLevelLayer(fs, conds_size, ratios[n], rnn_layers[n], rnn_hidden_size[n]))
+            self.frames_layers.append(FrameLevelLayer(fs, conds_size, ratios[n], rnn_layers[n], rnn_hidden_size[n],
+                                                      rnn_cell))
         self.sample_layer = SampleLevelLayer(ratios[0], conds_size, rnn_hidden_size[0], self.quantizer.q_levels)
         self._init_rnn_states(0)
 
     # ---- hidden-state store (model.py:236-250), dense: one (layers,B,H) tensor + validity per tier ----
     def _init_rnn_states(self, batch_size):
         self._state = {n: None for n in range(len(self.frames_layers))}
+        self._state_c = {n: None for n in range(len(self.frames_layers))}
         self._state_valid = {n: [False] * batch_size for n in range(len(self.frames_layers))}
 
     @property
@@ -264,9 +288,13 @@ class SampleRNNModel(torch.nn.Module):
             use = [1 if (r == 0 and valid[i] and self._state[n] is not None) else 0 for i, r in enumerate(reset_l)]
             use_t = torch.tensor(use, dtype=torch.uint8).to(dev, non_blocking=True)
             h_init = layer.initial_state(self._state[n] if any(use) else None, use_t)
-            upper, hn = layer._tier(xq8, fs_top - layer.input_samples, lut, None, conds, upper, h_init,
-                                    into_cat=(n == 0))
+            c_init = None
+            if layer.rnn_cell == 'lstm':
+                c_init = layer.initial_cell(self._state_c[n] if any(use) else None, use_t)
+            upper, hn, cn = layer._tier(xq8, fs_top - layer.input_samples, lut, None, conds, upper, h_init,
+                                        into_cat=(n == 0), c_init=c_init)
             self._state[n] = hn.detach()
+            self._state_c[n] = cn.detach() if layer.rnn_cell == 'lstm' else None
             self._state_valid[n] = [r in (0, 1) for r in reset_l]               # model.py:245-250
 
         r0 = self.sample_layer.input_samples

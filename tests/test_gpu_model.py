@@ -201,6 +201,51 @@ def test_config4_shape_three_tiers_large_batch_vs_cpu_oracle():
             assert float((model._state[n].cpu() - state.h[n]).abs().max()) <= 3e-2
 
 
+def test_config3_lstm_tiers_with_pase_speaker_vector_vs_cpu_oracle():
+    """BASELINE config 3 extensions (no reference implementation - parity unpinned, the definitions are the
+    oracle's O-C / O-D): LSTM tiers with learnable (h0, c0) and a PASE speaker vector in place of the
+    embedding row.  Two chunks with carry, loss + all gradients against the CPU oracle."""
+    from samplernn_pase_b200 import SampleRNNModel
+    s_dim = 100                                                                # PASE vector width
+    spec = O.ModelSpec([4, 4], [1, 1], [128, 128], 8, cell='lstm')
+    params = O.init_params(spec, conds_speaker_n=3, conds_speaker_size=s_dim, perturb=0.1)
+    model = SampleRNNModel('pase', 3, s_dim, 'acoustic', [9, 5, 4, 3], 10, 50, 8, [4, 4], [1, 1], [128, 128], True, 256,
+                           rnn_cell='lstm').cuda()
+    assert sorted(model.state_dict().keys()) == sorted(params.keys())
+    model.load_state_dict(params)
+    bsz = 6
+    wav, conds, _ = O.synthetic_utterances(spec, bsz, 2)
+    vecs = torch.randn(bsz, s_dim, generator=torch.Generator().manual_seed(9))
+    info = [{'speaker': {'pase': vecs[i]}} for i in range(bsz)]
+    p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    state = None
+    for k in range(2):
+        x, y, c = O.chunk_of(spec, wav, conds, k)
+        reset = [1] * bsz if k == 0 else [0, 0, 1, 0, 0, 0]
+        model.zero_grad()
+        for v in p_ref.values():
+            v.grad = None
+        y_hat, yq = model(x.cuda(), y.cuda(), c.cuda(), info, torch.tensor(reset))
+        loss = torch.nn.functional.nll_loss(y_hat.view(-1, 256), yq.view(-1))
+        loss.backward()
+        logp, tgt, state, _ = O.forward(p_ref, spec, x, y, c, None, reset, state, speaker_vectors=vecs)
+        ref = O.nll(logp, tgt)
+        ref.backward()
+        assert torch.equal(yq.cpu(), tgt)
+        d = float((y_hat.detach().cpu() - logp.detach()).abs().max())
+        names = [n for n, _ in model.named_parameters() if n != 'conds_mixer.speaker_embedding.weight']
+        got = torch.cat([dict(model.named_parameters())[n].grad.flatten().cpu() for n in names])
+        want = torch.cat([(p_ref[n].grad if p_ref[n].grad is not None else torch.zeros_like(p_ref[n])).flatten() for n in names])
+        r, cs = rel_l2(got, want), cosine(got, want)
+        report(f'config3 LSTM+PASE chunk {k}: loss {float(loss):.6f} ref {float(ref):.6f} max|dlogp| {d:.3e} '
+               f'ALL GRADS rel_l2 {r:.3e} cos {cs:.6f}')
+        assert abs(float(loss) - float(ref)) <= 5e-4 * float(ref) and d <= 0.05
+        assert r <= 0.1 and cs >= 0.995, (r, cs)
+        for n in range(2):
+            assert float((model._state[n].cpu() - state.h[n]).abs().max()) <= 3e-2
+            assert float((model._state_c[n].cpu() - state.c[n]).abs().max()) <= 5e-2
+
+
 def test_generation_is_consistent_with_teacher_forcing():
     """SURVEY probe P8: the log-probabilities each generated sample was drawn from must equal the
     teacher-forced log-probabilities of the generated sequence (RNG streams need not match the reference).
