@@ -36,6 +36,8 @@ RATIOS, LAYERS, HIDDEN = [4, 4], [1, 1], [1024, 1024]
 SLOTS_PER_GPU, SEQ_LEN = 64, 1000
 N_SPEAKERS = 126
 METRIC = 'teacher-forced training audio samples/sec'
+# dram bytes (read+write) of the comb_layer forward GEMM (m x 1024 x 2048) measured by ncu at m = 262 144; None = not captured
+NCU_BYTES_AT_262144 = None
 WORKLOAD = ('config2: 3-tier SampleRNN GRU ratios [4,4] H=1024, 64 slots/GPU x 1 s chunks (L=1000, RF=16000) '
             'of 8 s utterances with hidden-state carry, acoustic conds U=43, 126 speakers')
 
@@ -221,7 +223,7 @@ def run_gpu(args):
             pass
         peak = peaks.get('bf16_tflops_sustained', 1400.0)
         m_rows, h = b * rf, HIDDEN[0]
-        gemm_flops = 2.0 * m_rows * h * 3 * h                     # comb_layer forward: (B*RF, 3H) x (3H, H)
+        gemm_flops = 2.0 * m_rows * h * 2 * h                     # comb_layer forward GEMM as executed: (B*RF, 2H) x (2H, H)
         avg_ms = sum(kernel_ms) / max(len(kernel_ms), 1)
         achieved = gemm_flops / (avg_ms * 1e-3) / 1e12 if avg_ms else None
         total = args.steps * global_rows
@@ -243,9 +245,10 @@ def run_gpu(args):
             gpu_launches=launches,
             roofline=dict(bound='tensor', kernel='gemm_kernel<256,NT,epilogue bias+relu> (comb_layer forward, tcgen05)',
                           achieved=achieved, peak=peak, unit='TFLOP/s', frac=(achieved / peak) if achieved else None,
-                          # dram__bytes_read+write of this kernel from `ncu --set full` at 262 144 rows (2.129 GB,
-                          # profiles/r01_hot_kernels_ncu.txt [1]) scaled to this launch's rows; algorithmic = A + C + W
-                          traffic=2.129e9 * m_rows / 262144.0, traffic_algorithmic=2.0 * m_rows * 4 * h + 6.0 * h * h,
+                          # dram__bytes_read+write of this kernel from `ncu --set full` at 262 144 rows
+                          # (profiles/r01_hot_kernels_ncu.txt [1]) scaled to this launch's rows; algorithmic = A + C + W
+                          traffic=NCU_BYTES_AT_262144 * m_rows / 262144.0 if NCU_BYTES_AT_262144 else None,
+                          traffic_algorithmic=2.0 * m_rows * 3 * h + 4.0 * h * h,
                           launches_timed=len(kernel_ms), avg_launch_ms=avg_ms,
                           peak_source='MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
                           if peaks else 'fallback'),

@@ -132,6 +132,8 @@ typedef struct srnn_gemm_args {
   const void* aux; int64_t ldaux; int64_t aux_batch_stride;   /* bf16 [m,n] per batch or NULL */
   int32_t aux_mode;           /* 0 none, 1 add (before activation), 2 gate: C = acc * (aux > 0) */
   int32_t relu;               /* apply max(.,0) last */
+  int32_t aux_row_div;        /* 0/1: aux row = output row; d > 1: aux row = row / d (a term that is constant
+                                 over groups of d rows, e.g. the conditioning of the d samples of one frame) */
 } srnn_gemm_args;
 
 int srnn_gemm_bf16(const srnn_gemm_args* args, srnn_stream_t stream);

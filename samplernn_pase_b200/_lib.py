@@ -23,7 +23,7 @@ class GemmArgs(C.Structure):
         ('c_dtype', C.c_int32), ('n_fold', C.c_int32),
         ('bias', C.c_void_p),
         ('aux', C.c_void_p), ('ldaux', C.c_int64), ('aux_batch_stride', C.c_int64),
-        ('aux_mode', C.c_int32), ('relu', C.c_int32),
+        ('aux_mode', C.c_int32), ('relu', C.c_int32), ('aux_row_div', C.c_int32),
     ]
 
 

@@ -37,7 +37,7 @@ struct GemmParams {
   const float* bias;
   const __nv_bfloat16* aux;
   long long ldaux, aux_batch_stride;
-  int aux_mode, relu;
+  int aux_mode, relu, aux_row_div;
   // schedule
   int tiles_m, tiles_n, kb_per_batch, splits, kb_per_split, total_kb, total_work;
   // NLL epilogue
@@ -251,7 +251,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               if (full_chunk || n0 + i < p.n) f[i] += __ldg(p.bias + n0 + i);
           }
           if (p.aux_mode) {
-            const __nv_bfloat16* ap = p.aux + wk.b * p.aux_batch_stride + static_cast<long long>(j) * p.ldaux + n0;
+            const __nv_bfloat16* ap = p.aux + wk.b * p.aux_batch_stride + static_cast<long long>(j / p.aux_row_div) * p.ldaux + n0;
             const bool vec = full_chunk && ((reinterpret_cast<uintptr_t>(ap) & 15) == 0);
             float a[32];
             if (vec) {
@@ -551,6 +551,7 @@ extern "C" int srnn_gemm_bf16(const srnn_gemm_args* a, srnn_stream_t stream_) {
   p.bias = a->bias;
   p.aux = static_cast<const __nv_bfloat16*>(a->aux); p.ldaux = a->ldaux; p.aux_batch_stride = a->aux_batch_stride;
   p.aux_mode = a->aux ? a->aux_mode : 0; p.relu = a->relu;
+  p.aux_row_div = a->aux_row_div > 0 ? a->aux_row_div : 1;
   if (a->op == 0) {
     SRNN_CHECK_ARG(a->n_fold == 0 || (a->n % a->n_fold == 0 && a->n_fold % 32 == 0 && !a->aux),
                    "gemm NT: n_fold must divide n, be a multiple of 32, and exclude aux");

@@ -179,11 +179,12 @@ class FrameTierFn(torch.autograd.Function):
         inv_u = _empty(h, dtype=F32, device=dev)
         ops.weight_prep(uv, ug, (h, h, r), wu, (1, h, h * h), wu_t, (r * h, 1, h), inv_norm=inv_u)
         if into_cat and h % 32 == 0:
-            # lowest tier: write the upsampled conditioning straight into column block [2H,3H) of the
-            # sample-level concat buffer (model.py:196-199) - the returned tensor is a strided view of it
-            cat = _empty(b * t * r, 3 * h, device=dev)
-            up = cat[:, 2 * h:].view(b, t * r, h)
-            ops.gemm_nt(x_l, wu, up, b * t, r * h, h, h, h, 3 * h, bias=ub.t().contiguous().view(-1), n_fold=h)
+            # lowest tier: write the upsampled conditioning straight into column block [H,2H) of the
+            # sample-level operand buffer [emb-conv | upper] (model.py:196-199 without the conditioning
+            # block, which is hoisted to frame rate) - the returned tensor is a strided view of it
+            cat = _empty(b * t * r, 2 * h, device=dev)
+            up = cat[:, h:].view(b, t * r, h)
+            ops.gemm_nt(x_l, wu, up, b * t, r * h, h, h, h, 2 * h, bias=ub.t().contiguous().view(-1), n_fold=h)
         else:
             up = _empty(b, t * r, h, device=dev)
             ops.gemm_nt(x_l, wu, up, b * t, r * h, h, h, h, r * h, bias=ub.t().contiguous().view(-1))
@@ -257,7 +258,13 @@ class FrameTierFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------
 class SampleLevelFn(torch.autograd.Function):
     """mode 'fused': returns log p(target) per row, (B,RF) fp32 (logits never reach HBM).
-    mode 'full' : returns the (B,RF,Q) log-probabilities like the reference module."""
+    mode 'full' : returns the (B,RF,Q) log-probabilities like the reference module.
+
+    comb_layer (model.py:195-200) is evaluated as
+        h1 = relu([e | upper] . [W_e | W_u]^T  +  cterm[frame of the row]),   cterm = c_frame . W_c^T + b,
+    i.e. the conditioning block of the concat - constant over the FS samples of a frame - is multiplied once
+    per (slot, frame) instead of once per sample: K drops from 3H to 2H in the three big comb
+    GEMMs (forward, data gradient, weight gradient)."""
 
     @staticmethod
     def forward(ctx, xs_u8, conds, upper, target_u8, fused, emb, eg, ev, csw, csb, cw, cbias, w2g, w2v, b2, w3g, w3v, b3):
@@ -281,16 +288,28 @@ class SampleLevelFn(torch.autograd.Function):
         table = _empty(h, r0 * q, device=dev)
         for k in range(r0):
             ops.gemm_nt(we[:, k * q:], e_b, table[:, k * q:], h, q, q, r0 * q, q, r0 * q)
-        shared_cat = (upper.dim() == 3 and upper.stride(2) == 1 and upper.stride(1) == 3 * h and
-                      upper.stride(0) == rf * 3 * h and upper.storage_offset() == 2 * h and
-                      upper.untyped_storage().nbytes() >= m * 3 * h * 2)
-        if shared_cat:      # the tier below already wrote column block [2H,3H) of this buffer
-            cat = torch.as_strided(upper, (m, 3 * h), (3 * h, 1), 0)
+        # operand buffer [emb-conv | upper]; the tier below may already have written the upper block
+        shared_cat = (upper.dim() == 3 and upper.stride(2) == 1 and upper.stride(1) == 2 * h and
+                      upper.stride(0) == rf * 2 * h and upper.storage_offset() == h and
+                      upper.untyped_storage().nbytes() >= m * 2 * h * 2)
+        if shared_cat:
+            cat = torch.as_strided(upper, (m, 2 * h), (2 * h, 1), 0)
         else:
-            cat = _empty(m, 3 * h, device=dev)
-        ops.gemm_nt(onehot, table, cat, rf, h, r0 * q, q, r0 * q, 3 * h, batch=b, a_bs=w * q, c_bs=rf * 3 * h)
+            cat = _empty(m, 2 * h, device=dev)
+            cat[:, h:] = upper.reshape(m, h)
+        ops.gemm_nt(onehot, table, cat, rf, h, r0 * q, q, r0 * q, 2 * h, batch=b, a_bs=w * q, c_bs=rf * 2 * h)
 
-        # conditioning at frame rate, then repeated FS times into the concat buffer
+        # comb_layer weights: [W_e | W_u] (H, 2H) K-major, W_c (H, H), and the transposes for backward
+        cwc = cw.contiguous()
+        w_eu = _empty(h, 2 * h, device=dev)
+        w_c = _empty(h, h, device=dev)
+        wcomb_t = _empty(3 * h, h, device=dev)                               # rows: e | c | upper blocks of W^T
+        ops.weight_prep(cwc, None, (h, 3 * h, 1), wcomb_t, (1, h, 0))
+        ops.weight_prep(cwc[:, :h].contiguous(), None, (h, h, 1), w_eu, (2 * h, 1, 0))
+        ops.weight_prep(cwc[:, 2 * h:].contiguous(), None, (h, h, 1), w_eu[:, h:], (2 * h, 1, 0))
+        ops.weight_prep(cwc[:, h:2 * h].contiguous(), None, (h, h, 1), w_c, (h, 1, 0))
+
+        # conditioning at frame rate: c_frame = conds_expand(conds) (model.py:194), cterm = c_frame W_c^T + b
         conds_b = _empty(b * l, cp, device=dev)
         ops.pad_cast_bf16(conds.contiguous(), b * l, c, c, conds_b, cp, cp)
         wcs = _zeros(h, cp, dtype=BF16, device=dev)
@@ -298,16 +317,13 @@ class SampleLevelFn(torch.autograd.Function):
         ops.weight_prep(csw.contiguous(), None, (h, c, 1), wcs, (cp, 1, 0), wcs_t, (1, h, 0))
         c_frame = _empty(b * l, h, device=dev)
         ops.gemm_nt(conds_b, wcs, c_frame, b * l, h, cp, cp, cp, h, bias=csb.contiguous())
-        ops.repeat_rows(c_frame, b * l, h, h, fsz, cat[:, h:], 3 * h)
-        if not shared_cat:
-            cat[:, 2 * h:] = upper.reshape(m, h)
+        cterm = _empty(b * l, h, device=dev)
+        ops.gemm_nt(c_frame, w_c, cterm, b * l, h, h, h, h, h, bias=cbias.contiguous())
 
-        wcomb = _empty(h, 3 * h, device=dev)
-        wcomb_t = _empty(3 * h, h, device=dev)
-        ops.weight_prep(cw.contiguous(), None, (h, 3 * h, 1), wcomb, (3 * h, 1, 0), wcomb_t, (1, h, 0))
         h1 = _empty(m, h, device=dev)
         with ops.timed('comb_layer_fwd'):
-            ops.gemm_nt(cat, wcomb, h1, m, h, 3 * h, 3 * h, 3 * h, h, bias=cbias.contiguous(), relu=True)
+            ops.gemm_nt(cat, w_eu, h1, m, h, 2 * h, 2 * h, 2 * h, h, aux=cterm, ldaux=h, aux_mode=1, aux_row_div=fsz,
+                        relu=True)
         w2 = _empty(h, h, device=dev)
         w2_t = _empty(h, h, device=dev)
         inv_2 = _empty(h, dtype=F32, device=dev)
@@ -333,14 +349,14 @@ class SampleLevelFn(torch.autograd.Function):
             ops.gemm_nll(1, h2, w3, b3c, target_u8, m, h, h, h, lse=lse, logp_target=logp_t, logp=logp)
             out = logp.view(b, rf, q)
         ctx.dims = (b, w, l, c, h, q, r0, rf, m, fsz, cp, fused)
-        ctx.save_for_backward(onehot, e_b, we_t, inv_e, conds_b, wcs_t, cat, wcomb_t, h1, w2, w2_t, inv_2, h2, w3, w3_t,
-                              inv_3, target_u8, b3c, eg, ev, w2g, w2v, w3g, w3v)
+        ctx.save_for_backward(onehot, e_b, we_t, inv_e, conds_b, wcs_t, c_frame, cat, wcomb_t, h1, w2, w2_t, inv_2, h2, w3,
+                              w3_t, inv_3, target_u8, b3c, eg, ev, w2g, w2v, w3g, w3v)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        (onehot, e_b, we_t, inv_e, conds_b, wcs_t, cat, wcomb_t, h1, w2, w2_t, inv_2, h2, w3, w3_t, inv_3, target_u8, b3c,
-         eg, ev, w2g, w2v, w3g, w3v) = ctx.saved_tensors
+        (onehot, e_b, we_t, inv_e, conds_b, wcs_t, c_frame, cat, wcomb_t, h1, w2, w2_t, inv_2, h2, w3, w3_t, inv_3,
+         target_u8, b3c, eg, ev, w2g, w2v, w3g, w3v) = ctx.saved_tensors
         b, w, l, c, h, q, r0, rf, m, fsz, cp, fused = ctx.dims
         dev = gout.device
         gout = gout.contiguous().float()
@@ -363,18 +379,21 @@ class SampleLevelFn(torch.autograd.Function):
         d_w2v, d_w2g = ops.weight_prep_bwd(dw2, (h, 1, 0), w2v, w2g, inv_2, (h, h, 1))
         dh1 = _empty(m, h, device=dev)
         ops.gemm_nt(dh2, w2_t, dh1, m, h, h, h, h, h, aux=h1, ldaux=h, aux_mode=2)
-        # comb_layer
+        # comb_layer: [e | upper] blocks at sample rate, conditioning block at frame rate
         d_cbias = ops.colsum(dh1, m, h, h)
         d_cw = _zeros(h, 3 * h, device=dev)
-        ops.gemm_tn(dh1, cat, d_cw, h, 3 * h, m, h, 3 * h, 3 * h)
+        ops.gemm_tn(dh1, cat, d_cw, h, h, m, h, 2 * h, 3 * h)                              # d W_e
+        ops.gemm_tn(dh1, cat[:, h:], d_cw[:, 2 * h:], h, h, m, h, 2 * h, 3 * h)           # d W_u
+        seg = _empty(b * l, h, device=dev)                                   # sum of dh1 over the FS samples of a frame
+        ops.repeat_rows_bwd(dh1, b * l, h, h, fsz, seg, h)
+        ops.gemm_tn(seg, c_frame, d_cw[:, h:], h, h, b * l, h, h, 3 * h)                   # d W_c
         de = _empty(m, h, device=dev)
-        dc = _empty(m, h, device=dev)
         dupper = _empty(m, h, device=dev)
-        for j, dst in enumerate((de, dc, dupper)):
-            ops.gemm_nt(dh1, wcomb_t[j * h:], dst, m, h, h, h, h, h)
-        # conds_expand (frame rate)
+        ops.gemm_nt(dh1, wcomb_t, de, m, h, h, h, h, h)
+        ops.gemm_nt(dh1, wcomb_t[2 * h:], dupper, m, h, h, h, h, h)
         dc_frame = _empty(b * l, h, device=dev)
-        ops.repeat_rows_bwd(dc, b * l, h, h, fsz, dc_frame, h)
+        ops.gemm_nt(seg, wcomb_t[h:], dc_frame, b * l, h, h, h, h, h)
+        # conds_expand (frame rate)
         d_csb = ops.colsum(dc_frame, b * l, h, h)
         dwcs = _zeros(h, cp, device=dev)
         ops.gemm_tn(dc_frame, conds_b, dwcs, h, cp, b * l, h, cp, cp)
