@@ -506,10 +506,24 @@ static int run_tn(const srnn_gemm_args* a, GemmParams& p, cudaStream_t stream) {
   p.kb_per_batch = (a->k + BK - 1) / BK;
   p.total_kb = p.kb_per_batch * a->batch;
   const int tiles = p.tiles_m * p.tiles_n;
-  int splits = (2 * sm_count() + tiles - 1) / tiles;
-  if (splits > p.total_kb) splits = p.total_kb;
-  if (splits < 1) splits = 1;
-  p.kb_per_split = (p.total_kb + splits - 1) / splits;
+  // split-K factor: the persistent grid runs ceil(items / SMs) rounds, each costing the K-blocks of one
+  // split (4 MMAs x 128 cycles at BN=256) plus a full-tile fp32 atomic epilogue (contended when many
+  // splits hit the same tile).  Minimise rounds x (K-blocks per split x 512 + 32768) cycles: e.g. 32 tiles
+  // -> 9 splits = 288 items = 2 full rounds instead of 10 splits = 320 items = 3 rounds.
+  const int sms = sm_count();
+  int best = 1;
+  double best_cost = 1e30;
+  for (int sp = 1; sp <= 64 && sp <= p.total_kb; ++sp) {
+    const long long items = static_cast<long long>(tiles) * sp;
+    const long long rounds = (items + sms - 1) / sms;
+    const long long kb = (p.total_kb + sp - 1) / sp;
+    const double cost = static_cast<double>(rounds) * (static_cast<double>(kb) * 512.0 + 32768.0);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = sp;
+    }
+  }
+  p.kb_per_split = (p.total_kb + best - 1) / best;
   p.splits = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.total_work = tiles * p.splits;
   CUtensorMap ta, tb;
