@@ -259,12 +259,23 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         phase ^= 1;
         if (mw == 0) GRU_TS(2, s);
         tc_fence_after();
+        // running descriptors: only the 14-bit start-address field (low word) changes, so each MMA
+        // costs two 32-bit adds instead of rebuilding two 64-bit descriptors (the issue thread is the
+        // bottleneck here: ~27 SASS instructions per MMA before this change)
+        uint32_t a_lo = static_cast<uint32_t>(a_base) + ((mw * 32) >> 4);
+        uint32_t b_lo = static_cast<uint32_t>(b_base) + ((mw * 32) >> 4);
+        const uint32_t a_hi = static_cast<uint32_t>(a_base >> 32), b_hi = static_cast<uint32_t>(b_base >> 32);
+        const uint32_t d_tmem = tmem_base + mw * NCOLS;
+#pragma unroll 2
         for (int kb = 0; kb < KBC; ++kb) {
 #pragma unroll
-          for (int k16 = mw; k16 < 4; k16 += GRU_MMA_WARPS) {
-            umma_bf16(tmem_base + mw * NCOLS, a_base + ((kb * GRU_SLOT + k16 * 32) >> 4),
-                      b_base + ((kb * WBLOCK + k16 * 32) >> 4), IDESC, (kb > 0 || k16 >= GRU_MMA_WARPS) ? 1u : 0u);
+          for (int j = 0; j < 4 / GRU_MMA_WARPS; ++j) {
+            const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + j * ((GRU_MMA_WARPS * 32) >> 4));
+            const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + j * ((GRU_MMA_WARPS * 32) >> 4));
+            umma_bf16(d_tmem, ad, bd, IDESC, (kb > 0 || j > 0) ? 1u : 0u);
           }
+          a_lo += GRU_SLOT >> 4;
+          b_lo += WBLOCK >> 4;
         }
         umma_commit(acc_full);
         if (mw == 0) GRU_TS(3, s);
