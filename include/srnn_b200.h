@@ -134,6 +134,8 @@ typedef struct srnn_gemm_args {
   int32_t relu;               /* apply max(.,0) last */
   int32_t aux_row_div;        /* 0/1: aux row = output row; d > 1: aux row = row / d (a term that is constant
                                  over groups of d rows, e.g. the conditioning of the d samples of one frame) */
+  int32_t max_ctas;           /* 0: one persistent CTA per SM; n > 0: at most n CTAs (leaves SMs to a kernel that
+                                 runs concurrently on another stream, e.g. the persistent recurrence) */
 } srnn_gemm_args;
 
 int srnn_gemm_bf16(const srnn_gemm_args* args, srnn_stream_t stream);
@@ -186,7 +188,8 @@ typedef struct srnn_gru_args {
   uint32_t* sync;        /* >= 4*(hidden/8) bytes (one flag per CTA), zeroed by the caller before every launch */
   int32_t debug_flags;   /* must be 0.  Timing experiments only (results are WRONG when set):
                             1 = do not wait on the grid counter, 2 = skip TMA loads and MMAs,
-                            4 = skip the per-step global loads/stores of the epilogue */
+                            4 = skip the per-step global loads/stores of the epilogue;
+                            16 = (results stay correct) add a gpu-scope acquire fence after the grid wait */
   uint64_t* debug_ts;    /* NULL, or [256][8] clock64 stamps of CTA 0's pipeline events (profiling aid) */
   /* LSTM extension (cell = 1; no reference counterpart, torch.nn.LSTM semantics, gates i,f,g,o): every
    * "3H" above becomes 4H, `gates` is [batch*steps, 5H] (i, f, g, o, c_t). */
@@ -194,6 +197,8 @@ typedef struct srnn_gru_args {
   float* c_state;        /* LSTM fwd: fp32 [batch, H] cell state, in = c_init, out = c_T */
   const float* c_init;   /* LSTM bwd: the cell state the forward started from */
   float* dc0;            /* LSTM bwd out: dL/dc_init */
+  int32_t units_per_cta; /* 0 or 8: H/8 CTAs (fastest step); 16: H/16 CTAs, leaving SMs free for kernels that run
+                            concurrently on another stream (falls back to 8 if H % 32 != 0) */
 } srnn_gru_args;
 
 int srnn_gru_forward(const srnn_gru_args* args, srnn_stream_t stream);

@@ -23,7 +23,7 @@ class GemmArgs(C.Structure):
         ('c_dtype', C.c_int32), ('n_fold', C.c_int32),
         ('bias', C.c_void_p),
         ('aux', C.c_void_p), ('ldaux', C.c_int64), ('aux_batch_stride', C.c_int64),
-        ('aux_mode', C.c_int32), ('relu', C.c_int32), ('aux_row_div', C.c_int32),
+        ('aux_mode', C.c_int32), ('relu', C.c_int32), ('aux_row_div', C.c_int32), ('max_ctas', C.c_int32),
     ]
 
 
@@ -49,6 +49,7 @@ class GruArgs(C.Structure):
         ('dh_out', C.c_void_p), ('dgi', C.c_void_p), ('dgh', C.c_void_p), ('dh0', C.c_void_p),
         ('sync', C.c_void_p), ('debug_flags', C.c_int32), ('debug_ts', C.c_void_p),
         ('cell', C.c_int32), ('c_state', C.c_void_p), ('c_init', C.c_void_p), ('dc0', C.c_void_p),
+        ('units_per_cta', C.c_int32),
     ]
 
 

@@ -37,7 +37,7 @@ struct GemmParams {
   const float* bias;
   const __nv_bfloat16* aux;
   long long ldaux, aux_batch_stride;
-  int aux_mode, relu, aux_row_div;
+  int aux_mode, relu, aux_row_div, max_ctas;
   // schedule
   int tiles_m, tiles_n, kb_per_batch, splits, kb_per_split, total_kb, total_work;
   // NLL epilogue
@@ -451,7 +451,9 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     SRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemCfg<BN>::TOTAL));
     configured = true;
   }
-  int grid = p.total_work < sm_count() ? p.total_work : sm_count();
+  int cap = sm_count();
+  if (p.max_ctas > 0 && p.max_ctas < cap) cap = p.max_ctas;    // leave SMs to a concurrently running kernel
+  int grid = p.total_work < cap ? p.total_work : cap;
   if (grid < 1) return SRNN_OK;
   kern<<<grid, gemm_threads<EPI>(), SmemCfg<BN>::TOTAL, stream>>>(ta, tb, p);
   SRNN_CUDA(cudaGetLastError());
@@ -510,7 +512,8 @@ static int run_tn(const srnn_gemm_args* a, GemmParams& p, cudaStream_t stream) {
   // split (4 MMAs x 128 cycles at BN=256) plus a full-tile fp32 atomic epilogue (contended when many
   // splits hit the same tile).  Minimise rounds x (K-blocks per split x 512 + 32768) cycles: e.g. 32 tiles
   // -> 9 splits = 288 items = 2 full rounds instead of 10 splits = 320 items = 3 rounds.
-  const int sms = sm_count();
+  int sms = sm_count();
+  if (p.max_ctas > 0 && p.max_ctas < sms) sms = p.max_ctas;
   int best = 1;
   double best_cost = 1e30;
   for (int sp = 1; sp <= 64 && sp <= p.total_kb; ++sp) {
@@ -566,6 +569,7 @@ extern "C" int srnn_gemm_bf16(const srnn_gemm_args* a, srnn_stream_t stream_) {
   p.aux = static_cast<const __nv_bfloat16*>(a->aux); p.ldaux = a->ldaux; p.aux_batch_stride = a->aux_batch_stride;
   p.aux_mode = a->aux ? a->aux_mode : 0; p.relu = a->relu;
   p.aux_row_div = a->aux_row_div > 0 ? a->aux_row_div : 1;
+  p.max_ctas = a->max_ctas;
   if (a->op == 0) {
     SRNN_CHECK_ARG(a->n_fold == 0 || (a->n % a->n_fold == 0 && a->n_fold % 32 == 0 && !a->aux),
                    "gemm NT: n_fold must divide n, be a multiple of 32, and exclude aux");

@@ -30,7 +30,8 @@ namespace srnn {
 
 constexpr int GRU_THREADS = 224;   // warp 0 TMA, warps 1 and 6 MMA issuers, warps 2-5 epilogue
 constexpr int GRU_MMA_WARPS = 2;   // tcgen05.mma issue is ~60 cycles per instruction from one thread
-constexpr int GRU_U = 8;           // hidden units finalised per CTA
+// hidden units finalised per CTA: 8 (H/8 CTAs, the fastest step) or 16 (H/16 CTAs, which leaves more than
+// half of the SMs free for GEMMs running concurrently on another stream)
 constexpr int GRU_M = 64;          // batch rows per launch (MMA M)
 constexpr int GRU_SLOT = GRU_M * 128;   // one [64 rows][64 bf16] K block
 
@@ -75,6 +76,29 @@ __device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* p, float (&out)
   out[4] = bf16_lo(u.z); out[5] = bf16_hi(u.z);
   out[6] = bf16_lo(u.w); out[7] = bf16_hi(u.w);
 }
+template <int U>
+__device__ __forceinline__ void load_units(const __nv_bfloat16* p, float (&out)[U]) {
+#pragma unroll
+  for (int i = 0; i < U / 8; ++i) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p + i * 8);
+    out[i * 8 + 0] = bf16_lo(u.x); out[i * 8 + 1] = bf16_hi(u.x);
+    out[i * 8 + 2] = bf16_lo(u.y); out[i * 8 + 3] = bf16_hi(u.y);
+    out[i * 8 + 4] = bf16_lo(u.z); out[i * 8 + 5] = bf16_hi(u.z);
+    out[i * 8 + 6] = bf16_lo(u.w); out[i * 8 + 7] = bf16_hi(u.w);
+  }
+}
+template <int U>
+__device__ __forceinline__ void store_units(__nv_bfloat16* p, const float (&v)[U]) {
+#pragma unroll
+  for (int i = 0; i < U / 8; ++i) {
+    uint4 u;
+    u.x = pack_bf16x2(v[i * 8 + 0], v[i * 8 + 1]);
+    u.y = pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
+    u.z = pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]);
+    u.w = pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7]);
+    *reinterpret_cast<uint4*>(p + i * 8) = u;
+  }
+}
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float (&v)[8]) {
   uint4 u;
   u.x = pack_bf16x2(v[0], v[1]);
@@ -95,13 +119,19 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
 __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// Consumer side of the grid handshake.  The producers order their data stores before the counter
+// increment (release: MEMBAR.GPU + RED), so once the counter value has been READ here, the data are
+// already performed at L2.  The only consumer of that data is the TMA load issued below, which (a) is
+// control-dependent on the value read, (b) follows a generic->async proxy fence and (c) reads L2, never
+// this SM's L1.  A full gpu-scope acquire fence here (MEMBAR.ALL.GPU + CCTL.IVALL in SASS) therefore buys
+// nothing the TMA needs and costs ~900 cycles per timestep (0.5 us of ~5), so it is optional
+// (debug flag 16 re-enables it; tests/test_gpu_kernels.py::test_gru_grid_handshake_stress_bit_exact
+// checks 10 M handshakes bit-exactly both ways).
 __device__ __forceinline__ void grid_wait(const uint32_t* counter, uint32_t target, bool acquire_fence) {
   uint32_t spins = 0;
   while (ld_relaxed_gpu(counter) < target) {
     if (++spins > (1u << 24)) __trap();
   }
-  // acquire pattern = relaxed polling + ONE fence (an acquire load per iteration costs a gpu-scope
-  // fence and an L1 invalidation every time round the loop)
   if (acquire_fence) asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
@@ -160,10 +190,9 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 
 // LSTM = false: GRU (gates r,z,n; 3H pre-activations).  LSTM = true: LSTM (gates i,f,g,o; 4H), an
 // extension with no reference counterpart (BASELINE config 3; torch.nn.LSTM semantics, see oracle).
-template <bool BWD, int C, bool LSTM>
+template <bool BWD, int C, bool LSTM, int U>
 __global__ void __launch_bounds__(GRU_THREADS, 1)
 gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_x, const GruParams p) {
-  constexpr int U = GRU_U;
   constexpr int UC = U * C;                          // units owned by the cluster
   constexpr int GATES = LSTM ? 4 : 3;
   constexpr int NG = BWD ? 1 : GATES;
@@ -233,7 +262,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       for (int s = 0; s < rounds; ++s) {
         if (BWD && s == 0) continue;                 // the last timestep has no recurrent input
         if (s > 0 && !(p.flags & 1)) {
-          grid_wait(p.sync, G * static_cast<uint32_t>(s), !(p.flags & 8));
+          grid_wait(p.sync, G * static_cast<uint32_t>(s), (p.flags & 16) != 0);
           GRU_TS(0, s);
         }
         asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy writes -> TMA reads
@@ -344,8 +373,8 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
 #pragma unroll
                 for (int pw = 0; pw < GRU_MMA_WARPS; ++pw) f[i] += __uint_as_float(v[pw][e * 8 + i]);
               }
-              const int g = col / UC, dst = (col % UC) / U;
-              const uint32_t off = static_cast<uint32_t>((((crank * NG + g) * GRU_M + row) * U) * 4);
+              const int g = col / UC, dst = (col % UC) / U, sub = (col % U) / 8;
+              const uint32_t off = static_cast<uint32_t>((((crank * NG + g) * GRU_M + row) * U + sub * 8) * 4);
               const uint32_t ra = mapa(part_addr + off, static_cast<uint32_t>(dst));
               const uint32_t rb = mapa(ready_addr, static_cast<uint32_t>(dst));
               st_async_v4(ra, f[0], f[1], f[2], f[3], rb);
@@ -367,9 +396,12 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
 #pragma unroll
           for (int g = 0; g < NG; ++g) {
             const float4* rp = reinterpret_cast<const float4*>(part + ((r * NG + g) * GRU_M + row) * U);
-            const float4 a = rp[0], b = rp[1];
-            out[g * U + 0] += a.x; out[g * U + 1] += a.y; out[g * U + 2] += a.z; out[g * U + 3] += a.w;
-            out[g * U + 4] += b.x; out[g * U + 5] += b.y; out[g * U + 6] += b.z; out[g * U + 7] += b.w;
+#pragma unroll
+            for (int i4 = 0; i4 < U / 4; ++i4) {
+              const float4 a = rp[i4];
+              out[g * U + i4 * 4 + 0] += a.x; out[g * U + i4 * 4 + 1] += a.y;
+              out[g * U + i4 * 4 + 2] += a.z; out[g * U + i4 * 4 + 3] += a.w;
+            }
           }
       }
     };
@@ -393,10 +425,10 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         for (int i = 0; i < U; ++i) xi[i] = xf[i] = xg[i] = xo[i] = 0.f;
         if (io) {
           const __nv_bfloat16* gp = p.gi + rt * 4 * H + u0;
-          load_bf16x8(gp, xi);
-          load_bf16x8(gp + H, xf);
-          load_bf16x8(gp + 2 * H, xg);
-          load_bf16x8(gp + 3 * H, xo);
+          load_units<U>(gp, xi);
+          load_units<U>(gp + H, xf);
+          load_units<U>(gp + 2 * H, xg);
+          load_units<U>(gp + 3 * H, xo);
         }
         float acc[4 * U];
         exchange(acc, t);
@@ -410,17 +442,17 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           c[i] = gf_[i] * c[i] + gi_[i] * gg_[i];
           h[i] = go_[i] * tanh_fast(c[i]);
         }
-        if (io) store_bf16x8(p.h_ext + (static_cast<long long>(t + 1) * EB + row) * H + u0, h);
+        if (io) store_units<U>(p.h_ext + (static_cast<long long>(t + 1) * EB + row) * H + u0, h);
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (warp == 2 && lane == 0) red_release_gpu_add(p.sync, 1u);
-        if (p.hall && io) store_bf16x8(p.hall + rt * H + u0, h);
+        if (p.hall && io) store_units<U>(p.hall + rt * H + u0, h);
         if (p.gates && io) {                           // saved for backward: i, f, g, o, c_t  (5H per row)
           __nv_bfloat16* sp = p.gates + rt * 5 * H + u0;
-          store_bf16x8(sp, gi_);
-          store_bf16x8(sp + H, gf_);
-          store_bf16x8(sp + 2 * H, gg_);
-          store_bf16x8(sp + 3 * H, go_);
-          store_bf16x8(sp + 4 * H, c);
+          store_units<U>(sp, gi_);
+          store_units<U>(sp + H, gf_);
+          store_units<U>(sp + 2 * H, gg_);
+          store_units<U>(sp + 3 * H, go_);
+          store_units<U>(sp + 4 * H, c);
         }
       }
       if (row_ok) {
@@ -442,15 +474,15 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
 #pragma unroll
         for (int i = 0; i < U; ++i) dh[i] = gi_[i] = gf_[i] = gg_[i] = go_[i] = ct[i] = cp[i] = 0.f;
         if (io && t >= 0) {
-          load_bf16x8(p.dh_out + rt * H + u0, dh);
+          load_units<U>(p.dh_out + rt * H + u0, dh);
           const __nv_bfloat16* sp = p.gates + rt * 5 * H + u0;
-          load_bf16x8(sp, gi_);
-          load_bf16x8(sp + H, gf_);
-          load_bf16x8(sp + 2 * H, gg_);
-          load_bf16x8(sp + 3 * H, go_);
-          load_bf16x8(sp + 4 * H, ct);
+          load_units<U>(sp, gi_);
+          load_units<U>(sp + H, gf_);
+          load_units<U>(sp + 2 * H, gg_);
+          load_units<U>(sp + 3 * H, go_);
+          load_units<U>(sp + 4 * H, ct);
           if (t > 0) {
-            load_bf16x8(p.gates + (rt - 1) * 5 * H + 4 * H + u0, cp);
+            load_units<U>(p.gates + (rt - 1) * 5 * H + 4 * H + u0, cp);
           } else {
 #pragma unroll
             for (int i = 0; i < U; ++i) cp[i] = p.c_init[static_cast<long long>(row) * H + u0 + i];
@@ -484,19 +516,19 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         }
         if (io) {
           __nv_bfloat16* ghp = p.dgh + (static_cast<long long>(t) * EB + row) * 4 * H + u0;   // exchanged
-          store_bf16x8(ghp, pi);
-          store_bf16x8(ghp + H, pf);
-          store_bf16x8(ghp + 2 * H, pg);
-          store_bf16x8(ghp + 3 * H, po);
+          store_units<U>(ghp, pi);
+          store_units<U>(ghp + H, pf);
+          store_units<U>(ghp + 2 * H, pg);
+          store_units<U>(ghp + 3 * H, po);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (warp == 2 && lane == 0) red_release_gpu_add(p.sync, 1u);
         if (io) {                                               // same values, batch-major, for the GEMMs
           __nv_bfloat16* gip = p.dgi + rt * 4 * H + u0;
-          store_bf16x8(gip, pi);
-          store_bf16x8(gip + H, pf);
-          store_bf16x8(gip + 2 * H, pg);
-          store_bf16x8(gip + 3 * H, po);
+          store_units<U>(gip, pi);
+          store_units<U>(gip + H, pf);
+          store_units<U>(gip + 2 * H, pg);
+          store_units<U>(gip + 3 * H, po);
         }
       }
     } else if constexpr (!BWD) {
@@ -515,9 +547,9 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         for (int i = 0; i < U; ++i) gr[i] = gz[i] = gn[i] = 0.f;
         if (io) {
           const __nv_bfloat16* gp = p.gi + rt * 3 * H + u0;
-          load_bf16x8(gp, gr);
-          load_bf16x8(gp + H, gz);
-          load_bf16x8(gp + 2 * H, gn);
+          load_units<U>(gp, gr);
+          load_units<U>(gp + H, gz);
+          load_units<U>(gp + 2 * H, gn);
         }
         float acc[3 * U];
         exchange(acc, t);
@@ -530,7 +562,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           n[i] = tanh_fast(gn[i] + r[i] * hn[i]);
           h[i] = (1.f - z[i]) * n[i] + z[i] * h[i];
         }
-        if (io) store_bf16x8(p.h_ext + (static_cast<long long>(t + 1) * EB + row) * H + u0, h);
+        if (io) store_units<U>(p.h_ext + (static_cast<long long>(t + 1) * EB + row) * H + u0, h);
         // publish h_t: all epilogue threads' stores -> one release arrival per CTA
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (warp == 2 && lane == 0) {
@@ -538,13 +570,13 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           red_release_gpu_add(p.sync, 1u);
         }
         // the batch-major copy of h_t (GEMM operand) and the saved gates are off the critical path
-        if (p.hall && io) store_bf16x8(p.hall + rt * H + u0, h);
+        if (p.hall && io) store_units<U>(p.hall + rt * H + u0, h);
         if (p.gates && io) {
           __nv_bfloat16* sp = p.gates + rt * 4 * H + u0;
-          store_bf16x8(sp, r);
-          store_bf16x8(sp + H, z);
-          store_bf16x8(sp + 2 * H, n);
-          store_bf16x8(sp + 3 * H, hn);
+          store_units<U>(sp, r);
+          store_units<U>(sp + H, z);
+          store_units<U>(sp + 2 * H, n);
+          store_units<U>(sp + 3 * H, hn);
         }
       }
       if (row_ok) {
@@ -562,13 +594,13 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
 #pragma unroll
         for (int i = 0; i < U; ++i) dh[i] = r[i] = z[i] = n[i] = hn[i] = hp[i] = 0.f;
         if (io && t >= 0) {
-          load_bf16x8(p.dh_out + rt * H + u0, dh);
+          load_units<U>(p.dh_out + rt * H + u0, dh);
           const __nv_bfloat16* sp = p.gates + rt * 4 * H + u0;
-          load_bf16x8(sp, r);
-          load_bf16x8(sp + H, z);
-          load_bf16x8(sp + 2 * H, n);
-          load_bf16x8(sp + 3 * H, hn);
-          load_bf16x8(p.h_ext + (static_cast<long long>(t) * EB + row) * H + u0, hp);
+          load_units<U>(sp, r);
+          load_units<U>(sp + H, z);
+          load_units<U>(sp + 2 * H, n);
+          load_units<U>(sp + 3 * H, hn);
+          load_units<U>(p.h_ext + (static_cast<long long>(t) * EB + row) * H + u0, hp);
         }
         float d[U];
 #pragma unroll
@@ -597,17 +629,17 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         }
         if (io) {
           __nv_bfloat16* ghp = p.dgh + (static_cast<long long>(t) * EB + row) * 3 * H + u0;   // exchanged
-          store_bf16x8(ghp, gr);
-          store_bf16x8(ghp + H, gz);
-          store_bf16x8(ghp + 2 * H, ghn);
+          store_units<U>(ghp, gr);
+          store_units<U>(ghp + H, gz);
+          store_units<U>(ghp + 2 * H, ghn);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (warp == 2 && lane == 0) red_release_gpu_add(p.sync, 1u);
         if (io) {                                               // dgi is only read after the kernel
           __nv_bfloat16* gip = p.dgi + rt * 3 * H + u0;
-          store_bf16x8(gip, gr);
-          store_bf16x8(gip + H, gz);
-          store_bf16x8(gip + 2 * H, gn);
+          store_units<U>(gip, gr);
+          store_units<U>(gip + H, gz);
+          store_units<U>(gip + 2 * H, gn);
         }
       }
     }
@@ -622,24 +654,24 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <bool BWD, int C, bool LSTM>
+template <bool BWD, int C, bool LSTM, int U>
 static size_t gru_smem_bytes(int kbc) {
-  const int ncols = (BWD ? 1 : (LSTM ? 4 : 3)) * GRU_U * C;
+  const int ncols = (BWD ? 1 : (LSTM ? 4 : 3)) * U * C;
   return static_cast<size_t>(kbc) * ncols * 128 + static_cast<size_t>(kbc) * GRU_SLOT +
          static_cast<size_t>(ncols) * GRU_M * 4 + 256 + 1024;
 }
 
 // Can H/8 CTAs in clusters of C all be resident at once (they spin on one another)?
-template <bool BWD, int C, bool LSTM>
+template <bool BWD, int C, bool LSTM, int U>
 static bool gru_fits(int H, int kbc) {
-  auto kern = gru_kernel<BWD, C, LSTM>;
-  const size_t smem = gru_smem_bytes<BWD, C, LSTM>(kbc);
+  auto kern = gru_kernel<BWD, C, LSTM, U>;
+  const size_t smem = gru_smem_bytes<BWD, C, LSTM, U>(kbc);
   if (smem > 227 * 1024) return false;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     cudaGetLastError();
     return false;
   }
-  const int ctas = H / GRU_U;
+  const int ctas = H / U;
   if (C == 1) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GRU_THREADS, smem) != cudaSuccess) {
@@ -667,20 +699,20 @@ static bool gru_fits(int H, int kbc) {
   return clusters * C >= ctas;
 }
 
-template <bool BWD, int C, bool LSTM>
+template <bool BWD, int C, bool LSTM, int U>
 static int launch_gru(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   constexpr int GATES = LSTM ? 4 : 3;
   const int H = a->hidden, T = a->steps, B = a->batch;
   const int K = BWD ? GATES * H : H;
-  const int ctas = H / GRU_U;
-  const size_t smem = gru_smem_bytes<BWD, C, LSTM>(kbc);
+  const int ctas = H / U;
+  const size_t smem = gru_smem_bytes<BWD, C, LSTM, U>(kbc);
 
   CUtensorMap tw, tx;
   {
     // forward: W_hh [3H, H] rows = gate rows; backward: W_hh^T [H, 3H] rows = units
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)(BWD ? H : GATES * H)};
     const uint64_t strides[1] = {(uint64_t)K * 2};
-    const uint32_t box[2] = {64, (uint32_t)(GRU_U * C)};
+    const uint32_t box[2] = {64, (uint32_t)(U * C)};
     int rc = make_tmap_bf16(&tw, a->w_hh, 2, dims, strides, box, true);
     if (rc) return rc;
   }
@@ -712,7 +744,7 @@ static int launch_gru(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   p.flags = a->debug_flags;
   p.ts = reinterpret_cast<unsigned long long*>(a->debug_ts);
 
-  auto kern = gru_kernel<BWD, C, LSTM>;
+  auto kern = gru_kernel<BWD, C, LSTM, U>;
   SRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ctas);
@@ -737,25 +769,33 @@ static int launch_gru(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   return SRNN_OK;
 }
 
-// Largest cluster size whose K split is whole K blocks, whose units tile H and whose slice fits smem.
-template <bool BWD, bool LSTM>
+// Cluster size: K split in whole K blocks, units tile H, slice fits smem, all clusters co-resident.
+template <bool BWD, bool LSTM, int U>
 static int pick_cluster(int H, int* kbc_out) {
   const int K = BWD ? (LSTM ? 4 : 3) * H : H;
   const int kb_total = (K + 63) / 64;
-  // measured (B=64, H=1024): forward 6.2 us/step at C=2 vs 6.8 at C=4 (DSMEM exchange volume grows
-  // with C); backward needs C>=4 for the 3H-wide slice to fit shared memory
+  // measured (B=64, H=1024, U=8): forward 5.0 us/step at C=2 vs 6.0 at C=4 (exchange volume grows with
+  // C); backward needs C>=4 for the 3H-wide slice to fit shared memory
   const int fwd_order[4] = {2, 4, 8, 1};
   const int bwd_order[4] = {4, 8, 2, 1};
   for (int i = 0; i < 4; ++i) {
     const int c = BWD ? bwd_order[i] : fwd_order[i];
-    if (kb_total % c != 0 || H % (GRU_U * c) != 0) continue;
+    if (kb_total % c != 0 || H % (U * c) != 0) continue;
     const int kbc = kb_total / c;
     bool fits = false;
-    switch (c) {
-      case 8: fits = gru_fits<BWD, 8, LSTM>(H, kbc); break;
-      case 4: fits = gru_fits<BWD, 4, LSTM>(H, kbc); break;
-      case 2: fits = gru_fits<BWD, 2, LSTM>(H, kbc); break;
-      default: fits = gru_fits<BWD, 1, LSTM>(H, kbc); break;
+    if constexpr (U == 8) {
+      switch (c) {
+        case 8: fits = gru_fits<BWD, 8, LSTM, 8>(H, kbc); break;
+        case 4: fits = gru_fits<BWD, 4, LSTM, 8>(H, kbc); break;
+        case 2: fits = gru_fits<BWD, 2, LSTM, 8>(H, kbc); break;
+        default: fits = gru_fits<BWD, 1, LSTM, 8>(H, kbc); break;
+      }
+    } else {                                           // wide CTAs: clusters of 2 or 4 only (MMA N <= 256)
+      switch (c) {
+        case 4: fits = gru_fits<BWD, 4, LSTM, 16>(H, kbc); break;
+        case 2: fits = gru_fits<BWD, 2, LSTM, 16>(H, kbc); break;
+        default: fits = false; break;
+      }
     }
     if (!fits) continue;
     *kbc_out = kbc;
@@ -764,11 +804,11 @@ static int pick_cluster(int H, int* kbc_out) {
   return 0;
 }
 
-template <bool BWD, bool LSTM>
-static int dispatch_gru(const srnn_gru_args* a, cudaStream_t stream) {
-  static int cached_h = -1, cached_c = 0, cached_kbc = 0;      // per instantiation (fwd / bwd)
+template <bool BWD, bool LSTM, int U>
+static int dispatch_gru_u(const srnn_gru_args* a, cudaStream_t stream) {
+  static int cached_h = -1, cached_c = 0, cached_kbc = 0;      // per instantiation
   if (cached_h != a->hidden) {
-    cached_c = pick_cluster<BWD, LSTM>(a->hidden, &cached_kbc);
+    cached_c = pick_cluster<BWD, LSTM, U>(a->hidden, &cached_kbc);
     cached_h = a->hidden;
   }
   int kbc = cached_kbc;
@@ -776,20 +816,46 @@ static int dispatch_gru(const srnn_gru_args* a, cudaStream_t stream) {
   if (a->debug_flags >> 8) {                         // experiments: force a cluster size (bits 8..)
     const int forced = a->debug_flags >> 8;
     const int kb_total = ((BWD ? (LSTM ? 4 : 3) : 1) * a->hidden + 63) / 64;
-    if (kb_total % forced == 0 && a->hidden % (GRU_U * forced) == 0) {
+    if (kb_total % forced == 0 && a->hidden % (U * forced) == 0) {
       c = forced;
       kbc = kb_total / forced;
     }
   }
-  SRNN_CHECK_ARG(c > 0, "gru: no cluster decomposition fits hidden=%d", a->hidden);
-  SRNN_CHECK_ARG(a->hidden / GRU_U <= sm_count(), "gru: hidden/8 = %d CTAs exceeds the SM count %d", a->hidden / GRU_U,
-                 sm_count());
-  switch (c) {
-    case 8: return launch_gru<BWD, 8, LSTM>(a, kbc, stream);
-    case 4: return launch_gru<BWD, 4, LSTM>(a, kbc, stream);
-    case 2: return launch_gru<BWD, 2, LSTM>(a, kbc, stream);
-    default: return launch_gru<BWD, 1, LSTM>(a, kbc, stream);
+  SRNN_CHECK_ARG(c > 0, "gru: no cluster decomposition fits hidden=%d with %d units per CTA", a->hidden, U);
+  if constexpr (U == 8) {
+    switch (c) {
+      case 8: return launch_gru<BWD, 8, LSTM, 8>(a, kbc, stream);
+      case 4: return launch_gru<BWD, 4, LSTM, 8>(a, kbc, stream);
+      case 2: return launch_gru<BWD, 2, LSTM, 8>(a, kbc, stream);
+      default: return launch_gru<BWD, 1, LSTM, 8>(a, kbc, stream);
+    }
+  } else {
+    switch (c) {
+      case 4: return launch_gru<BWD, 4, LSTM, 16>(a, kbc, stream);
+      default: return launch_gru<BWD, 2, LSTM, 16>(a, kbc, stream);
+    }
   }
+}
+
+template <bool BWD, bool LSTM>
+static int dispatch_gru(const srnn_gru_args* a, cudaStream_t stream) {
+  // 16 units per CTA when asked for (and possible), else 8; more than the SM count of CTAs never fits
+  bool wide = a->units_per_cta == 16 && a->hidden % 32 == 0;
+  if (wide) {                                          // fall back to 8 units when the wide slice does not fit
+    static int probed_h = -1, probed_c = 0;
+    if (probed_h != a->hidden) {
+      int kbc = 0;
+      probed_c = pick_cluster<BWD, LSTM, 16>(a->hidden, &kbc);
+      probed_h = a->hidden;
+    }
+    wide = probed_c > 0;
+  }
+  if (!wide) {
+    SRNN_CHECK_ARG(a->hidden / 8 <= sm_count(), "gru: hidden/8 = %d CTAs exceeds the SM count %d", a->hidden / 8,
+                   sm_count());
+    return dispatch_gru_u<BWD, LSTM, 8>(a, stream);
+  }
+  return dispatch_gru_u<BWD, LSTM, 16>(a, stream);
 }
 
 }  // namespace srnn
@@ -805,6 +871,8 @@ static int check_common(const srnn_gru_args* a) {
   SRNN_CHECK_ARG(a->w_hh && a->h_ext && a->gates && a->sync, "gru: null buffer");
   SRNN_CHECK_ARG(a->ext_batch >= a->batch, "gru: ext_batch (%d) must be >= batch (%d)", a->ext_batch, a->batch);
   SRNN_CHECK_ARG(a->cell == 0 || a->cell == 1, "gru: cell must be 0 (GRU) or 1 (LSTM)");
+  SRNN_CHECK_ARG(a->units_per_cta == 0 || a->units_per_cta == 8 || a->units_per_cta == 16,
+                 "gru: units_per_cta must be 0, 8 or 16");
   return SRNN_OK;
 }
 

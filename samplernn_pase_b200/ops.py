@@ -23,6 +23,9 @@ def _count(n=1):
     launch_count += n
 
 
+#: > 0 caps the persistent GEMM grids (set while GEMMs share the GPU with a recurrent kernel on another stream)
+gemm_max_ctas = 0
+
 #: when a dict, ``timed(tag)`` brackets the enclosed launches with CUDA events on the current stream
 #: and appends (start, end) to ``event_log[tag]``; bench.py reads them after the timed region.
 event_log = None
@@ -220,6 +223,7 @@ def gemm_nt(a, b, c, m, n, k, lda, ldb, ldc, batch=1, a_bs=0, c_bs=0, bias=None,
     g.ldaux, g.aux_batch_stride, g.aux_mode = ldaux, aux_bs, aux_mode if aux is not None else 0
     g.relu = int(relu)
     g.aux_row_div = aux_row_div
+    g.max_ctas = gemm_max_ctas
     _lib.profile_note = f'NT m={m}x{batch} n={n} k={k}'
     call('srnn_gemm_bf16', C.byref(g), stream())
     _count()
@@ -237,6 +241,7 @@ def gemm_tn(a, b, c, m, n, k, lda, ldb, ldc, batch=1, a_bs=0, b_bs=0, a_off=0, b
     g.b, g.ldb, g.b_batch_stride, g.b_row_offset = b.data_ptr(), ldb, b_bs, b_off
     g.c, g.ldc, g.c_batch_stride = c.data_ptr(), ldc, 0
     g.c_dtype = 1
+    g.max_ctas = gemm_max_ctas
     _lib.profile_note = f'TN m={m} n={n} k={k}x{batch}'
     call('srnn_gemm_bf16', C.byref(g), stream())
     _count()
@@ -267,6 +272,7 @@ def gemm_nll(mode, a, w, bias, target, m, k, lda, ldw, lse=None, logp_target=Non
 GRU_MAX_BATCH = 64
 gru_debug_flags = 0      # timing experiments only (scripts/gru_microbench.py)
 gru_debug_ts = None      # int64 [256, 8] tensor receiving CTA 0's pipeline timestamps
+gru_units_per_cta = 8    # 16 halves the recurrent kernels' CTA count (SMs left free for concurrent GEMMs)
 
 
 def _gru_call(name, batch, steps, hidden, cell=0, **bufs):
@@ -284,6 +290,7 @@ def _gru_call(name, batch, steps, hidden, cell=0, **bufs):
         sync = torch.zeros(256, dtype=torch.int32, device=bufs['h_ext'][0].device)
         a.sync = sync.data_ptr()
         a.debug_flags = gru_debug_flags
+        a.units_per_cta = gru_units_per_cta
         a.debug_ts = gru_debug_ts.data_ptr() if gru_debug_ts is not None else None
         _lib.profile_note = f'B={nb} T={steps} H={hidden}' + (' lstm' if cell else '')
         call(name, C.byref(a), stream())

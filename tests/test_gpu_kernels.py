@@ -282,6 +282,56 @@ def test_gru_backward(ops, bsz, t, h):
     assert rel_l2(dh0, h0_r.grad) < 3e-2, rel_l2(dh0, h0_r.grad)
 
 
+def test_gru_grid_handshake_stress_bit_exact(ops):
+    """The recurrence's forward data path has no atomics, so repeated launches must be BIT-identical; a
+    stale read across the grid-wide handshake (release counter -> relaxed polling -> proxy fence -> TMA) would
+    show up as a mismatch.  40 launches x 2000 steps x 128 CTAs = 10 M handshakes, with and without the
+    consumer-side acquire fence (debug flag 8)."""
+    bsz, t, h = 64, 2000, 1024
+    gi = rnd(bsz, t, 3 * h).to(BF16)
+    w_hh = rnd(3 * h, h, scale=1 / math.sqrt(h), seed=1).to(BF16)
+    b_hh = rnd(3 * h, scale=0.1, seed=2)
+    h0 = rnd(bsz, h, scale=0.5, seed=3)
+    dh_out = rnd(bsz, t, h, scale=0.1, seed=4).to(BF16)
+
+    def run(flags):
+        ops.gru_debug_flags = flags
+        try:
+            h_ext = torch.zeros(t + 1, bsz, h, dtype=BF16, device='cuda')
+            h_ext[0] = h0.to(BF16)
+            hall = torch.zeros(bsz * t, h, dtype=BF16, device='cuda')
+            h_state = h0.clone()
+            gates = torch.empty(bsz * t, 4 * h, dtype=BF16, device='cuda')
+            ops.gru_forward(gi.view(bsz * t, 3 * h), w_hh, b_hh, h_ext, hall, h_state, gates, bsz, t, h)
+            dgi = torch.empty(bsz * t, 3 * h, dtype=BF16, device='cuda')
+            dgh = torch.empty(bsz * t, 3 * h, dtype=BF16, device='cuda')
+            dh0 = torch.empty(bsz, h, dtype=F32, device='cuda')
+            ops.gru_backward(w_hh.t().contiguous(), h_ext, gates, dh_out.view(bsz * t, h), dgi, dgh, dh0, bsz, t, h)
+            return hall, h_state, dgi, dh0
+        finally:
+            ops.gru_debug_flags = 0
+
+    ref = run(16)                       # flag 16: keep the consumer-side acquire fence
+    for i in range(20):
+        for flags in (0, 16):
+            got = run(flags)
+            assert all(torch.equal(a, b) for a, b in zip(got, ref)), (i, flags)
+
+
+def test_gru_and_lstm_with_16_units_per_cta(ops):
+    """The half-grid variant of the recurrent kernels (H/16 CTAs) must give the same results."""
+    ops.gru_units_per_cta = 16
+    try:
+        test_gru_forward(ops, 64, 33, 1024)
+        test_gru_backward(ops, 64, 17, 1024)
+        test_gru_forward(ops, 8, 40, 128)
+        test_gru_backward(ops, 8, 40, 128)
+        test_lstm_forward_backward(ops, 64, 17, 1024)
+        test_lstm_forward_backward(ops, 8, 20, 128)
+    finally:
+        ops.gru_units_per_cta = 8
+
+
 @pytest.mark.parametrize('bsz,t,h', [(3, 5, 32), (8, 20, 64), (64, 17, 1024), (70, 6, 128)])
 def test_lstm_forward_backward(ops, bsz, t, h):
     """LSTM extension (BASELINE config 3; no reference counterpart): torch.nn.LSTM semantics, checked
