@@ -78,8 +78,12 @@ __device__ __forceinline__ Work decode_work(const GemmParams& p, int w) {
     wk.kb_begin = 0;
     wk.kb_end = p.kb_per_batch;
   } else {
-    int split = w % p.splits;
-    int tile = w / p.splits;
+    // split-major order: the CTAs that run at the same time work on the SAME K slab of different output
+    // tiles, so the A/B rows of that slab are fetched from HBM once and shared through L2 (tile-major order
+    // made every CTA stream private rows: 3x the algorithmic DRAM reads in ncu)
+    const int tiles = p.tiles_m * p.tiles_n;
+    int split = w / tiles;
+    int tile = w - split * tiles;
     wk.nt = tile % p.tiles_n;
     wk.mt = tile / p.tiles_n;
     wk.b = 0;
