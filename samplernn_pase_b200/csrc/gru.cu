@@ -221,7 +221,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           grid_wait(p.sync, G * static_cast<uint32_t>(s), (p.flags & 16) != 0);
           GRU_TS(0, s);
         }
-        asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy writes -> TMA reads
+        asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy writes -> TMA reads (free: measured)
         const int slot = BWD ? (T - s) : s;          // time slot of the exchange buffer
         mbar_expect_tx(full, bytes);
         for (int kb = 0; kb < KBC; ++kb) tma_load_3d(hbuf + kb * GRU_SLOT, &tma_x, full, (kb0 + kb) * 64, 0, slot);
