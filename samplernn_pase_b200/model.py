@@ -311,10 +311,10 @@ class SampleRNNModel(torch.nn.Module):
             y_hat, yq64 = y_hat.index_select(0, idx), yq64.index_select(0, idx)
         return y_hat, yq64
 
-    def test(self, utt_conds, info, return_logp=False, generator=None):
+    def test(self, utt_conds, info, return_logp=False, generator=None, use_graphs=True):
         """model.py:289-351: autoregressive generation.  ``utt_conds`` (B,t,U) - the reference is called
         with B == 1 and ``info`` a single dict; a list of dicts generates B utterances at once.  Returns
         int64 (B, (t+1)*frame_size) whose first frame_size entries are ``quantize_zero()``."""
         from .generate import generate
         self._init_rnn_states(0)                      # model.py:301: generation starts from rnn_h0
-        return generate(self, utt_conds, info, return_logp=return_logp, generator=generator)
+        return generate(self, utt_conds, info, return_logp=return_logp, generator=generator, use_graphs=use_graphs)

@@ -272,6 +272,20 @@ def test_generation_is_consistent_with_teacher_forcing():
     assert d <= 0.05, d
     single = model.test(utt[:1].cuda(), info[0])                               # the reference's calling convention
     assert single.shape == (1, (t + 1) * fs)
+    assert all(torch.equal(v.cpu(), params[k]) for k, v in model.state_dict().items())   # generation is read-only
+    # CUDA-graph path (default generator, frames >= 3): same consistency check on a longer utterance
+    t2 = 5
+    utt2 = torch.randn(bsz, t2, 43, generator=torch.Generator().manual_seed(4))
+    torch.cuda.manual_seed(11)
+    y2, logp2 = model.test(utt2.cuda(), info, return_logp=True)
+    y2 = y2.cpu()
+    spec2 = O.ModelSpec([2, 2, 3], [1, 2, 1], [64, 64, 64], t2)
+    rf2 = t2 * fs
+    ref2 = O.forward_indices(params, spec2, y2[:, :rf2 + fs - 1], y2[:, fs:fs + rf2], utt2, torch.arange(bsz), [1] * bsz)[0]
+    d2 = float((logp2.cpu() - ref2).abs().max())
+    report(f'generation (CUDA-graph path) vs teacher forcing ({rf2} samples): max|dlogp| {d2:.3e}')
+    assert d2 <= 0.05, d2
+    assert len(set(y2[0, fs:].tolist())) > 3                                   # it really samples
 
 
 def test_chunked_equals_unchunked_with_carry():
