@@ -32,8 +32,9 @@
 
 namespace srnn {
 
-constexpr int GRU_THREADS = 224;   // warp 0 TMA, warps 1 and 6 MMA issuers, warps 2-5 epilogue
-constexpr int GRU_MMA_WARPS = 2;   // tcgen05.mma issue is ~60 cycles per instruction from one thread
+// warps 0, 1 and 6.. MMA issuers (MW of them: a tcgen05.mma of this size costs ~90 cycles of issue from one
+// thread, ~24 of tensor pipe; thread 0 is also the TMA producer), warps 2-5 epilogue
+constexpr int gru_threads(int mw) { return 32 * (4 + mw); }
 // hidden units finalised per CTA: 8 (H/8 CTAs, the fastest step) or 16 (H/16 CTAs, which leaves more than
 // half of the SMs free for GEMMs running concurrently on another stream)
 constexpr int GRU_M = 64;          // batch rows per launch (MMA M)
@@ -42,6 +43,8 @@ constexpr int GRU_SLOT = GRU_M * 128;   // one [64 rows][64 bf16] K block
 struct GruParams {
   int batch, steps, hidden, ext_batch;
   int kbc;                         // K blocks (of 64) per CTA
+  int hslot;                       // bytes between K blocks of the staged [batch, K slice] operand
+  int one_box;                     // the whole slice arrives as ONE 4-D TMA box (else one box per K block)
   const __nv_bfloat16* gi;
   const float* b_hh;
   __nv_bfloat16* h_ext;
@@ -60,9 +63,22 @@ struct GruParams {
   unsigned long long* ts;          // debug timestamps [256][8] of CTA 0 (nullable)
 };
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// debug stamps: clock64 of CTA 0 per timestep [step][8], or (flag 128) the global timer of EVERY CTA at
+// timestep 24 [cta][8] to see the skew between CTAs
 #define GRU_TS(slot_, step_)                                                                 \
   do {                                                                                       \
-    if (p.ts && blockIdx.x == 0 && (step_) < 256) p.ts[(step_) * 8 + (slot_)] = clock64();   \
+    if (p.ts) {                                                                              \
+      if (p.flags & 128) {                                                                   \
+        if ((step_) == 24 && blockIdx.x < 256) p.ts[blockIdx.x * 8 + (slot_)] = globaltimer_ns(); \
+      } else if (blockIdx.x == 0 && (step_) < 256) {                                         \
+        p.ts[(step_) * 8 + (slot_)] = clock64();                                             \
+      }                                                                                      \
+    }                                                                                        \
   } while (0)
 
 // MUFU approximations (max relative error 2^-11, below the bf16 rounding of the matmul operand)
@@ -146,8 +162,8 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float a, float
 
 // LSTM = false: GRU (gates r,z,n; 3H pre-activations).  LSTM = true: LSTM (gates i,f,g,o; 4H), an
 // extension with no reference counterpart (BASELINE config 3; torch.nn.LSTM semantics, see oracle).
-template <bool BWD, int C, bool LSTM, int U>
-__global__ void __launch_bounds__(GRU_THREADS, 1)
+template <bool BWD, int C, bool LSTM, int U, int MW>
+__global__ void __launch_bounds__(gru_threads(MW), 1)
 gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_x, const GruParams p) {
   constexpr int UC = U * C;                          // units owned by the cluster
   constexpr int GATES = LSTM ? 4 : 3;
@@ -156,7 +172,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
   constexpr int NB = (NCOLS + 31) / 32;              // 32-column TMEM load batches per partial
   // one partial accumulator per issuing warp: partial w lives at columns [w*NCOLS, (w+1)*NCOLS); the
   // epilogue reads whole 32-column chunks, so the allocation covers the over-read of the last chunk
-  constexpr int TMEM_NEED = (GRU_MMA_WARPS - 1) * NCOLS + NB * 32;
+  constexpr int TMEM_NEED = (MW - 1) * NCOLS + NB * 32;
   constexpr uint32_t TMEM_COLS = TMEM_NEED <= 32 ? 32 : (TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 :
                                  (TMEM_NEED <= 256 ? 256 : 512)));
   constexpr uint32_t IDESC = idesc_bf16(GRU_M, NCOLS, false, false);
@@ -190,7 +206,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
     tma_prefetch_desc(&tma_x);
     mbar_init(wfull, 1);
     mbar_init(full, 1);
-    mbar_init(acc_full, GRU_MMA_WARPS);
+    mbar_init(acc_full, MW);
     mbar_init(part_ready, 1);
     fence_barrier_init();
   }
@@ -204,63 +220,60 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
   if (C > 1) cluster_sync_all();                     // every CTA's barriers exist before remote arrivals
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ------------------------------ TMA producer (whole warp polls, lane 0 issues) ------------
+  if (warp == 0 || warp == 1 || warp >= 6) {
+    // ------------------------------ TMA producer + MMA issuers ------------------------------
+    // Thread 0 first waits for the grid, brings this CTA's K slice of the exchanged matrix, then joins the other
+    // issuing threads (a CTA's load and its MMAs of one timestep are never concurrent, so the producer needs no
+    // warp of its own).  The K steps of a block are dealt round-robin to the MW issuing threads, each with its
+    // own partial accumulator (summed by the epilogue).
     if (lane == 0) {
-      mbar_expect_tx(wfull, static_cast<uint32_t>(KBC * WBLOCK));
-      for (int kb = 0; kb < KBC; ++kb)
-        for (int g = 0; g < NG; ++g)
-          tma_load_2d(sw + kb * WBLOCK + g * UC * 128, &tma_w, wfull, (kb0 + kb) * 64,
-                      (BWD ? 0 : g * H) + cluster_id * UC);   // gate g rows of W_hh (fwd)
-    }
-    const uint32_t bytes = static_cast<uint32_t>(KBC) * static_cast<uint32_t>(B) * 128u;
-    if (lane == 0) {
-      for (int s = 0; s < rounds; ++s) {
-        if (BWD && s == 0) continue;                 // the last timestep has no recurrent input
-        if (s > 0 && !(p.flags & 1)) {
-          grid_wait(p.sync, G * static_cast<uint32_t>(s), (p.flags & 16) != 0);
-          GRU_TS(0, s);
-        }
-        asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy writes -> TMA reads (free: measured)
-        const int slot = BWD ? (T - s) : s;          // time slot of the exchange buffer
-        mbar_expect_tx(full, bytes);
-        for (int kb = 0; kb < KBC; ++kb) tma_load_3d(hbuf + kb * GRU_SLOT, &tma_x, full, (kb0 + kb) * 64, 0, slot);
-        GRU_TS(1, s);
+      const int mw = warp < 2 ? warp : warp - 4;
+      if (mw == 0) {
+        mbar_expect_tx(wfull, static_cast<uint32_t>(KBC * WBLOCK));
+        for (int kb = 0; kb < KBC; ++kb)
+          for (int g = 0; g < NG; ++g)
+            tma_load_2d(sw + kb * WBLOCK + g * UC * 128, &tma_w, wfull, (kb0 + kb) * 64,
+                        (BWD ? 0 : g * H) + cluster_id * UC);   // gate g rows of W_hh (fwd)
       }
-    }
-    __syncwarp();
-  } else if (warp == 1 || warp == 6) {
-    if (lane == 0) {
-      // ------------------------------ MMA issuers: K steps dealt round-robin to 2 threads, each with
-      // its own partial accumulator (summed by the epilogue) --------------------
-      const int mw = warp == 1 ? 0 : 1;
+      const uint32_t bytes = static_cast<uint32_t>(KBC) * static_cast<uint32_t>(B) * 128u;
       mbar_wait(wfull, 0);
       const uint64_t a_base = smem_desc_sw128(smem_u32(hbuf), 16, 1024);
       const uint64_t b_base = smem_desc_sw128(smem_u32(sw), 16, 1024);
+      const uint32_t a_hi = static_cast<uint32_t>(a_base >> 32), b_hi = static_cast<uint32_t>(b_base >> 32);
+      const uint32_t d_tmem = tmem_base + mw * NCOLS;
+      const uint32_t hslot16 = static_cast<uint32_t>(p.hslot) >> 4;
       uint32_t phase = 0;
       for (int s = 0; s < rounds; ++s) {
-        if (BWD && s == 0) continue;
+        if (BWD && s == 0) continue;                 // the last timestep has no recurrent input
+        if (mw == 0) {
+          if (s > 0 && !(p.flags & 1)) {
+            grid_wait(p.sync, G * static_cast<uint32_t>(s), (p.flags & 16) != 0);
+            GRU_TS(0, s);
+          }
+          asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy writes -> TMA reads (free: measured)
+          const int slot = BWD ? (T - s) : s;        // time slot of the exchange buffer
+          mbar_expect_tx(full, bytes);
+          if (p.one_box) {
+            tma_load_4d(hbuf, &tma_x, full, 0, 0, kb0, slot);
+          } else {
+            for (int kb = 0; kb < KBC; ++kb)
+              tma_load_3d(hbuf + kb * GRU_SLOT, &tma_x, full, (kb0 + kb) * 64, 0, slot);
+          }
+          GRU_TS(1, s);
+        }
         mbar_wait(full, phase);
         phase ^= 1;
         if (mw == 0) GRU_TS(2, s);
         tc_fence_after();
-        // running descriptors: only the 14-bit start-address field (low word) changes, so each MMA
-        // costs two 32-bit adds instead of rebuilding two 64-bit descriptors (the issue thread is the
-        // bottleneck here: ~27 SASS instructions per MMA before this change)
-        uint32_t a_lo = static_cast<uint32_t>(a_base) + ((mw * 32) >> 4);
-        uint32_t b_lo = static_cast<uint32_t>(b_base) + ((mw * 32) >> 4);
-        const uint32_t a_hi = static_cast<uint32_t>(a_base >> 32), b_hi = static_cast<uint32_t>(b_base >> 32);
-        const uint32_t d_tmem = tmem_base + mw * NCOLS;
-#pragma unroll 2
-        for (int kb = 0; kb < KBC; ++kb) {
-#pragma unroll
-          for (int j = 0; j < 4 / GRU_MMA_WARPS; ++j) {
-            const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + j * ((GRU_MMA_WARPS * 32) >> 4));
-            const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + j * ((GRU_MMA_WARPS * 32) >> 4));
-            umma_bf16(d_tmem, ad, bd, IDESC, (kb > 0 || j > 0) ? 1u : 0u);
-          }
-          a_lo += GRU_SLOT >> 4;
-          b_lo += WBLOCK >> 4;
+        // K steps (16 columns = 32 bytes inside a 64-column block) are dealt round-robin: issuer mw takes steps
+        // mw, mw + MW, ...  Only the 14-bit start-address field (low descriptor word) changes.
+        const uint32_t a_lo0 = static_cast<uint32_t>(a_base), b_lo0 = static_cast<uint32_t>(b_base);
+#pragma unroll 4
+        for (int ks = mw; ks < KBC * 4; ks += MW) {
+          const uint32_t kb = static_cast<uint32_t>(ks) >> 2, j = static_cast<uint32_t>(ks) & 3u;
+          const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo0 + kb * hslot16 + j * 2u);
+          const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo0 + kb * (WBLOCK >> 4) + j * 2u);
+          umma_bf16(d_tmem, ad, bd, IDESC, ks >= MW ? 1u : 0u);
         }
         umma_commit(acc_full);
         if (mw == 0) GRU_TS(3, s);
@@ -292,18 +305,19 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         acc_phase ^= 1;
         tc_fence_after();
         static_assert(NCOLS <= 32, "C == 1: one 32-column chunk per partial");
-        uint32_t v[GRU_MMA_WARPS][32];
 #pragma unroll
-        for (int pw = 0; pw < GRU_MMA_WARPS; ++pw) tmem_ld32(t_addr + pw * NCOLS, v[pw]);
-        tmem_ld_wait();
-        tc_fence_before();
+        for (int i = 0; i < NG * U; ++i) out[i] = 0.f;
 #pragma unroll
-        for (int i = 0; i < NG * U; ++i) {
-          float acc = 0.f;
+        for (int pw = 0; pw < MW; pw += 2) {           // two partial tiles in flight per wait
+          if (pw >= KBC * 4) break;                    // fewer K steps than issuers: those partials were never written
+          uint32_t v[2][32];
+          tmem_ld32(t_addr + pw * NCOLS, v[0]);
+          tmem_ld32(t_addr + (pw + 1) * NCOLS, v[1]);
+          tmem_ld_wait();
 #pragma unroll
-          for (int pw = 0; pw < GRU_MMA_WARPS; ++pw) acc += __uint_as_float(v[pw][i]);
-          out[i] = acc;
+          for (int i = 0; i < NG * U; ++i) out[i] += __uint_as_float(v[0][i]) + __uint_as_float(v[1][i]);
         }
+        tc_fence_before();
         return;
       }
       if (warp == 2 && lane == 0) mbar_expect_tx(part_ready, RECV_BYTES);
@@ -313,9 +327,9 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       tc_fence_after();
 #pragma unroll
       for (int bi = 0; bi < NB; ++bi) {                // 32 result columns per batch, ONE wait per batch
-        uint32_t v[GRU_MMA_WARPS][32];
+        uint32_t v[MW][32];
 #pragma unroll
-        for (int pw = 0; pw < GRU_MMA_WARPS; ++pw) tmem_ld32(t_addr + pw * NCOLS + bi * 32, v[pw]);
+        for (int pw = 0; pw < MW; ++pw) tmem_ld32(t_addr + pw * NCOLS + bi * 32, v[pw]);
         tmem_ld_wait();
         if (lane_ok) {
 #pragma unroll
@@ -327,7 +341,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
               for (int i = 0; i < 8; ++i) {
                 f[i] = 0.f;
 #pragma unroll
-                for (int pw = 0; pw < GRU_MMA_WARPS; ++pw) f[i] += __uint_as_float(v[pw][e * 8 + i]);
+                for (int pw = 0; pw < MW; ++pw) f[i] += __uint_as_float(v[pw][e * 8 + i]);
               }
               const int g = col / UC, dst = (col % UC) / U, sub = (col % U) / 8;
               const uint32_t off = static_cast<uint32_t>((((crank * NG + g) * GRU_M + row) * U + sub * 8) * 4);
@@ -590,7 +604,10 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           store_units<U>(ghp + 2 * H, ghn);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && lane == 0) red_release_gpu_add(p.sync, 1u);
+        if (warp == 2 && lane == 0) {
+          GRU_TS(6, s + 1);                                     // stamps are indexed by the CONSUMING round
+          red_release_gpu_add(p.sync, 1u);
+        }
         if (io) {                                               // dgi is only read after the kernel
           __nv_bfloat16* gip = p.dgi + rt * 3 * H + u0;
           store_units<U>(gip, gr);
@@ -617,10 +634,22 @@ static size_t gru_smem_bytes(int kbc) {
          static_cast<size_t>(ncols) * GRU_M * 4 + 256 + 1024;
 }
 
+// MMA issuing warps: 4 when the 4 partial accumulators fit the 512 TMEM columns, else 2
+template <bool BWD, int C, bool LSTM, int U>
+constexpr int gru_mw() {
+  constexpr int ncols = (BWD ? 1 : (LSTM ? 4 : 3)) * U * C;
+  if (U != 8) return 2;                                // 16 units per thread: 4 partial tiles would spill
+  // (8 issuers at C=1 were measured no faster than 4: 64 MMAs in ~1550 cycles either way, i.e. the ~24-cycle
+  // occupancy of the tensor pipe per M=64 instruction is the bound, no longer the issue rate)
+  return 3 * ncols + ((ncols + 31) / 32) * 32 <= 512 ? 4 : 2;
+}
+
 // Can H/8 CTAs in clusters of C all be resident at once (they spin on one another)?
 template <bool BWD, int C, bool LSTM, int U>
 static bool gru_fits(int H, int kbc) {
-  auto kern = gru_kernel<BWD, C, LSTM, U>;
+  constexpr int MW = gru_mw<BWD, C, LSTM, U>();
+  constexpr int GRU_THREADS = gru_threads(MW);
+  auto kern = gru_kernel<BWD, C, LSTM, U, MW>;
   const size_t smem = gru_smem_bytes<BWD, C, LSTM, U>(kbc);
   if (smem > 227 * 1024) return false;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -655,9 +684,10 @@ static bool gru_fits(int H, int kbc) {
   return clusters * C >= ctas;
 }
 
-template <bool BWD, int C, bool LSTM, int U>
-static int launch_gru(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
+template <bool BWD, int C, bool LSTM, int U, int MW>
+static int launch_gru_mw(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   constexpr int GATES = LSTM ? 4 : 3;
+  constexpr int GRU_THREADS = gru_threads(MW);
   const int H = a->hidden, T = a->steps, B = a->batch;
   const int K = BWD ? GATES * H : H;
   const int ctas = H / U;
@@ -672,17 +702,32 @@ static int launch_gru(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
     int rc = make_tmap_bf16(&tw, a->w_hh, 2, dims, strides, box, true);
     if (rc) return rc;
   }
+  // exchange buffer, TIME-major: forward h_ext [T+1, EB, H]; backward dgh [T, EB, 3H].  When K is a whole
+  // number of 64-column blocks and the batch a whole number of 8-row swizzle atoms, the buffer is viewed as
+  // [slot][K block][row][64] (strides not monotonic: legal for a tiled map) so that ONE box brings the CTA's
+  // whole [batch, K slice] operand, K block by K block, in the layout the MMA reads (8 TMA issues -> 1).
+  const bool one_box = K % 64 == 0 && B % 8 == 0 && kbc * B * 128 <= 160 * 1024 && !(a->debug_flags & 32);
   {
-    // exchange buffer, TIME-major: forward h_ext [T+1, EB, H]; backward dgh [T, EB, 3H]
     const uint64_t slots = BWD ? (uint64_t)T : (uint64_t)T + 1;
-    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)B, slots};
-    const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)K * 2 * (uint64_t)a->ext_batch};
-    const uint32_t box[3] = {64, (uint32_t)B, 1};
-    int rc = make_tmap_bf16(&tx, BWD ? (const void*)a->dgh : (const void*)a->h_ext, 3, dims, strides, box, true);
+    const void* base = BWD ? (const void*)a->dgh : (const void*)a->h_ext;
+    int rc;
+    if (one_box) {
+      const uint64_t dims[4] = {64, (uint64_t)B, (uint64_t)(K / 64), slots};
+      const uint64_t strides[3] = {(uint64_t)K * 2, 128, (uint64_t)K * 2 * (uint64_t)a->ext_batch};
+      const uint32_t box[4] = {64, (uint32_t)B, (uint32_t)kbc, 1};
+      rc = make_tmap_bf16(&tx, base, 4, dims, strides, box, true);
+    } else {
+      const uint64_t dims[3] = {(uint64_t)K, (uint64_t)B, slots};
+      const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)K * 2 * (uint64_t)a->ext_batch};
+      const uint32_t box[3] = {64, (uint32_t)B, 1};
+      rc = make_tmap_bf16(&tx, base, 3, dims, strides, box, true);
+    }
     if (rc) return rc;
   }
   GruParams p{};
   p.batch = B; p.steps = T; p.hidden = H; p.ext_batch = a->ext_batch; p.kbc = kbc;
+  p.one_box = one_box ? 1 : 0;
+  p.hslot = one_box ? B * 128 : GRU_SLOT;
   p.gi = static_cast<const __nv_bfloat16*>(a->gi);
   p.b_hh = a->b_hh;
   p.h_ext = static_cast<__nv_bfloat16*>(a->h_ext);
@@ -700,7 +745,7 @@ static int launch_gru(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   p.flags = a->debug_flags;
   p.ts = reinterpret_cast<unsigned long long*>(a->debug_ts);
 
-  auto kern = gru_kernel<BWD, C, LSTM, U>;
+  auto kern = gru_kernel<BWD, C, LSTM, U, MW>;
   SRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ctas);
@@ -725,14 +770,24 @@ static int launch_gru(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   return SRNN_OK;
 }
 
+template <bool BWD, int C, bool LSTM, int U>
+static int launch_gru(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
+  constexpr int MW = gru_mw<BWD, C, LSTM, U>();
+  if constexpr (MW != 2 && U == 8 && !LSTM) {          // experiments: debug flag 64 = two issuing warps
+    if (a->debug_flags & 64) return launch_gru_mw<BWD, C, LSTM, U, 2>(a, kbc, stream);
+  }
+  return launch_gru_mw<BWD, C, LSTM, U, MW>(a, kbc, stream);
+}
+
 // Cluster size: K split in whole K blocks, units tile H, slice fits smem, all clusters co-resident.
 template <bool BWD, bool LSTM, int U>
 static int pick_cluster(int H, int* kbc_out) {
   const int K = BWD ? (LSTM ? 4 : 3) * H : H;
   const int kb_total = (K + 63) / 64;
-  // measured (B=64, H=1024, U=8): forward 5.0 us/step at C=2 vs 6.0 at C=4 (exchange volume grows with
-  // C); backward needs C>=4 for the 3H-wide slice to fit shared memory
-  const int fwd_order[4] = {2, 4, 8, 1};
+  // measured (B=64, H=1024, U=8), us per step forward: C=1 (whole K in one CTA, no cluster exchange, 128 KB
+  // of h per CTA and step) 3.9-4.1, C=2 4.4-4.5, C=4 5.6 (exchange volume grows with C);
+  // backward needs C>=4 for the 3H-wide slice to fit shared memory
+  const int fwd_order[4] = {1, 2, 4, 8};
   const int bwd_order[4] = {4, 8, 2, 1};
   for (int i = 0; i < 4; ++i) {
     const int c = BWD ? bwd_order[i] : fwd_order[i];

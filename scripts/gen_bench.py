@@ -14,6 +14,7 @@ from samplernn_pase_b200 import SampleRNNModel, ops  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=256)
 ap.add_argument('--frames', type=int, default=8)
+ap.add_argument('--profile', action='store_true')
 a = ap.parse_args()
 torch.manual_seed(0)
 model = SampleRNNModel(**bench.model_kwargs(a.frames)).cuda()
@@ -29,3 +30,20 @@ dt = time.perf_counter() - t0
 n = a.frames * int(model.frame_size)
 print(f'generated {a.batch} x {n} samples in {dt:.3f} s: {1e6 * dt / n:.1f} us per sample step, '
       f'{a.batch * n / dt / 1e3:.1f} k samples/s, {ops.launch_count / n:.1f} kernel launches per sample step')
+if '--profile' in sys.argv:
+    # device time of every C-ABI call of the eager path (CUDA events; launch gaps excluded)
+    import collections
+    from samplernn_pase_b200 import _lib
+    _lib.profile_log = []
+    model.test(utt, info, use_graphs=False)
+    torch.cuda.synchronize()
+    log, _lib.profile_log = _lib.profile_log, None
+    agg = collections.OrderedDict()
+    for name, note, s, e in log:
+        d = agg.setdefault((name, note if 'gemm' in name or 'gru' in name else ''), [0, 0.0])
+        d[0] += 1
+        d[1] += s.elapsed_time(e)
+    tot = sum(v[1] for v in agg.values())
+    print(f'eager path: {len(log) / n:.1f} C calls and {1e3 * tot / n:.1f} us of device time per sample step')
+    for (name, note), (cnt, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f'{1e3 * ms / n:8.2f} us/sample  x{cnt / n:5.2f}  {1e3 * ms / cnt:7.2f} us each  {name:22s} {note}')
