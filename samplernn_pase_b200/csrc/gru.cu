@@ -261,6 +261,8 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           }
           GRU_TS(1, s);
         }
+        // (splitting the operand into 4 boxes with their own barriers so the MMAs could start on the first
+        // part was measured useless: the TMA unit services the boxes interleaved and they all land together)
         mbar_wait(full, phase);
         phase ^= 1;
         if (mw == 0) GRU_TS(2, s);
