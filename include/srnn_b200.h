@@ -228,6 +228,27 @@ int srnn_masked_nll_mean(const float* logp_target, const uint8_t* slot_valid, in
 int srnn_adam_clipped(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
                       double beta1, double beta2, double eps, int32_t step, double grad_scale, srnn_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Autoregressive generation (SampleRNNModel.test, model.py:289-351), per-sample kernels.
+ * ------------------------------------------------------------------------------------------- */
+/* Embedding side of the sample-level layer for ONE time step (model.py:192-200): the embedding, the
+ * conv1d over the last r0 samples and the embedding block of comb_layer are linear in the one-hot codes,
+ * so with fixed weights they are r0 tables of q rows (table bf16 (r0*q, hidden), row k*q+code):
+ *   out[b, :] = act( sum_{k<r0} table[k*q + idx[b*idx_ld + k], :] + pre[b*pre_ld + :] )
+ * pre (bf16, nullable) carries the conditioning / upper-tier blocks and the bias; relu != 0 applies ReLU. */
+int srnn_embed_sum(const void* table_bf16, const uint8_t* idx, int64_t idx_ld, int32_t batch, int32_t r0, int32_t q,
+                   int32_t hidden, const void* pre_bf16, int64_t pre_ld, int32_t relu, void* out_bf16,
+                   int64_t out_ld, srnn_stream_t stream);
+/* log-softmax + the draw (model.py:203, 346-348).  in[b*ld + :q] holds log-probabilities, or raw logits when
+ * normalise != 0 (then the log-softmax is taken here); if logp_out is non-null the log-probabilities are
+ * written to logp_out[b*ld_out + :q].  pick[b] is sampled from them by inverse CDF with the uniform u[b] in
+ * [0,1) (multinomial of the softmax), or is the arg-max when u is null.  If win is non-null, the utterance's
+ * window of its last win_len codes (u8 (batch, win_len)) is shifted left by one and pick[b] appended; if out is
+ * non-null, out[b*out_ld] = pick[b]. */
+int srnn_sample_categorical(const float* in, int64_t ld, int32_t batch, int32_t q, int32_t normalise, float* logp_out,
+                            int64_t ld_out, const float* u, uint8_t* win, int32_t win_len, uint8_t* out,
+                            int64_t out_ld, srnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -445,6 +445,208 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 }
 
 // ---------------------------------------------------------------------------------------------
+// Small-M NT GEMM (M <= 512: the per-sample GEMMs of generation, model.py:289-351, and tiny shapes).
+// With so few rows the 128 x 256 persistent kernel runs on a handful of SMs, each streaming its
+// whole K extent through one SM's ~60 B/clk L2 port (256 x 1024 x 1024: 8 CTAs, 14 us).  Here the
+// tile is 128 x 64 and the K extent is SPLIT over a thread-block cluster of CS CTAs (2 x 16 tiles x 4
+// = 128 CTAs for the same shape); every CTA leaves its fp32 partial tile in shared memory and, after one
+// cluster barrier, reduces a 1/CS column slice of the tile over its peers' shared memory (DSMEM loads),
+// applies bias / aux / ReLU and stores it.  Deterministic (fixed summation order), no atomics, no
+// workspace.
+// ---------------------------------------------------------------------------------------------
+constexpr int SBN = 64;
+constexpr int S_STAGES = 3;                              // 3 x 24 KB + 34 KB partial tile: two CTAs per SM
+constexpr int S_STAGE = BM * BK * 2 + SBN * BK * 2;      // 24 KB
+constexpr int S_RED_LD = SBN + 4;                        // padded fp32 row (bank spread for the 16-byte stores)
+constexpr int S_RED_OFF = S_STAGES * S_STAGE;
+constexpr int S_BAR_OFF = S_RED_OFF + BM * S_RED_LD * 4;
+constexpr int S_TOTAL = S_BAR_OFF + 256 + 1024;
+
+template <int CS>
+__global__ void __launch_bounds__(384, 2)
+gemm_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                  const GemmParams p) {
+  constexpr uint32_t IDESC = idesc_bf16(BM, SBN, false, false);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* red = reinterpret_cast<float*>(smem + S_RED_OFF);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S_BAR_OFF);
+  uint64_t* empty = full + S_STAGES;
+  uint64_t* tfull = empty + S_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
+  const int tile = blockIdx.x / CS;
+  const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+  const int kb_begin = static_cast<int>(crank) * p.kb_per_split;
+  const int kb_end = min(kb_begin + p.kb_per_split, p.total_kb);
+  const int nkb = max(kb_end - kb_begin, 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, SBN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * S_STAGE;
+        mbar_expect_tx(&full[stage], S_STAGE);
+        tma_load_3d(sa, &tma_a, &full[stage], kb * BK, mt * BM, 0);
+        tma_load_2d(sa + BM * BK * 2, &tma_b, &full[stage], kb * BK, nt * SBN);
+        if (++stage == S_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && nkb > 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * S_STAGE);
+        const uint32_t b_addr = a_addr + BM * BK * 2;
+#pragma unroll
+        for (int k16 = 0; k16 < BK / 16; ++k16)
+          umma_bf16(tmem_base, smem_desc_sw128(a_addr + k16 * 32, 16, 1024), smem_desc_sw128(b_addr + k16 * 32, 16, 1024),
+                    IDESC, (kb > kb_begin || k16 > 0) ? 1u : 0u);
+        umma_commit(&empty[stage]);
+        if (++stage == S_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tfull);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // partial tile: TMEM -> this CTA's shared memory (zeros when this rank got no K blocks)
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    uint32_t v[32];
+    if (nkb > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 32, v);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0u;
+    }
+    float4* dst = reinterpret_cast<float4*>(red + row * S_RED_LD + half * 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      dst[i] = make_float4(__uint_as_float(v[i * 4]), __uint_as_float(v[i * 4 + 1]), __uint_as_float(v[i * 4 + 2]),
+                           __uint_as_float(v[i * 4 + 3]));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CS > 1) cluster_sync_all();                      // every rank's partial tile is in its shared memory
+
+  if (warp >= 4) {
+    constexpr int CPC = SBN / CS;                      // columns reduced by this CTA
+    constexpr int CPT = CPC / 2;                       // ... per thread: 32 / 16 / 8
+    const int tid = threadIdx.x - 128;
+    const int row = tid >> 1;
+    const int c0 = static_cast<int>(crank) * CPC + (tid & 1) * CPT;
+    float f[CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) f[i] = 0.f;
+    const float* mine = red + row * S_RED_LD + c0;
+#pragma unroll
+    for (int src = 0; src < CS; ++src) {
+#pragma unroll
+      for (int i = 0; i < CPT / 4; ++i) {
+        float4 t;
+        if constexpr (CS == 1) {
+          t = reinterpret_cast<const float4*>(mine)[i];
+        } else {
+          t = ld_dsmem_f4(mapa(smem_u32(mine) + i * 16, static_cast<uint32_t>(src)));
+        }
+        f[i * 4 + 0] += t.x; f[i * 4 + 1] += t.y; f[i * 4 + 2] += t.z; f[i * 4 + 3] += t.w;
+      }
+    }
+    const int gr = mt * BM + row;
+    const int gc = nt * SBN + c0;
+    if (gr < p.m && gc < p.n) {
+      const bool full_cols = gc + CPT <= p.n;
+      if (p.bias) {
+#pragma unroll
+        for (int i = 0; i < CPT; ++i)
+          if (full_cols || gc + i < p.n) f[i] += __ldg(p.bias + gc + i);
+      }
+      if (p.aux_mode) {
+        const __nv_bfloat16* ap = p.aux + static_cast<long long>(gr / p.aux_row_div) * p.ldaux + gc;
+#pragma unroll
+        for (int i = 0; i < CPT; ++i)
+          if (full_cols || gc + i < p.n) f[i] += __bfloat162float(ap[i]);
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) f[i] = fmaxf(f[i], 0.f);
+      }
+      if (p.c_dtype == 0) {
+        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.c) + static_cast<long long>(gr) * p.ldc + gc;
+        if (full_cols && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+          for (int i = 0; i < CPT / 8; ++i) {
+            uint4 u;
+            u.x = pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1]);
+            u.y = pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3]);
+            u.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]);
+            u.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
+            reinterpret_cast<uint4*>(cp)[i] = u;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < CPT; ++i)
+            if (gc + i < p.n) cp[i] = __float2bfloat16_rn(f[i]);
+        }
+      } else {
+        float* cp = reinterpret_cast<float*>(p.c) + static_cast<long long>(gr) * p.ldc + gc;
+        if (full_cols && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+          for (int i = 0; i < CPT / 4; ++i)
+            reinterpret_cast<float4*>(cp)[i] = make_float4(f[i * 4], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < CPT; ++i)
+            if (gc + i < p.n) cp[i] = f[i];
+        }
+      }
+    }
+  }
+  if (CS > 1) cluster_sync_all();                      // nobody exits while a peer may still read its partial tile
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, SBN);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 template <int BN, bool TN, int EPI>
@@ -498,6 +700,66 @@ static int run_nt(const srnn_gemm_args* a, GemmParams& p, bool nll, cudaStream_t
   if (nll) return launch<256, false, 1>(ta, tb, p, stream);
   if (bn == 256) return launch<256, false, 0>(ta, tb, p, stream);
   return launch<128, false, 0>(ta, tb, p, stream);
+}
+
+template <int CS>
+static int launch_small(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_small_kernel<CS>;
+  static bool configured = false;   // per instantiation
+  if (!configured) {
+    SRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S_TOTAL));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.tiles_m * p.tiles_n * CS);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = S_TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CS > 1 ? 1 : 0;
+  SRNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  return SRNN_OK;
+}
+
+// M <= 512, one batch, plain epilogue: 128 x 64 tiles, K split over a cluster so that ~1-2 CTAs per SM exist
+static int run_nt_small(const srnn_gemm_args* a, GemmParams& p, cudaStream_t stream) {
+  SRNN_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0, "gemm NT: lda/ldb must be multiples of 8 elements (lda=%lld ldb=%lld)",
+                 (long long)a->lda, (long long)a->ldb);
+  SRNN_CHECK_ARG(aligned16(a->a) && aligned16(a->b), "gemm NT: operand pointers must be 16-byte aligned");
+  p.tiles_m = (a->m + BM - 1) / BM;
+  p.tiles_n = (a->n + SBN - 1) / SBN;
+  p.total_kb = p.kb_per_batch = (a->k + BK - 1) / BK;
+  const int tiles = p.tiles_m * p.tiles_n;
+  int cs = 1;
+  while (cs < 4 && tiles * cs * 2 <= 2 * sm_count() && p.total_kb >= cs * 4) cs *= 2;
+  p.splits = cs;
+  p.kb_per_split = (p.total_kb + cs - 1) / cs;
+  p.total_work = tiles;
+  CUtensorMap ta, tb;
+  {
+    const uint64_t dims[3] = {(uint64_t)a->k, (uint64_t)a->m, 1};
+    const uint64_t strides[2] = {(uint64_t)a->lda * 2, (uint64_t)a->lda * 2 * (uint64_t)a->m};
+    const uint32_t box[3] = {BK, BM, 1};
+    int rc = make_tmap_bf16(&ta, a->a, 3, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a->k, (uint64_t)a->n};
+    const uint64_t strides[1] = {(uint64_t)a->ldb * 2};
+    const uint32_t box[2] = {BK, SBN};
+    int rc = make_tmap_bf16(&tb, a->b, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  switch (cs) {
+    case 4: return launch_small<4>(ta, tb, p, stream);
+    case 2: return launch_small<2>(ta, tb, p, stream);
+    default: return launch_small<1>(ta, tb, p, stream);
+  }
 }
 
 static int run_tn(const srnn_gemm_args* a, GemmParams& p, cudaStream_t stream) {
@@ -577,6 +839,8 @@ extern "C" int srnn_gemm_bf16(const srnn_gemm_args* a, srnn_stream_t stream_) {
   if (a->op == 0) {
     SRNN_CHECK_ARG(a->n_fold == 0 || (a->n % a->n_fold == 0 && a->n_fold % 32 == 0 && !a->aux),
                    "gemm NT: n_fold must divide n, be a multiple of 32, and exclude aux");
+    if (a->m <= 512 && a->batch == 1 && a->n_fold == 0 && p.aux_mode != 2 && a->max_ctas == 0)
+      return run_nt_small(a, p, stream);
     return run_nt(a, p, false, stream);
   }
   SRNN_CHECK_ARG(a->op == 1, "gemm: op must be 0 (NT) or 1 (TN)");

@@ -137,20 +137,6 @@ __device__ __forceinline__ void grid_wait(const uint32_t* counter, uint32_t targ
   if (acquire_fence) asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
-// ---- cluster / distributed shared memory helpers ------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-  return r;
-}
 // Push 16 bytes into a peer CTA's shared memory; the peer's mbarrier receives complete_tx(16), so the
 // consumer needs no fence: waiting on its own barrier makes the data visible (like a TMA load).
 __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float a, float b, float c, float d,

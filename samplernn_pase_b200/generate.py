@@ -66,11 +66,18 @@ class SampleWeights:
         self.table = _e(h, r0 * q, device=dev)                     # T[o, k*Q+q] = sum_q' We[o,q',k] E[q,q']
         for k in range(r0):
             ops.gemm_nt(we[:, k * q:], e_b, self.table[:, k * q:], h, q, q, r0 * q, q, r0 * q)
+        self.wcomb = _e(h, 3 * h, device=dev)
+        ops.weight_prep(sl.comb_layer.weight.detach().contiguous(), None, (h, 3 * h, 1), self.wcomb, (3 * h, 1, 0))
+        # folded tables for one-step generation: tt[k*Q+q, o] = sum_q' E[q,q'] We[o,q',k] (embedding + conv tap k of
+        # code q), then through the embedding block of comb_layer: table_t[k*Q+q, :] = Wcomb[:, :H] . tt[k*Q+q, :]
+        tt = _e(r0 * q, h, device=dev)
+        for k in range(r0):
+            ops.gemm_nt(e_b, we[:, k * q:], tt[k * q:], q, h, q, q, r0 * q, h)
+        self.table_t = _e(r0 * q, h, device=dev)
+        ops.gemm_nt(tt, self.wcomb, self.table_t, r0 * q, h, h, h, 3 * h, h)
         self.wcs = _z(h, self.cp, device=dev)
         ops.weight_prep(sl.conds_expand.weight.detach().contiguous(), None, (h, c, 1), self.wcs, (self.cp, 1, 0))
         self.csb = sl.conds_expand.bias.detach().contiguous()
-        self.wcomb = _e(h, 3 * h, device=dev)
-        ops.weight_prep(sl.comb_layer.weight.detach().contiguous(), None, (h, 3 * h, 1), self.wcomb, (3 * h, 1, 0))
         self.cbias = sl.comb_layer.bias.detach().contiguous()
         self.w2 = _e(h, h, device=dev)
         ops.weight_prep(sl.comb_layer_expand.weight_v.detach(), sl.comb_layer_expand.weight_g.detach(), (h, h, 1),
@@ -81,16 +88,17 @@ class SampleWeights:
         self.b3 = sl.adapt.bias.detach().contiguous()
 
 
-def tier_step(w, lut, prev_u8, conds_row, upper, h_state):
-    """One frame of a tier for every utterance: ``prev_u8`` (B, fs) the fs samples before the frame,
-    ``conds_row`` (B,1,C) fp32, ``upper`` (B,H) bf16 or None, ``h_state`` (layers,B,H) fp32 updated in place.
-    Returns the r upsampled conditioning vectors (B, r, H) bf16."""
-    b = prev_u8.shape[0]
-    dev = prev_u8.device
+def tier_step(w, lut, win, conds_row, upper, upper_ld, h_state, out):
+    """One frame of a tier for every utterance.  ``win`` (B, FS) uint8 holds the last FS generated samples (the
+    tier reads its last fs), ``conds_row`` (B,1,C) fp32, ``upper`` a (B,H) bf16 view with row stride ``upper_ld``
+    (or None for the top tier), ``h_state`` (layers,B,H) fp32 updated in place.  Writes the r upsampled
+    conditioning vectors into ``out`` (B, r, H) bf16."""
+    b, fs_top = win.shape
+    dev = win.device
     h = w.h
-    ain = ops.tier_input(prev_u8, 0, lut, None, conds_row, b, 1, w.fs, w.kp)
+    ain = ops.tier_input(win, fs_top - w.fs, lut, None, conds_row, b, 1, w.fs, w.kp)
     x = _e(b, h, device=dev)
-    ops.gemm_nt(ain, w.wcat, x, b, h, w.kp, w.kp, w.kp, h, bias=w.bias_u, aux=upper, ldaux=h, aux_mode=1)
+    ops.gemm_nt(ain, w.wcat, x, b, h, w.kp, w.kp, w.kp, h, bias=w.bias_u, aux=upper, ldaux=upper_ld, aux_mode=1)
     for i, (wih, whh, b_ih, b_hh) in enumerate(w.rnn):
         gi = _e(b, 3 * h, device=dev)
         ops.gemm_nt(x, wih, gi, b, 3 * h, h, h, h, 3 * h, bias=b_ih)
@@ -100,66 +108,83 @@ def tier_step(w, lut, prev_u8, conds_row, upper, h_state):
         gates = _e(b, 4 * h, device=dev)
         ops.gru_forward(gi, whh, b_hh, h_ext, hall, h_state[i], gates, b, 1, h)
         x = hall
-    up = _e(b, w.r, h, device=dev)
-    ops.gemm_nt(x, w.wu, up, b, w.r * h, h, h, h, w.r * h, bias=w.bias_up)
-    return up
+    ops.gemm_nt(x, w.wu, out, b, w.r * h, h, h, h, w.r * h, bias=w.bias_up)
+    return out
 
 
-def sample_step(w, last_u8, c_term, upper):
-    """log-probabilities (B,256) of the next sample given the last r0 samples (B,r0) uint8, the
-    conditioning term ``c_term`` (B,H) bf16 (conds_expand of the current frame) and ``upper`` (B,H)."""
-    b = last_u8.shape[0]
-    dev = last_u8.device
-    h, q, r0 = w.h, w.q, w.r0
-    onehot = ops.onehot_rows(last_u8.contiguous(), q)              # (B, r0, Q) == (B, r0*Q)
-    cat = _e(b, 3 * h, device=dev)
-    ops.gemm_nt(onehot, w.table, cat, b, h, r0 * q, r0 * q, r0 * q, 3 * h)
-    cat[:, h:2 * h] = c_term
-    cat[:, 2 * h:] = upper
+def frame_terms(sw, conds_b, c_term, cc):
+    """Per top-tier frame: ``c_term`` = conds_expand(conds) (model.py:194) and ``cc`` = the conditioning block of
+    comb_layer applied to it, plus comb_layer's bias (model.py:195-200) - both constant over the frame."""
+    b, h, cp = conds_b.shape[0], sw.h, sw.cp
+    ops.gemm_nt(conds_b, sw.wcs, c_term, b, h, cp, cp, cp, h, bias=sw.csb)
+    ops.gemm_nt(c_term, sw.wcomb[:, h:], cc, b, h, h, h, 3 * h, h, bias=sw.cbias)
+
+
+def sample_pre(sw, up0, cc, pre):
+    """Per lowest-tier frame: pre[b, j] = comb_layer's upper-tier block applied to the j-th upsampled vector + cc[b]
+    (everything of comb_layer's input that does not depend on the samples of the frame)."""
+    b, r0, h = up0.shape
+    ops.gemm_nt(up0, sw.wcomb[:, 2 * h:], pre, b * r0, h, h, h, 3 * h, h, aux=cc, ldaux=h, aux_mode=1, aux_row_div=r0)
+
+
+def sample_step(sw, win, pre_j, pre_ld, logits):
+    """Logits (B,256) fp32 of the next sample: the embedding side is a sum of r0 table rows selected by the last r0
+    samples of ``win`` (srnn_embed_sum), then comb_layer_expand and adapt (model.py:201-202); the log-softmax
+    (model.py:203) is taken by the sampling kernel."""
+    b, fs_top = win.shape
+    dev = win.device
+    h, q, r0 = sw.h, sw.q, sw.r0
     h1 = _e(b, h, device=dev)
-    ops.gemm_nt(cat, w.wcomb, h1, b, h, 3 * h, 3 * h, 3 * h, h, bias=w.cbias, relu=True)
+    ops.embed_sum(sw.table_t, win[:, fs_top - r0:], fs_top, b, r0, q, h, pre_j, pre_ld, True, h1, h)
     h2 = _e(b, h, device=dev)
-    ops.gemm_nt(h1, w.w2, h2, b, h, h, h, h, h, bias=w.b2, relu=True)
-    lse = _e(b, dtype=F32, device=dev)
-    lpt = _e(b, dtype=F32, device=dev)
-    logp = _e(b, q, dtype=F32, device=dev)
-    tgt = torch.zeros(b, dtype=torch.uint8, device=dev)
-    ops.gemm_nll(1, h2, w.w3, w.b3, tgt, b, h, h, h, lse=lse, logp_target=lpt, logp=logp)
-    return logp
+    ops.gemm_nt(h1, sw.w2, h2, b, h, h, h, h, h, bias=sw.b2, relu=True)
+    ops.gemm_nt(h2, sw.w3, logits, b, q, h, h, h, q, bias=sw.b3)
+    return logits
 
 
 #: set True to decode greedily (argmax) instead of sampling - lets eager and CUDA-graph runs be compared exactly
 _GREEDY = False
 
 
-def _frame_phase(p, tiers, sw, lut, win, conds_cur, c_term, outs, states, frame_out, logp_frame, generator):
-    """One sample step at phase ``p = xi % FS`` of a top-tier frame, written against STATIC buffers so that it can be
-    captured in a CUDA graph: ``win`` (B,FS) holds the last FS generated samples, ``outs`` the tiers' current
-    upsampled outputs, ``frame_out[:, p]`` receives the new sample."""
-    fs_top = win.shape[1]
+class _GenState:
+    """Static buffers of a generation call (CUDA-graph capturable step programs run against these)."""
+
+    def __init__(self, b, fs_top, tiers, sw, c, return_logp, dev):
+        self.win = None
+        self.conds_cur = torch.empty(b, 1, c, dtype=F32, device=dev)
+        self.conds_b = _e(b, sw.cp, device=dev)
+        self.c_term = _e(b, sw.h, device=dev)
+        self.cc = _e(b, sw.h, device=dev)
+        self.outs = [_e(b, w.r, w.h, device=dev) for w in tiers]
+        self.pre = _e(b, sw.r0, sw.h, device=dev)
+        self.frame_out = torch.empty(b, fs_top, dtype=torch.uint8, device=dev)
+        self.logp_frame = torch.empty(b, fs_top, sw.q, dtype=F32, device=dev) if return_logp else None
+        self.logits = torch.empty(b, sw.q, dtype=F32, device=dev)
+        self.u_frame = torch.empty(fs_top, b, dtype=F32, device=dev)
+
+
+def _frame_phase(p, tiers, sw, lut, st, states):
+    """One sample step at phase ``p = xi % FS`` of a top-tier frame, written against the static buffers of ``st`` so
+    that it can be captured in a CUDA graph: ``st.win`` (B,FS) holds the last FS generated samples, ``st.outs`` the
+    tiers' current upsampled outputs, ``st.frame_out[:, p]`` receives the new sample."""
+    win = st.win
+    b, fs_top = win.shape
     for n in reversed(range(len(tiers))):                                    # model.py:312-337
         w = tiers[n]
         if p % w.fs != 0:
             continue
-        upper = None
+        upper, upper_ld = None, 0
         if n != len(tiers) - 1:
             frame_index = (p % tiers[n + 1].fs) // w.fs                      # == (xi // fs_n) % r_{n+1}
-            upper = outs[n + 1][:, frame_index].contiguous()
-        up = tier_step(w, lut, win[:, fs_top - w.fs:].contiguous(), conds_cur, upper, states[n])
-        if outs[n] is None:
-            outs[n] = up
-        else:
-            outs[n].copy_(up)
-    upper = outs[0][:, p % sw.r0].contiguous()                               # model.py:343
-    logp = sample_step(sw, win[:, fs_top - sw.r0:].contiguous(), c_term, upper)
-    if logp_frame is not None:
-        logp_frame[:, p] = logp
-    if _GREEDY:                                                              # debugging aid: deterministic decoding
-        new = logp.argmax(dim=1, keepdim=True).to(torch.uint8)
-    else:
-        new = torch.multinomial(logp.exp(), 1, generator=generator).to(torch.uint8)   # model.py:346-348
-    frame_out[:, p] = new[:, 0]
-    win.copy_(torch.cat([win[:, 1:], new], dim=1))
+            upper, upper_ld = st.outs[n + 1][:, frame_index], tiers[n + 1].r * w.h
+        tier_step(w, lut, win, st.conds_cur, upper, upper_ld, states[n], st.outs[n])
+        if n == 0:
+            sample_pre(sw, st.outs[0], st.cc, st.pre)
+    j = p % sw.r0                                                            # model.py:343
+    sample_step(sw, win, st.pre[:, j], sw.r0 * sw.h, st.logits)
+    # model.py:203,346-348: log-softmax, draw from it, append to the window of the last FS samples
+    ops.sample_categorical(st.logits, b, sw.q, None if _GREEDY else st.u_frame[p], win, fs_top, st.frame_out[:, p],
+                           fs_top, normalise=True, logp_out=st.logp_frame[:, p] if st.logp_frame is not None else None)
 
 
 @torch.no_grad()
@@ -170,8 +195,8 @@ def generate(model, utt_conds, info, return_logp=False, generator=None, use_grap
 
     The FS sample steps of one top-tier frame always run the same kernels on the same buffers (which tier
     fires and which upsampled vector is read depends only on ``xi % FS``), so after an eager first frame the
-    FS step programs are captured once as CUDA graphs and replayed for every later frame: the launch-bound
-    Python loop (~300 us per sample step) becomes FS graph replays per frame."""
+    FS step programs are captured once as CUDA graphs and replayed for every later frame.  The uniforms of
+    the draws are produced once per frame outside the graphs, so any ``generator`` works with them."""
     dev = utt_conds.device
     b, t, _ = utt_conds.shape
     infos = info if isinstance(info, (list, tuple)) else [info] * b
@@ -188,23 +213,17 @@ def generate(model, utt_conds, info, return_logp=False, generator=None, use_grap
     sw = SampleWeights(model.sample_layer, c)
     # learnable h0 (model.py:111); clone(): for b == 1 expand().contiguous() would alias the parameter itself
     states = [w.h0[:, None, :].expand(-1, b, -1).clone() for w in tiers]
-    outs = [None] * len(tiers)
+    st = _GenState(b, fs_top, tiers, sw, c, return_logp, dev)
+    st.win = y[:, :fs_top].clone()                                           # the FS samples before the frame
     logps = [] if return_logp else None
-    cp = sw.cp
-    win = y[:, :fs_top].clone()                                              # the FS samples before the frame
-    conds_cur = torch.empty(b, 1, c, dtype=F32, device=dev)
-    conds_b = _e(b, cp, device=dev)
-    c_term = _e(b, sw.h, device=dev)
-    frame_out = torch.empty(b, fs_top, dtype=torch.uint8, device=dev)
-    logp_frame = torch.empty(b, fs_top, sw.q, dtype=F32, device=dev) if return_logp else None
     graphs = None
-    # a custom generator cannot be captured; above ~128 utterances the step is GPU-bound and the graph's extra
-    # buffer copies cost more than the launch overhead they save (measured: B=64 158 vs 280 us/step, B=256 358 vs 314)
-    graphed = use_graphs and generator is None and t > 2 and b <= 128
+    graphed = use_graphs and t > 2
     for f in range(t):                                                       # top-tier frames; xi = (f+1)*FS + p
-        conds_cur.copy_(conds[:, f: f + 1])                                  # model.py:308-309: conds index xi//FS - 1
-        ops.pad_cast_bf16(conds_cur.view(b, c), b, c, c, conds_b, cp, cp)
-        ops.gemm_nt(conds_b, sw.wcs, c_term, b, sw.h, cp, cp, cp, sw.h, bias=sw.csb)
+        st.conds_cur.copy_(conds[:, f: f + 1])                               # model.py:308-309: conds index xi//FS - 1
+        ops.pad_cast_bf16(st.conds_cur.view(b, c), b, c, c, st.conds_b, sw.cp, sw.cp)
+        frame_terms(sw, st.conds_b, st.c_term, st.cc)
+        if not _GREEDY:
+            st.u_frame.uniform_(generator=generator)                         # the frame's FS x B uniforms (outside the graphs)
         if graphed and f == 1:                                               # frame 0 ran eagerly (lazy init done)
             graphs = []
             pool = None
@@ -212,7 +231,7 @@ def generate(model, utt_conds, info, return_logp=False, generator=None, use_grap
             for p in range(fs_top):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, pool=pool):
-                    _frame_phase(p, tiers, sw, lut, win, conds_cur, c_term, outs, states, frame_out, logp_frame, None)
+                    _frame_phase(p, tiers, sw, lut, st, states)
                 pool = g.pool()
                 graphs.append(g)
         if graphs is not None:
@@ -220,10 +239,10 @@ def generate(model, utt_conds, info, return_logp=False, generator=None, use_grap
                 g.replay()
         else:
             for p in range(fs_top):
-                _frame_phase(p, tiers, sw, lut, win, conds_cur, c_term, outs, states, frame_out, logp_frame, generator)
-        y[:, (f + 1) * fs_top: (f + 2) * fs_top] = frame_out
+                _frame_phase(p, tiers, sw, lut, st, states)
+        y[:, (f + 1) * fs_top: (f + 2) * fs_top] = st.frame_out
         if return_logp:
-            logps.append(logp_frame.clone())
+            logps.append(st.logp_frame.clone())
     out = y.to(torch.int64)
     if return_logp:
         return out, torch.cat(logps, dim=1)

@@ -110,6 +110,26 @@ def onehot_rows(idx_u8, q=256):
     return out
 
 
+def embed_sum(table, idx_u8, idx_ld, batch, r0, q, hidden, pre, pre_ld, relu, out, out_ld):
+    """out[b] = act(sum_k table[k*q + idx[b*idx_ld + k]] + pre[b]); ``idx_u8`` may be a view into a wider window."""
+    _need(table, BF16, 'embed_sum table')
+    _need(idx_u8, torch.uint8, 'embed_sum idx')
+    call('srnn_embed_sum', ptr(table), ptr(idx_u8), idx_ld, batch, r0, q, hidden, ptr(pre), pre_ld, int(relu), ptr(out),
+         out_ld, stream())
+    _count()
+    return out
+
+
+def sample_categorical(x, batch, q, u, win, win_len, out, out_ld, normalise=False, logp_out=None):
+    """Draw one code per row from exp(log-probabilities) (inverse CDF with the uniforms ``u``; arg-max when ``u`` is
+    None), append it to the row's window ``win`` (shifted left by one) and store it at ``out[b*out_ld]``.  With
+    ``normalise`` the rows of ``x`` are raw logits and the log-softmax is taken first (written to ``logp_out``)."""
+    _need(x, F32, 'sample input')
+    call('srnn_sample_categorical', ptr(x), x.stride(0), batch, q, int(normalise), ptr(logp_out),
+         logp_out.stride(0) if logp_out is not None else 0, ptr(u), ptr(win), win_len, ptr(out), out_ld, stream())
+    _count()
+
+
 # ----------------------------------------------------------------------------------------------
 # parameter preparation
 # ----------------------------------------------------------------------------------------------
@@ -249,7 +269,7 @@ def gemm_tn(a, b, c, m, n, k, lda, ldb, ldc, batch=1, a_bs=0, b_bs=0, a_off=0, b
 
 
 def gemm_nll(mode, a, w, bias, target, m, k, lda, ldw, lse=None, logp_target=None, logp=None, row_grad=None, g=None,
-             dlogits=None):
+             dlogits=None, ldlogp=256):
     n = NllArgs()
     n.mode, n.m, n.k = mode, m, k
     n.a, n.lda, n.w, n.ldw = a.data_ptr(), lda, w.data_ptr(), ldw
@@ -257,7 +277,7 @@ def gemm_nll(mode, a, w, bias, target, m, k, lda, ldw, lse=None, logp_target=Non
     n.target = target.data_ptr()
     n.lse = lse.data_ptr() if lse is not None else None
     n.logp_target = logp_target.data_ptr() if logp_target is not None else None
-    n.logp, n.ldlogp = (logp.data_ptr(), 256) if logp is not None else (None, 0)
+    n.logp, n.ldlogp = (logp.data_ptr(), ldlogp) if logp is not None else (None, 0)
     n.row_grad = row_grad.data_ptr() if row_grad is not None else None
     n.g, n.ldg = (g.data_ptr(), 256) if g is not None else (None, 0)
     n.dlogits, n.lddlogits = (dlogits.data_ptr(), 256) if dlogits is not None else (None, 0)
@@ -275,6 +295,9 @@ gru_debug_ts = None      # int64 [256, 8] tensor receiving CTA 0's pipeline time
 gru_units_per_cta = 8    # 16 halves the recurrent kernels' CTA count (SMs left free for concurrent GEMMs)
 
 
+_gru_scratch = {}
+
+
 def _gru_call(name, batch, steps, hidden, cell=0, **bufs):
     """Runs the persistent kernel over slot groups of <= 64 rows (independent sequences).
     ``bufs``: field -> (tensor, elements per batch row); time-major buffers advance by one row."""
@@ -287,14 +310,20 @@ def _gru_call(name, batch, steps, hidden, cell=0, **bufs):
                 setattr(a, key, None)
             else:
                 setattr(a, key, t.data_ptr() + b0 * per_row * t.element_size())
-        sync = torch.zeros(256, dtype=torch.int32, device=bufs['h_ext'][0].device)
+        dev = bufs['h_ext'][0].device
+        if steps == 1:                     # a single timestep never waits on the arrival counter: no zeroing needed
+            sync = _gru_scratch.get(dev)
+            if sync is None:
+                sync = _gru_scratch[dev] = torch.zeros(256, dtype=torch.int32, device=dev)
+        else:
+            sync = torch.zeros(256, dtype=torch.int32, device=dev)
         a.sync = sync.data_ptr()
         a.debug_flags = gru_debug_flags
         a.units_per_cta = gru_units_per_cta
         a.debug_ts = gru_debug_ts.data_ptr() if gru_debug_ts is not None else None
         _lib.profile_note = f'B={nb} T={steps} H={hidden}' + (' lstm' if cell else '')
         call(name, C.byref(a), stream())
-        _count(2)
+        _count(1 if steps == 1 else 2)
 
 
 def gru_forward(gi, w_hh, b_hh, h_ext, hall, h_state, gates, batch, steps, hidden):

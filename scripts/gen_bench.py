@@ -15,21 +15,33 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=256)
 ap.add_argument('--frames', type=int, default=8)
 ap.add_argument('--profile', action='store_true')
+ap.add_argument('--eager', action='store_true')
 a = ap.parse_args()
 torch.manual_seed(0)
 model = SampleRNNModel(**bench.model_kwargs(a.frames)).cuda()
 utt = torch.randn(a.batch, a.frames, 43).cuda()
 info = [{'speaker': {'index': i % 126}} for i in range(a.batch)]
-model.test(utt[:, :2], info)                   # warm-up
+model.test(utt[:, :3], info)                   # warm-up (lazy initialisation, allocator)
 torch.cuda.synchronize()
-ops.launch_count = 0
-t0 = time.perf_counter()
-y = model.test(utt, info)
-torch.cuda.synchronize()
-dt = time.perf_counter() - t0
-n = a.frames * int(model.frame_size)
-print(f'generated {a.batch} x {n} samples in {dt:.3f} s: {1e6 * dt / n:.1f} us per sample step, '
-      f'{a.batch * n / dt / 1e3:.1f} k samples/s, {ops.launch_count / n:.1f} kernel launches per sample step')
+
+
+def run(frames):
+    ops.launch_count = 0
+    t0 = time.perf_counter()
+    model.test(utt[:, :frames], info, use_graphs=not a.eager)
+    torch.cuda.synchronize()
+    return time.perf_counter() - t0
+
+
+# the call prepares the weights and captures the step graphs once: report the whole call and the marginal step
+short = max(a.frames // 4, 3)
+dt_short, dt = run(short), run(a.frames)
+fs = int(model.frame_size)
+n = a.frames * fs
+step_us = 1e6 * (dt - dt_short) / ((a.frames - short) * fs)
+print(f'[{short} frames {dt_short:.3f} s, {a.frames} frames {dt:.3f} s] generated {a.batch} x {n} samples in {dt:.3f} s (whole call: {a.batch * n / dt / 1e3:.1f} k samples/s); '
+      f'marginal {step_us:.1f} us per sample step = {a.batch / step_us * 1e3:.1f} k samples/s; '
+      f'setup + graph capture {1e3 * (dt - step_us * n * 1e-6):.1f} ms')
 if '--profile' in sys.argv:
     # device time of every C-ABI call of the eager path (CUDA events; launch gaps excluded)
     import collections

@@ -126,6 +126,30 @@ def test_gemm_nt_epilogue_bias_aux_relu_gate(ops):
     assert rel_l2(c, ref) < 1e-5
 
 
+@pytest.mark.parametrize('m,n,k', [(256, 1024, 1024), (200, 72, 4096), (512, 4096, 1024), (64, 256, 192), (3, 3072, 1024)])
+def test_gemm_nt_small_m_cluster_split_k(ops, m, n, k):
+    """M <= 512 takes the 128x64-tile kernel whose K extent is split over a thread-block cluster (generation GEMMs):
+    bias + aux (one aux row per `div` output rows) + ReLU, bf16 and fp32 outputs, strided aux / C."""
+    div = 4 if m % 4 == 0 else 1
+    a, b = rnd(m, k, scale=0.5).to(BF16), rnd(n, k, seed=1, scale=0.5).to(BF16)
+    bias = rnd(n, seed=2)
+    aux = rnd(m // div, 2 * n, seed=3).to(BF16)
+    ref = torch.relu(_gemm_ref(a, b) + bias + aux[:, n:].float().repeat_interleave(div, dim=0))
+    c = torch.zeros(m, n + 8, dtype=F32, device='cuda')
+    ops.gemm_nt(a, b, c, m, n, k, k, k, n + 8, bias=bias, aux=aux[:, n:], ldaux=2 * n, aux_mode=1, relu=True,
+                aux_row_div=div)
+    assert rel_l2(c[:, :n], ref) < 1e-5 and float(c[:, n:].abs().max()) == 0.0
+    cb = torch.zeros(m, n + 8, dtype=BF16, device='cuda')
+    ops.gemm_nt(a, b, cb, m, n, k, k, k, n + 8, bias=bias, aux=aux[:, n:], ldaux=2 * n, aux_mode=1, relu=True,
+                aux_row_div=div)
+    assert rel_l2(cb[:, :n], ref) < 4e-3 and float(cb[:, n:].float().abs().max()) == 0.0
+    c2 = torch.empty(m, n, dtype=F32, device='cuda')
+    ops.gemm_nt(a, b, c2, m, n, k, k, k, n)                # plain; twice: the result is deterministic
+    c3 = torch.empty(m, n, dtype=F32, device='cuda')
+    ops.gemm_nt(a, b, c3, m, n, k, k, k, n)
+    assert rel_l2(c2, _gemm_ref(a, b)) < 1e-5 and torch.equal(c2, c3)
+
+
 def test_gemm_nt_batched_overlapping_rows_and_strided_c(ops):
     """The sample-level contraction: A rows are overlapping windows of a (B, W, Q) one-hot buffer."""
     bsz, rf, r0, q, h = 3, 200, 4, 256, 64
@@ -459,3 +483,71 @@ def test_adam_clipped_matches_reference_golden(ops):
         for s in range(3):
             ops.adam_clipped(w, g.t(f'g{s}_{key}').cuda().contiguous(), m, v, 1e-3, 0.9, 0.999, 1e-8, s + 1)
         assert float((w.cpu() - g.t(f'w3_{key}')).abs().max()) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# generation kernels (model.py:289-351)
+# ------------------------------------------------------------------------------------------------
+def test_embed_sum_matches_gather_and_sum(ops):
+    """srnn_embed_sum == relu(sum of the r0 selected table rows + pre), fp32 accumulate, one bf16 rounding."""
+    b, r0, q, h, fs = 37, 4, 256, 192, 16
+    table = rnd(r0 * q, h, scale=0.5).to(BF16)
+    win = torch.randint(0, 256, (b, fs), generator=torch.Generator().manual_seed(2)).to(torch.uint8).cuda()
+    pre = rnd(b, 3, h, scale=0.5, seed=1).to(BF16)
+    out = torch.empty(b, h, dtype=BF16, device='cuda')
+    ops.embed_sum(table, win[:, fs - r0:], fs, b, r0, q, h, pre[:, 1], 3 * h, True, out, h)
+    idx = win[:, fs - r0:].long() + torch.arange(r0, device='cuda') * q
+    ref = pre[:, 1].float()
+    for k in range(r0):
+        ref = ref + table[idx[:, k]].float()
+    ref = torch.relu(ref).to(BF16)
+    assert torch.equal(out, ref)
+    ops.embed_sum(table, win[:, fs - r0:], fs, b, r0, q, h, None, 0, False, out, h)      # no pre, no relu
+    ref = sum(table[idx[:, k]].float() for k in range(r0)).to(BF16)
+    assert torch.equal(out, ref)
+
+
+def test_sample_categorical_inverse_cdf_argmax_and_window(ops):
+    b, q, fs = 300, 256, 16
+    g = torch.Generator().manual_seed(7)
+    logits = torch.randn(b, q, generator=g) * 3
+    logits[5, 40:] = -float('inf')                                            # mass on a prefix only
+    logits[6, :200] = -float('inf')                                           # mass on a suffix only
+    logp = torch.log_softmax(logits, dim=1).cuda()
+    u = torch.rand(b, generator=g)
+    u[0], u[1] = 0.0, 0.99999994                                              # the ends of [0, 1)
+    win = torch.randint(0, 256, (b, fs), generator=g).to(torch.uint8).cuda()
+    win0 = win.clone()
+    out = torch.zeros(b, 3, dtype=torch.uint8, device='cuda')
+    ops.sample_categorical(logp, b, q, u.cuda(), win, fs, out[:, 1], 3)
+    pick = out[:, 1].long().cpu()
+    assert torch.equal(win[:, :-1], win0[:, 1:]) and torch.equal(win[:, -1], out[:, 1])    # shifted window
+    assert bool((out[:, 0] == 0).all()) and bool((out[:, 2] == 0).all())                    # strided store
+    # the pick is the inverse CDF of u up to fp32 summation error at the class boundaries
+    cdf = torch.exp(logp.double().cpu()).cumsum(1)
+    tgt = (u.double() * cdf[:, -1])
+    lo = torch.where(pick > 0, cdf.gather(1, (pick - 1).clamp(min=0)[:, None])[:, 0], torch.zeros(b, dtype=torch.float64))
+    hi = cdf.gather(1, pick[:, None])[:, 0]
+    assert bool(((tgt >= lo - 1e-5) & (tgt <= hi + 1e-5)).all())
+    assert bool((torch.exp(logp.cpu()).gather(1, pick[:, None]) > 0).all())                # never a zero-mass class
+    assert pick[5] < 40 and pick[6] >= 200
+    # arg-max mode, lowest index on ties
+    logp2 = logp.clone()
+    logp2[3, 17] = logp2[3, 99] = 1.0
+    ops.sample_categorical(logp2, b, q, None, None, 0, out[:, 0], 3)
+    assert torch.equal(out[:, 0].long().cpu(), logp2.cpu().argmax(dim=1)) and int(out[3, 0]) == 17
+    # raw logits in: the log-softmax is taken by the kernel (and returned), the same uniforms give the same picks
+    lp = torch.zeros(b, 2, q, dtype=F32, device='cuda')
+    raw = (logits + 3.0).cuda()
+    ops.sample_categorical(raw, b, q, u.cuda(), None, 0, out[:, 2], 3, normalise=True, logp_out=lp[:, 1])
+    finite = torch.isfinite(logp)
+    assert float((lp[:, 1][finite] - logp[finite]).abs().max()) <= 2e-6 and bool((lp[:, 1][~finite] == -float('inf')).all())
+    assert float((out[:, 2] != out[:, 1]).float().mean()) <= 0.01 and float(lp[:, 0].abs().max()) == 0.0
+    # empirical distribution of many draws from one row
+    n = 200_000
+    row = torch.log_softmax(torch.randn(1, q, generator=g) * 2, dim=1)
+    draws = torch.empty(n, dtype=torch.uint8, device='cuda')
+    ops.sample_categorical(row.expand(n, q).contiguous().cuda(), n, q, torch.rand(n, generator=g).cuda(), None, 0, draws, 1)
+    freq = torch.bincount(draws.long().cpu(), minlength=q).double() / n
+    p = torch.exp(row[0].double())
+    assert float((freq - p).abs().max()) <= 5 * float(torch.sqrt(p.max() / n)) + 1e-4
