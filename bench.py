@@ -42,11 +42,42 @@ WORKLOAD = ('config2: 3-tier SampleRNN GRU ratios [4,4] H=1024, 64 slots/GPU x 1
             'of 8 s utterances with hidden-state carry, acoustic conds U=43, 126 speakers')
 
 
-def model_kwargs(seq_len=SEQ_LEN):
-    return dict(conds_speaker_type='embedding', conds_speaker_n=N_SPEAKERS, conds_speaker_size=15,
+CHUNKS = 8                   # sequential-loader chunks per utterance batch (8 s of audio)
+EXTRA = {}                   # extension keywords of SampleRNNModel (rnn_cell) for the other BASELINE configs
+SPEAKER = ('embedding', 15)  # conds_speaker_type, conds_speaker_size
+
+
+def select_workload(name):
+    """BASELINE.json configs[1] is the default and the one the driver measures; configs[2] and configs[3] can be
+    timed with ``--workload`` at their PER-GPU shard (weak scaling: the full configs are 8 such ranks)."""
+    global RATIOS, LAYERS, HIDDEN, SLOTS_PER_GPU, CHUNKS, EXTRA, SPEAKER, WORKLOAD
+    if name == 'config3':
+        SLOTS_PER_GPU, EXTRA, SPEAKER = 16, dict(rnn_cell='lstm'), ('pase', 100)
+        WORKLOAD = ('config3: 3-tier SampleRNN LSTM ratios [4,4] H=1024 with a 100-d PASE speaker vector, 16 slots/GPU '
+                    '(global batch 128 on 8 GPUs) x 1 s chunks of 8 s utterances with (h, c) carry')
+    elif name == 'config4':
+        RATIOS, LAYERS, HIDDEN, SLOTS_PER_GPU, CHUNKS = [4, 4, 4], [1, 1, 1], [1024, 1024, 1024], 32, 16
+        WORKLOAD = ('config4: 4-tier SampleRNN GRU ratios [4,4,4] H=1024, 32 slots/GPU (global batch 256 on 8 GPUs) x '
+                    '16 sequential 1 s chunks (L=250, RF=16000) of 16 s utterances with hidden-state carry')
+    elif name != 'config2':
+        raise SystemExit(f'unknown workload {name}')
+
+
+def model_kwargs(seq_len=None):
+    if seq_len is None:
+        seq_len = seq_len_default()
+    return dict(conds_speaker_type=SPEAKER[0], conds_speaker_n=N_SPEAKERS, conds_speaker_size=SPEAKER[1],
                 conds_utterance_type='acoustic', conds_utterance_linguistic_n=[9, 5, 4, 3],
                 conds_utterance_linguistic_emb_size=10, conds_size=50, sequence_length=seq_len, ratios=RATIOS,
-                rnn_layers=LAYERS, rnn_hidden_size=HIDDEN, q_type_ulaw=True, q_levels=256)
+                rnn_layers=LAYERS, rnn_hidden_size=HIDDEN, q_type_ulaw=True, q_levels=256, **EXTRA)
+
+
+def seq_len_default():
+    """Frames of the top tier per chunk such that a chunk is 16 000 samples (1 s of 16 kHz audio)."""
+    fs = 1
+    for r in RATIOS:
+        fs *= r
+    return 16000 // fs
 
 
 def flops_per_sample_fwd():
@@ -57,7 +88,8 @@ def flops_per_sample_fwd():
     fs = 1
     for n, r in enumerate(RATIOS):
         fs *= r
-        f += (1.0 / fs) * 2 * (fs * h + c * h + LAYERS[n] * 2 * 3 * h * h + r * h * h)
+        gates = 4 if EXTRA.get('rnn_cell') == 'lstm' else 3
+        f += (1.0 / fs) * 2 * (fs * h + c * h + LAYERS[n] * 2 * gates * h * h + r * h * h)
     return f
 
 
@@ -67,7 +99,7 @@ def flops_per_sample_fwd():
 def cpu_reference(steps, warmup, batch=8, seq_len=64):
     from oracle import samplernn_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    spec = O.ModelSpec(RATIOS, LAYERS, HIDDEN, seq_len)
+    spec = O.ModelSpec(RATIOS, LAYERS, HIDDEN, seq_len, cell=EXTRA.get('rnn_cell', 'gru'))
     params = O.init_params(spec, conds_speaker_n=N_SPEAKERS)
     trainer = O.CpuTrainer(spec, params)
     wav, conds, spk = O.synthetic_utterances(spec, batch, warmup + steps)
@@ -160,12 +192,16 @@ def run_gpu(args):
     fs = int(model.frame_size)
     rf = int(model.receptive_field)
     b = SLOTS_PER_GPU
-    chunks = 8
-    wav, conds, spk = synthetic.synthetic_utterances(fs, rf, SEQ_LEN, b, chunks, seed=4321 + rank, n_speakers=N_SPEAKERS)
+    chunks = CHUNKS
+    seq_len = seq_len_default()
+    wav, conds, spk = synthetic.synthetic_utterances(fs, rf, seq_len, b, chunks, seed=4321 + rank, n_speakers=N_SPEAKERS)
     info = [{'speaker': {'index': int(s)}} for s in spk]
+    if SPEAKER[0] == 'pase':
+        vecs = torch.randn(b, SPEAKER[1], generator=torch.Generator().manual_seed(99 + rank))
+        info = [{'speaker': {'pase': vecs[i]}} for i in range(b)]
     host = []
     for k in range(chunks):
-        x, y, c = synthetic.chunk_of(fs, rf, SEQ_LEN, wav, conds, k)
+        x, y, c = synthetic.chunk_of(fs, rf, seq_len, wav, conds, k)
         host.append((x.pin_memory(), y.pin_memory(), c.pin_memory()))
     resident = [tuple(t.to(dev) for t in h) for h in host]
     resets = [torch.ones(b, dtype=torch.int64), torch.zeros(b, dtype=torch.int64)]
@@ -224,6 +260,7 @@ def run_gpu(args):
         peak = peaks.get('bf16_tflops_sustained', 1400.0)
         m_rows, h = b * rf, HIDDEN[0]
         gemm_flops = 2.0 * m_rows * h * 2 * h                     # comb_layer forward GEMM as executed: (B*RF, 2H) x (2H, H)
+        r0 = RATIOS[0]
         avg_ms = sum(kernel_ms) / max(len(kernel_ms), 1)
         achieved = gemm_flops / (avg_ms * 1e-3) / 1e12 if avg_ms else None
         total = args.steps * global_rows
@@ -248,7 +285,7 @@ def run_gpu(args):
                           # dram__bytes_read+write of this kernel from `ncu --set full` at 262 144 rows
                           # (profiles/r01_hot_kernels_ncu.txt [1]) scaled to this launch's rows; algorithmic = A + C + W
                           traffic=NCU_BYTES_AT_262144 * m_rows / 262144.0 if NCU_BYTES_AT_262144 else None,
-                          traffic_algorithmic=2.0 * m_rows * 3 * h + 2.0 * (m_rows // 16) * h + 4.0 * h * h,
+                          traffic_algorithmic=2.0 * m_rows * 3 * h + 2.0 * (m_rows // r0) * h + 4.0 * h * h,
                           launches_timed=len(kernel_ms), avg_launch_ms=avg_ms,
                           peak_source='MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
                           if peaks else 'fallback'),
@@ -265,7 +302,9 @@ def main():
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='config2', choices=['config2', 'config3', 'config4'])
     args = ap.parse_args()
+    select_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
         run_reference(args)
