@@ -593,7 +593,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (warp == 2 && lane == 0) {
-          GRU_TS(6, s + 1);                                     // stamps are indexed by the CONSUMING round
+          GRU_TS(6, s);
           red_release_gpu_add(p.sync, 1u);
         }
         if (io) {                                               // dgi is only read after the kernel

@@ -20,7 +20,7 @@ def timed(name, fn, flops=None, nbytes=None):
     e0.record(); fn(); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     extra = f'{flops / ms / 1e9:8.1f} TFLOP/s' if flops else f'{nbytes / ms / 1e6:8.1f} GB/s'
-    print(f'{name:34s} {ms:8.3f} ms  {extra}')
+    print(f'{name:50s} {ms:8.3f} ms  {extra}')
 
 
 cat = torch.randn(m, 2 * h, device=dev).to(bf)
@@ -53,3 +53,19 @@ timed('quantize_ulaw 64 x 16015', lambda: ops.quantize_ulaw(x, want_i64=True, wa
 timed('colsum m x 1024 bf16', lambda: ops.colsum(h1, m, h, h), nbytes=m * h * 2)
 idx = torch.randint(0, 256, (64, 16003), dtype=torch.uint8, device=dev)
 timed('onehot_rows 64 x 16003 x 256', lambda: ops.onehot_rows(idx), nbytes=idx.numel() * 513)
+# generation kernels (BASELINE config 5: 256 utterances)
+bg = 256
+hg1 = torch.randn(bg, h, device=dev).to(bf)
+hg2 = torch.empty(bg, h, dtype=bf, device=dev)
+timed('small-M NT 256 x 1024 x 1024 (cluster split-K 4)', lambda: ops.gemm_nt(hg1, w2, hg2, bg, h, h, h, h, h, bias=bias, relu=True),
+      flops=2.0 * bg * h * h)
+table = torch.randn(4 * q, h, device=dev).to(bf)
+win = torch.randint(0, 256, (bg, 16), dtype=torch.uint8, device=dev)
+pre = torch.randn(bg, 4, h, device=dev).to(bf)
+timed('embed_sum 256 x (4 rows of 1024)', lambda: ops.embed_sum(table, win[:, 12:], 16, bg, 4, q, h, pre[:, 1], 4 * h, True, hg2, h),
+      nbytes=bg * (5 * h * 2 + h * 2))
+logits = torch.randn(bg, q, device=dev)
+u = torch.rand(bg, device=dev)
+picks = torch.empty(bg, dtype=torch.uint8, device=dev)
+timed('log-softmax + draw 256 x 256', lambda: ops.sample_categorical(logits, bg, q, u, win, 16, picks, 1, normalise=True),
+      nbytes=bg * q * 4)
