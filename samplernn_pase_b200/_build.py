@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, 'libsrnn_b200.so')
 STAMP = os.path.join(HERE, '.libsrnn_b200.stamp')
 SOURCES = ['core.cu', 'gemm.cu', 'gru.cu', 'elementwise.cu', 'generate.cu']
 FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-Xcompiler', '-fPIC',
-         '--cudart', 'shared']
+         '--cudart', 'shared'] + os.environ.get('SRNN_NVCC_EXTRA', '').split()
 
 
 def _digest():

@@ -16,6 +16,7 @@
 // TMEM allocator, warps 4-7 = epilogue (one TMEM lane quadrant each).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -447,36 +448,55 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 // ---------------------------------------------------------------------------------------------
 // Small-M NT GEMM (M <= 512: the per-sample GEMMs of generation, model.py:289-351, and tiny shapes).
 // With so few rows the 128 x 256 persistent kernel runs on a handful of SMs, each streaming its
-// whole K extent through one SM's ~60 B/clk L2 port (256 x 1024 x 1024: 8 CTAs, 14 us).  Here the
-// tile is 128 x 64 and the K extent is SPLIT over a thread-block cluster of CS CTAs (2 x 16 tiles x 4
-// = 128 CTAs for the same shape); every CTA leaves its fp32 partial tile in shared memory and, after one
-// cluster barrier, reduces a 1/CS column slice of the tile over its peers' shared memory (DSMEM loads),
-// applies bias / aux / ReLU and stores it.  Deterministic (fixed summation order), no atomics, no
-// workspace.
+// whole K extent through one SM's L2 port with only 4 x 48 KB in flight (256 x 1024 x 1024: 8 CTAs,
+// 14 us).  Here the tile is 128 x 64 and the K extent is SPLIT over a thread-block cluster of CS CTAs
+// (2 x 16 tiles x 4 = 128 CTAs for the same shape, every CTA with its whole K share in flight at once).
+// Reduction, push model (as in the recurrent kernel): every rank sends, for each destination rank, the
+// 64/CS columns that rank finalises straight into the destination's shared memory with st.async; the
+// bytes complete on the destination's mbarrier.  The destination then sums the CS slices in a fixed order
+// from its own shared memory, applies bias / aux / ReLU and stores.  Deterministic, no atomics, no
+// workspace.  (A pull model - cluster barrier, then DSMEM loads of the peers' partial tiles - was measured
+// 3 us slower per launch: the 16-byte remote loads are latency- and request-rate-bound.)
 // ---------------------------------------------------------------------------------------------
 constexpr int SBN = 64;
-constexpr int S_STAGES = 3;                              // 3 x 24 KB + 34 KB partial tile: two CTAs per SM
+constexpr int S_STAGES = 4;
 constexpr int S_STAGE = BM * BK * 2 + SBN * BK * 2;      // 24 KB
-constexpr int S_RED_LD = SBN + 4;                        // padded fp32 row (bank spread for the 16-byte stores)
-constexpr int S_RED_OFF = S_STAGES * S_STAGE;
-constexpr int S_BAR_OFF = S_RED_OFF + BM * S_RED_LD * 4;
+constexpr int S_RECV_OFF = S_STAGES * S_STAGE;           // recv[src rank][128 rows][64/CS columns] fp32 = 32 KB
+constexpr int S_BAR_OFF = S_RECV_OFF + BM * SBN * 4;
 constexpr int S_TOTAL = S_BAR_OFF + 256 + 1024;
 
+#ifdef SRNN_SMALL_TS
+__device__ unsigned long long g_small_ts[512 * 8];
+#define SMALL_TS(slot_)                                                                          \
+  do {                                                                                           \
+    if (threadIdx.x == (slot_ == 2 ? 32 : (slot_ >= 3 ? 128 : 0)) && blockIdx.x < 512) {         \
+      unsigned long long t_;                                                                     \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                     \
+      g_small_ts[blockIdx.x * 8 + (slot_)] = t_;                                                 \
+    }                                                                                            \
+  } while (0)
+#else
+#define SMALL_TS(slot_)
+#endif
+
 template <int CS>
-__global__ void __launch_bounds__(384, 2)
+__global__ void __launch_bounds__(384, 1)
 gemm_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const GemmParams p) {
   constexpr uint32_t IDESC = idesc_bf16(BM, SBN, false, false);
+  constexpr int CPC = SBN / CS;                        // columns finalised by one rank
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* red = reinterpret_cast<float*>(smem + S_RED_OFF);
+  float* recv = reinterpret_cast<float*>(smem + S_RECV_OFF);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S_BAR_OFF);
   uint64_t* empty = full + S_STAGES;
   uint64_t* tfull = empty + S_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  uint64_t* recv_bar = tfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(recv_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  SMALL_TS(0);
   const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
   const int tile = blockIdx.x / CS;
   const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
@@ -494,7 +514,9 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       mbar_init(&empty[s], 1);
     }
     mbar_init(tfull, 1);
+    mbar_init(recv_bar, 1);
     fence_barrier_init();
+    if (CS > 1) mbar_expect_tx(recv_bar, static_cast<uint32_t>((CS - 1) * BM * CPC * 4));   // the peers' slices
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, SBN);
@@ -503,7 +525,9 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (CS > 1) cluster_arrive();                        // (waited for just before the first remote push)
   const uint32_t tmem_base = *tmem_slot;
+  SMALL_TS(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -528,6 +552,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full[stage], phase);
+        if (kb == kb_begin) SMALL_TS(2);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + stage * S_STAGE);
         const uint32_t b_addr = a_addr + BM * BK * 2;
@@ -545,54 +570,62 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // partial tile: TMEM -> this CTA's shared memory (zeros when this rank got no K blocks)
+    // ---- partial tile out of TMEM; each group of 4 columns goes to the rank that finalises it -------------
     const int q = warp & 3, half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     uint32_t v[32];
     if (nkb > 0) {
       mbar_wait(tfull, 0);
+      SMALL_TS(3);
       tc_fence_after();
       tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 32, v);
       tmem_ld_wait();
     } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = 0u;
+      for (int i = 0; i < 32; ++i) v[i] = 0u;          // this rank got no K blocks
     }
-    float4* dst = reinterpret_cast<float4*>(red + row * S_RED_LD + half * 32);
+    if (CS > 1) cluster_wait();                        // every rank's barriers are initialised
+    const uint32_t recv_addr = smem_u32(recv);
+    const uint32_t bar_addr = smem_u32(recv_bar);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      dst[i] = make_float4(__uint_as_float(v[i * 4]), __uint_as_float(v[i * 4 + 1]), __uint_as_float(v[i * 4 + 2]),
-                           __uint_as_float(v[i * 4 + 3]));
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (CS > 1) cluster_sync_all();                      // every rank's partial tile is in its shared memory
+    for (int i = 0; i < 8; ++i) {
+      const int col = half * 32 + i * 4;               // tile column of this float4
+      const int dst = col / CPC;
+      const uint32_t off = static_cast<uint32_t>(((static_cast<int>(crank) * BM + row) * CPC + col % CPC) * 4);
+      if (CS == 1 || dst == static_cast<int>(crank)) {
+        *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(recv) + off) =
+            make_float4(__uint_as_float(v[i * 4]), __uint_as_float(v[i * 4 + 1]), __uint_as_float(v[i * 4 + 2]),
+                        __uint_as_float(v[i * 4 + 3]));
+      } else {
+        st_async_v4(mapa(recv_addr + off, static_cast<uint32_t>(dst)), __uint_as_float(v[i * 4]),
+                    __uint_as_float(v[i * 4 + 1]), __uint_as_float(v[i * 4 + 2]), __uint_as_float(v[i * 4 + 3]),
+                    mapa(bar_addr, static_cast<uint32_t>(dst)));
+      }
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 256;" ::: "memory");     // this rank's own slice is complete in shared memory
+    if (CS > 1) mbar_wait(recv_bar, 0);                // ... and so are the peers' slices
+    SMALL_TS(4);
 
-  if (warp >= 4) {
-    constexpr int CPC = SBN / CS;                      // columns reduced by this CTA
-    constexpr int CPT = CPC / 2;                       // ... per thread: 32 / 16 / 8
+    // ---- sum the CS slices of this rank's columns (fixed order), epilogue, store ---------------------------
+    constexpr int CPT = CPC / 2;                       // columns per thread: 32 / 16 / 8
     const int tid = threadIdx.x - 128;
-    const int row = tid >> 1;
-    const int c0 = static_cast<int>(crank) * CPC + (tid & 1) * CPT;
+    const int r2 = tid >> 1;
+    const int c0 = (tid & 1) * CPT;
     float f[CPT];
 #pragma unroll
     for (int i = 0; i < CPT; ++i) f[i] = 0.f;
-    const float* mine = red + row * S_RED_LD + c0;
 #pragma unroll
     for (int src = 0; src < CS; ++src) {
+      const float4* sp = reinterpret_cast<const float4*>(recv + (src * BM + r2) * CPC + c0);
 #pragma unroll
       for (int i = 0; i < CPT / 4; ++i) {
-        float4 t;
-        if constexpr (CS == 1) {
-          t = reinterpret_cast<const float4*>(mine)[i];
-        } else {
-          t = ld_dsmem_f4(mapa(smem_u32(mine) + i * 16, static_cast<uint32_t>(src)));
-        }
+        const float4 t = sp[i];
         f[i * 4 + 0] += t.x; f[i * 4 + 1] += t.y; f[i * 4 + 2] += t.z; f[i * 4 + 3] += t.w;
       }
     }
-    const int gr = mt * BM + row;
-    const int gc = nt * SBN + c0;
+    const int gr = mt * BM + r2;
+    const int gc = nt * SBN + static_cast<int>(crank) * CPC + c0;
     if (gr < p.m && gc < p.n) {
       const bool full_cols = gc + CPT <= p.n;
       if (p.bias) {
@@ -640,11 +673,22 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         }
       }
     }
+    SMALL_TS(5);
   }
-  if (CS > 1) cluster_sync_all();                      // nobody exits while a peer may still read its partial tile
+  // A rank leaves only after every slice addressed to it has landed (recv_bar above); its own pushes carry their
+  // data with them.  Warps 0-3 still owe the wait half of the cluster barrier.
+  if (CS > 1 && warp < 4) cluster_wait();
+  tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, SBN);
+  SMALL_TS(6);
 }
+
+#ifdef SRNN_SMALL_TS
+extern "C" int srnn_debug_small_ts(unsigned long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_small_ts, sizeof(g_small_ts)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -726,7 +770,7 @@ static int launch_small(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
   return SRNN_OK;
 }
 
-// M <= 512, one batch, plain epilogue: 128 x 64 tiles, K split over a cluster so that ~1-2 CTAs per SM exist
+// M <= 512, one batch, plain epilogue: 128 x 64 tiles, K split over a cluster while the CTAs still fit one wave
 static int run_nt_small(const srnn_gemm_args* a, GemmParams& p, cudaStream_t stream) {
   SRNN_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0, "gemm NT: lda/ldb must be multiples of 8 elements (lda=%lld ldb=%lld)",
                  (long long)a->lda, (long long)a->ldb);
@@ -736,7 +780,10 @@ static int run_nt_small(const srnn_gemm_args* a, GemmParams& p, cudaStream_t str
   p.total_kb = p.kb_per_batch = (a->k + BK - 1) / BK;
   const int tiles = p.tiles_m * p.tiles_n;
   int cs = 1;
-  while (cs < 4 && tiles * cs * 2 <= 2 * sm_count() && p.total_kb >= cs * 4) cs *= 2;
+  while (cs < 4 && tiles * cs * 2 <= sm_count() && p.total_kb >= cs * 4) cs *= 2;   // one wave of CTAs, >= 2 K blocks each
+#ifdef SRNN_SMALL_TS
+  if (const char* e = getenv("SRNN_SMALL_CS")) cs = atoi(e);
+#endif
   p.splits = cs;
   p.kb_per_split = (p.total_kb + cs - 1) / cs;
   p.total_work = tiles;

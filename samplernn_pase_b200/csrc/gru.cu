@@ -137,15 +137,6 @@ __device__ __forceinline__ void grid_wait(const uint32_t* counter, uint32_t targ
   if (acquire_fence) asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
-// Push 16 bytes into a peer CTA's shared memory; the peer's mbarrier receives complete_tx(16), so the
-// consumer needs no fence: waiting on its own barrier makes the data visible (like a TMA load).
-__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float a, float b, float c, float d,
-                                            uint32_t remote_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
-               ::"r"(remote_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(remote_bar)
-               : "memory");
-}
-
 // LSTM = false: GRU (gates r,z,n; 3H pre-activations).  LSTM = true: LSTM (gates i,f,g,o; 4H), an
 // extension with no reference counterpart (BASELINE config 3; torch.nn.LSTM semantics, see oracle).
 template <bool BWD, int C, bool LSTM, int U, int MW>
