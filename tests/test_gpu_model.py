@@ -286,6 +286,18 @@ def test_generation_is_consistent_with_teacher_forcing():
     report(f'generation (CUDA-graph path) vs teacher forcing ({rf2} samples): max|dlogp| {d2:.3e}')
     assert d2 <= 0.05, d2
     assert len(set(y2[0, fs:].tolist())) > 3                                   # it really samples
+    # more utterances than one recurrent launch or one GEMM M tile holds (3 slot groups: 64 + 64 + 2 rows)
+    bsz3, t3 = 130, 3
+    utt3 = torch.randn(bsz3, t3, 43, generator=torch.Generator().manual_seed(6))
+    info3 = [{'speaker': {'index': i % 5}} for i in range(bsz3)]
+    y3, logp3 = model.test(utt3.cuda(), info3, return_logp=True)
+    y3 = y3.cpu()
+    rf3 = t3 * fs
+    ref3 = O.forward_indices(params, spec, y3[:, :rf3 + fs - 1], y3[:, fs:fs + rf3], utt3, torch.arange(bsz3) % 5,
+                             [1] * bsz3)[0]
+    d3 = float((logp3.cpu() - ref3).abs().max())
+    report(f'generation, 130 utterances vs teacher forcing ({rf3} samples): max|dlogp| {d3:.3e}')
+    assert d3 <= 0.05, d3
 
 
 def test_chunked_equals_unchunked_with_carry():
