@@ -37,18 +37,22 @@ class TierWeights:
                         self.wcat[:, fs:], (self.kp, 1, 0))
         self.bias_u = (layer.x_expand.bias + layer.conds_expand.bias).detach().contiguous()
         self.rnn = []
+        self.lstm = layer.rnn_cell == 'lstm'
+        ng = 4 if self.lstm else 3
+        self.ng = ng
         flat = layer.rnn.flat(layer.rnn_layers)
         for i in range(layer.rnn_layers):
             w_ih, w_hh, b_ih, b_hh = (t.detach().contiguous() for t in flat[4 * i: 4 * i + 4])
-            wih, whh = _e(3 * h, h, device=dev), _e(3 * h, h, device=dev)
-            ops.weight_prep(w_ih, None, (3 * h, h, 1), wih, (h, 1, 0))
-            ops.weight_prep(w_hh, None, (3 * h, h, 1), whh, (h, 1, 0))
+            wih, whh = _e(ng * h, h, device=dev), _e(ng * h, h, device=dev)
+            ops.weight_prep(w_ih, None, (ng * h, h, 1), wih, (h, 1, 0))
+            ops.weight_prep(w_hh, None, (ng * h, h, 1), whh, (h, 1, 0))
             self.rnn.append((wih, whh, b_ih, b_hh))
         self.wu = _e(r * h, h, device=dev)
         ops.weight_prep(layer.upsample.weight_v.detach(), layer.upsample.weight_g.detach(), (h, h, r), self.wu,
                         (1, h, h * h))
         self.bias_up = layer.upsample_bias.detach().t().contiguous().view(-1)
         self.h0 = layer.rnn_h0.detach()
+        self.c0 = layer.rnn_c0.detach() if self.lstm else None
 
 
 class SampleWeights:
@@ -88,11 +92,11 @@ class SampleWeights:
         self.b3 = sl.adapt.bias.detach().contiguous()
 
 
-def tier_step(w, lut, win, conds_row, upper, upper_ld, h_state, out):
+def tier_step(w, lut, win, conds_row, upper, upper_ld, h_state, out, c_state=None):
     """One frame of a tier for every utterance.  ``win`` (B, FS) uint8 holds the last FS generated samples (the
     tier reads its last fs), ``conds_row`` (B,1,C) fp32, ``upper`` a (B,H) bf16 view with row stride ``upper_ld``
-    (or None for the top tier), ``h_state`` (layers,B,H) fp32 updated in place.  Writes the r upsampled
-    conditioning vectors into ``out`` (B, r, H) bf16."""
+    (or None for the top tier), ``h_state`` (and for LSTM tiers ``c_state``) (layers,B,H) fp32 updated in place.
+    Writes the r upsampled conditioning vectors into ``out`` (B, r, H) bf16."""
     b, fs_top = win.shape
     dev = win.device
     h = w.h
@@ -100,13 +104,17 @@ def tier_step(w, lut, win, conds_row, upper, upper_ld, h_state, out):
     x = _e(b, h, device=dev)
     ops.gemm_nt(ain, w.wcat, x, b, h, w.kp, w.kp, w.kp, h, bias=w.bias_u, aux=upper, ldaux=upper_ld, aux_mode=1)
     for i, (wih, whh, b_ih, b_hh) in enumerate(w.rnn):
-        gi = _e(b, 3 * h, device=dev)
-        ops.gemm_nt(x, wih, gi, b, 3 * h, h, h, h, 3 * h, bias=b_ih)
+        gi = _e(b, w.ng * h, device=dev)
+        ops.gemm_nt(x, wih, gi, b, w.ng * h, h, h, h, w.ng * h, bias=b_ih)
         h_ext = _e(2, b, h, device=dev)
         ops.pad_cast_bf16(h_state[i], b, h, h, h_ext, h, h)
         hall = _e(b, h, device=dev)
-        gates = _e(b, 4 * h, device=dev)
-        ops.gru_forward(gi, whh, b_hh, h_ext, hall, h_state[i], gates, b, 1, h)
+        if w.lstm:
+            gates = _e(b, 5 * h, device=dev)
+            ops.lstm_forward(gi, whh, b_hh, h_ext, hall, h_state[i], c_state[i], gates, b, 1, h)
+        else:
+            gates = _e(b, 4 * h, device=dev)
+            ops.gru_forward(gi, whh, b_hh, h_ext, hall, h_state[i], gates, b, 1, h)
         x = hall
     ops.gemm_nt(x, w.wu, out, b, w.r * h, h, h, h, w.r * h, bias=w.bias_up)
     return out
@@ -163,7 +171,7 @@ class _GenState:
         self.u_frame = torch.empty(fs_top, b, dtype=F32, device=dev)
 
 
-def _frame_phase(p, tiers, sw, lut, st, states):
+def _frame_phase(p, tiers, sw, lut, st, states, cstates):
     """One sample step at phase ``p = xi % FS`` of a top-tier frame, written against the static buffers of ``st`` so
     that it can be captured in a CUDA graph: ``st.win`` (B,FS) holds the last FS generated samples, ``st.outs`` the
     tiers' current upsampled outputs, ``st.frame_out[:, p]`` receives the new sample."""
@@ -177,7 +185,7 @@ def _frame_phase(p, tiers, sw, lut, st, states):
         if n != len(tiers) - 1:
             frame_index = (p % tiers[n + 1].fs) // w.fs                      # == (xi // fs_n) % r_{n+1}
             upper, upper_ld = st.outs[n + 1][:, frame_index], tiers[n + 1].r * w.h
-        tier_step(w, lut, win, st.conds_cur, upper, upper_ld, states[n], st.outs[n])
+        tier_step(w, lut, win, st.conds_cur, upper, upper_ld, states[n], st.outs[n], cstates[n])
         if n == 0:
             sample_pre(sw, st.outs[0], st.cc, st.pre)
     j = p % sw.r0                                                            # model.py:343
@@ -207,12 +215,11 @@ def generate(model, utt_conds, info, return_logp=False, generator=None, use_grap
     lut = q.lut(dev)
     total = (t + 1) * fs_top
     y = torch.full((b, total), q.quantize_zero(), dtype=torch.uint8, device=dev)
-    if any(layer.rnn_cell != 'gru' for layer in model.frames_layers):
-        raise NotImplementedError('generation is implemented for GRU tiers (the reference cell)')
     tiers = [TierWeights(layer, c) for layer in model.frames_layers]
     sw = SampleWeights(model.sample_layer, c)
     # learnable h0 (model.py:111); clone(): for b == 1 expand().contiguous() would alias the parameter itself
     states = [w.h0[:, None, :].expand(-1, b, -1).clone() for w in tiers]
+    cstates = [w.c0[:, None, :].expand(-1, b, -1).clone() if w.lstm else None for w in tiers]   # LSTM extension
     st = _GenState(b, fs_top, tiers, sw, c, return_logp, dev)
     st.win = y[:, :fs_top].clone()                                           # the FS samples before the frame
     logps = [] if return_logp else None
@@ -231,7 +238,7 @@ def generate(model, utt_conds, info, return_logp=False, generator=None, use_grap
             for p in range(fs_top):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, pool=pool):
-                    _frame_phase(p, tiers, sw, lut, st, states)
+                    _frame_phase(p, tiers, sw, lut, st, states, cstates)
                 pool = g.pool()
                 graphs.append(g)
         if graphs is not None:
@@ -239,7 +246,7 @@ def generate(model, utt_conds, info, return_logp=False, generator=None, use_grap
                 g.replay()
         else:
             for p in range(fs_top):
-                _frame_phase(p, tiers, sw, lut, st, states)
+                _frame_phase(p, tiers, sw, lut, st, states, cstates)
         y[:, (f + 1) * fs_top: (f + 2) * fs_top] = st.frame_out
         if return_logp:
             logps.append(st.logp_frame.clone())

@@ -300,6 +300,29 @@ def test_generation_is_consistent_with_teacher_forcing():
     assert d3 <= 0.05, d3
 
 
+def test_generation_with_lstm_tiers_is_consistent_with_teacher_forcing():
+    """The LSTM extension (BASELINE config 3 cell) generates through the same step programs: the log-probabilities
+    the samples were drawn from equal the oracle's teacher-forced ones (oracle definition: torch.nn.LSTM semantics)."""
+    from samplernn_pase_b200 import SampleRNNModel
+    spec = O.ModelSpec([4, 4], [1, 1], [64, 64], 3, cell='lstm')
+    params = O.init_params(spec, conds_speaker_n=5, perturb=0.1)
+    model = SampleRNNModel('embedding', 5, 15, 'acoustic', [9, 5, 4, 3], 10, 50, 3, [4, 4], [1, 1], [64, 64], True, 256,
+                           rnn_cell='lstm').cuda()
+    model.load_state_dict(params)
+    bsz, t, fs = 5, 4, 16
+    utt = torch.randn(bsz, t, 43, generator=torch.Generator().manual_seed(8))
+    info = [{'speaker': {'index': i % 5}} for i in range(bsz)]
+    torch.cuda.manual_seed(3)
+    y, logp = model.test(utt.cuda(), info, return_logp=True)
+    y = y.cpu()
+    rf = t * fs
+    spec_t = O.ModelSpec([4, 4], [1, 1], [64, 64], t, cell='lstm')
+    ref = O.forward_indices(params, spec_t, y[:, :rf + fs - 1], y[:, fs:fs + rf], utt, torch.arange(bsz) % 5, [1] * bsz)[0]
+    d = float((logp.cpu() - ref).abs().max())
+    report(f'generation with LSTM tiers vs teacher forcing ({rf} samples): max|dlogp| {d:.3e}')
+    assert d <= 0.05, d
+
+
 def test_chunked_equals_unchunked_with_carry():
     """Size-independent property (SURVEY probe P2): K chunks with carry == one long forward."""
     from samplernn_pase_b200 import SampleRNNModel
