@@ -231,6 +231,11 @@ int srnn_adam_clipped(float* param, const float* grad, float* exp_avg, float* ex
 /* ---------------------------------------------------------------------------------------------
  * Autoregressive generation (SampleRNNModel.test, model.py:289-351), per-sample kernels.
  * ------------------------------------------------------------------------------------------- */
+/* Process-wide switch: launch the per-sample kernels (srnn_embed_sum, the small-M path of srnn_gemm_bf16,
+ * srnn_sample_categorical) with programmatic dependent launch, so that the launch and set-up of each overlaps the
+ * tail of its predecessor in the stream (every such kernel waits for its prerequisites before touching global
+ * memory).  Off by default. */
+int srnn_set_pdl(int32_t on);
 /* Embedding side of the sample-level layer for ONE time step (model.py:192-200): the embedding, the
  * conv1d over the last r0 samples and the embedding block of comb_layer are linear in the one-hot codes,
  * so with fixed weights they are r0 tables of q rows (table bf16 (r0*q, hidden), row k*q+code):

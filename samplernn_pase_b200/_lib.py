@@ -74,6 +74,7 @@ SIGNATURES = {
     'srnn_repeat_rows': [P, I64, I32, I64, I32, P, I64, P],
     'srnn_repeat_rows_bwd': [P, I64, I32, I64, I32, P, I64, P],
     'srnn_colsum': [P, I64, I32, I64, P, P],
+    'srnn_set_pdl': [I32],
     'srnn_embed_sum': [P, P, I64, I32, I32, I32, I32, P, I64, I32, P, I64, P],
     'srnn_sample_categorical': [P, I64, I32, I32, I32, P, I64, P, P, I32, P, I64, P],
     'srnn_gemm_bf16': [C.POINTER(GemmArgs), P],

@@ -33,6 +33,9 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 int sm_count();
+// Programmatic dependent launch (srnn_set_pdl): kernels that support it are launched so that the NEXT kernel in the
+// stream may start while they still run; such kernels call pdl_wait() before their first global-memory access.
+bool pdl_enabled();
 
 // ---------------------------------------------------------------------------------------------
 // TMA tensor maps (driver entry point fetched through the runtime, no -lcuda needed)
@@ -257,6 +260,12 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
                : "memory");
   return v;
 }
+
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// launch_dependents: the next kernel in the stream may be scheduled from now on (it must itself wait).
+// wait: all prerequisite grids have completed and their memory is visible (no-op for a normal launch).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- misc ----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -84,6 +84,15 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 }  // namespace srnn
 
+namespace srnn {
+static bool g_pdl = false;
+bool pdl_enabled() { return g_pdl; }
+}  // namespace srnn
+
+extern "C" int srnn_set_pdl(int32_t on) {
+  srnn::g_pdl = on != 0;
+  return SRNN_OK;
+}
 extern "C" const char* srnn_last_error(void) { return srnn::g_err; }
 extern "C" int srnn_abi_version(void) { return SRNN_ABI_VERSION; }
 extern "C" int srnn_device_info(int* sms, int* major, int* minor) {

@@ -497,6 +497,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   SMALL_TS(0);
+  pdl_launch_dependents();                             // the next kernel's launch may overlap this one (it waits itself)
   const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
   const int tile = blockIdx.x / CS;
   const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
@@ -528,6 +529,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   if (CS > 1) cluster_arrive();                        // (waited for just before the first remote push)
   const uint32_t tmem_base = *tmem_slot;
   SMALL_TS(1);
+  pdl_wait();                                          // set-up above overlapped the previous kernel; its data from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -759,13 +761,22 @@ static int launch_small(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
   cfg.blockDim = dim3(384);
   cfg.dynamicSmemBytes = S_TOTAL;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CS > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CS;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = CS > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   SRNN_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   return SRNN_OK;
 }

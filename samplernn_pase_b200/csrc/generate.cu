@@ -15,6 +15,8 @@ namespace srnn {
 __global__ void embed_sum_kernel(const __nv_bfloat16* __restrict__ table, const uint8_t* __restrict__ idx,
                                  long long idx_ld, int r0, int q, int hidden, const __nv_bfloat16* __restrict__ pre,
                                  long long pre_ld, int relu, __nv_bfloat16* __restrict__ out, long long out_ld) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
   if (c8 * 8 >= hidden) return;
@@ -53,6 +55,8 @@ constexpr int SAMPLE_PER = 8;                          // classes per lane (q <=
 __global__ void sample_kernel(const float* __restrict__ in, long long ld, int batch, int q, int normalise,
                               float* __restrict__ logp_out, long long ld_out, const float* __restrict__ u,
                               uint8_t* __restrict__ win, int win_len, uint8_t* __restrict__ out, long long out_ld) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= batch) return;
@@ -154,6 +158,21 @@ __global__ void sample_kernel(const float* __restrict__ in, long long ld, int ba
   if (out && lane == 0) out[b * out_ld] = static_cast<uint8_t>(pick);
 }
 
+// <<<>>> with the programmatic-stream-serialization attribute when srnn_set_pdl(1) is in effect
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace srnn
 
 using namespace srnn;
@@ -168,10 +187,10 @@ extern "C" int srnn_embed_sum(const void* table, const uint8_t* idx, int64_t idx
                    reinterpret_cast<uintptr_t>(pre)) & 15) == 0, "embed_sum: pointers must be 16-byte aligned");
   const int threads = 128;
   dim3 grid((hidden / 8 + threads - 1) / threads, batch);
-  embed_sum_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(s)>>>(
-      static_cast<const __nv_bfloat16*>(table), idx, idx_ld, r0, q, hidden, static_cast<const __nv_bfloat16*>(pre),
-      pre_ld, relu, static_cast<__nv_bfloat16*>(out), out_ld);
-  SRNN_CUDA(cudaGetLastError());
+  SRNN_CUDA(launch_pdl(embed_sum_kernel, grid, dim3(threads), static_cast<cudaStream_t>(s),
+                       static_cast<const __nv_bfloat16*>(table), idx, static_cast<long long>(idx_ld), r0, q, hidden,
+                       static_cast<const __nv_bfloat16*>(pre), static_cast<long long>(pre_ld), relu,
+                       static_cast<__nv_bfloat16*>(out), static_cast<long long>(out_ld)));
   return SRNN_OK;
 }
 
@@ -182,8 +201,8 @@ extern "C" int srnn_sample_categorical(const float* in, int64_t ld, int32_t batc
                  "sample_categorical: bad arguments");
   SRNN_CHECK_ARG(!win || win_len > 0, "sample_categorical: win_len must be positive");
   const int warps = 4;
-  sample_kernel<<<(batch + warps - 1) / warps, warps * 32, 0, static_cast<cudaStream_t>(s)>>>(
-      in, ld, batch, q, normalise, logp_out, ld_out, u, win, win_len, out, out_ld);
-  SRNN_CUDA(cudaGetLastError());
+  SRNN_CUDA(launch_pdl(sample_kernel, dim3((batch + warps - 1) / warps), dim3(warps * 32), static_cast<cudaStream_t>(s),
+                       in, static_cast<long long>(ld), batch, q, normalise, logp_out, static_cast<long long>(ld_out), u,
+                       win, win_len, out, static_cast<long long>(out_ld)));
   return SRNN_OK;
 }

@@ -222,9 +222,22 @@ def generate(model, utt_conds, info, return_logp=False, generator=None, use_grap
     cstates = [w.c0[:, None, :].expand(-1, b, -1).clone() if w.lstm else None for w in tiers]   # LSTM extension
     st = _GenState(b, fs_top, tiers, sw, c, return_logp, dev)
     st.win = y[:, :fs_top].clone()                                           # the FS samples before the frame
+    graphed = use_graphs and t > 2
+    ops.set_pdl(_PDL)
+    try:
+        return _generate_frames(model, st, states, cstates, tiers, sw, lut, conds, y, t, b, c, fs_top, graphed, generator,
+                                return_logp)
+    finally:
+        ops.set_pdl(False)
+
+
+#: launch the per-sample kernels with programmatic dependent launch (their launch / set-up overlaps the predecessor)
+_PDL = True
+
+
+def _generate_frames(model, st, states, cstates, tiers, sw, lut, conds, y, t, b, c, fs_top, graphed, generator, return_logp):
     logps = [] if return_logp else None
     graphs = None
-    graphed = use_graphs and t > 2
     for f in range(t):                                                       # top-tier frames; xi = (f+1)*FS + p
         st.conds_cur.copy_(conds[:, f: f + 1])                               # model.py:308-309: conds index xi//FS - 1
         ops.pad_cast_bf16(st.conds_cur.view(b, c), b, c, c, st.conds_b, sw.cp, sw.cp)

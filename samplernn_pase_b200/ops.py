@@ -110,6 +110,11 @@ def onehot_rows(idx_u8, q=256):
     return out
 
 
+def set_pdl(on):
+    """Programmatic dependent launch for the per-sample generation kernels (process-wide switch)."""
+    call('srnn_set_pdl', int(bool(on)))
+
+
 def embed_sum(table, idx_u8, idx_ld, batch, r0, q, hidden, pre, pre_ld, relu, out, out_ld):
     """out[b] = act(sum_k table[k*q + idx[b*idx_ld + k]] + pre[b]); ``idx_u8`` may be a view into a wider window."""
     _need(table, BF16, 'embed_sum table')
