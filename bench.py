@@ -51,7 +51,11 @@ def select_workload(name):
     """BASELINE.json configs[1] is the default and the one the driver measures; configs[2] and configs[3] can be
     timed with ``--workload`` at their PER-GPU shard (weak scaling: the full configs are 8 such ranks)."""
     global RATIOS, LAYERS, HIDDEN, SLOTS_PER_GPU, CHUNKS, EXTRA, SPEAKER, WORKLOAD
-    if name == 'config3':
+    if name == 'config1':
+        RATIOS, SLOTS_PER_GPU, CHUNKS = [20, 4], 8, 1
+        WORKLOAD = ('config1: 2-tier SampleRNN of config.default.json (ratios [20,4], H=1024, 47.8 M parameters), '
+                    '8 slots x one 1 s chunk (L=200, RF=16000), acoustic conds U=43, 126 speakers')
+    elif name == 'config3':
         SLOTS_PER_GPU, EXTRA, SPEAKER = 16, dict(rnn_cell='lstm'), ('pase', 100)
         WORKLOAD = ('config3: 3-tier SampleRNN LSTM ratios [4,4] H=1024 with a 100-d PASE speaker vector, 16 slots/GPU '
                     '(global batch 128 on 8 GPUs) x 1 s chunks of 8 s utterances with (h, c) carry')
@@ -302,7 +306,7 @@ def main():
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='config2', choices=['config2', 'config3', 'config4'])
+    ap.add_argument('--workload', default='config2', choices=['config1', 'config2', 'config3', 'config4'])
     args = ap.parse_args()
     select_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
