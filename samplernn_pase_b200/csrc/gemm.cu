@@ -39,6 +39,7 @@ struct GemmParams {
   const __nv_bfloat16* aux;
   long long ldaux, aux_batch_stride;
   int aux_mode, relu, aux_row_div, max_ctas;
+  int c_tma;                       // bf16 C tiles leave through shared memory + TMA stores (tma_c is valid)
   // schedule
   int tiles_m, tiles_n, kb_per_batch, splits, kb_per_split, total_kb, total_work;
   // NLL epilogue
@@ -59,7 +60,8 @@ struct SmemCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int STAGES = BN == 256 ? 4 : 6;
-  static constexpr int BAR_OFF = STAGES * STAGE;
+  static constexpr int STG_OFF = STAGES * STAGE;          // store staging: 8 epilogue warps x 2 x (32 rows x 64 B)
+  static constexpr int BAR_OFF = STG_OFF + 8 * 2 * 2048;
   static constexpr int BIAS_OFF = BAR_OFF + 256;
   static constexpr int TOTAL = BIAS_OFF + 1024 + 1024;  // + bias tile + alignment slack
 };
@@ -98,7 +100,7 @@ __device__ __forceinline__ Work decode_work(const GemmParams& p, int w) {
 template <int BN, bool TN, int EPI>
 __global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const GemmParams p) {
+            const __grid_constant__ CUtensorMap tma_c, const GemmParams p) {
   using Cfg = SmemCfg<BN>;
   constexpr int S = Cfg::STAGES;
   constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -122,6 +124,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (EPI == 0 && p.c_tma) tma_prefetch_desc(&tma_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) {
@@ -228,6 +231,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int c_end = c_begin + CHUNKS_PER_WARP;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int stg_buf = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const Work wk = decode_work<TN>(p, w);
       if (wk.kb_end <= wk.kb_begin) continue;
@@ -245,7 +249,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           uint32_t v[32];
           tmem_ld32(t_addr + c * 32, v);
           tmem_ld_wait();
-          if (!row_ok) continue;
+          if (!row_ok && !p.c_tma) continue;           // (the TMA store needs the whole warp; it clips rows >= m itself)
           const bool full_chunk = n0 + 32 <= p.n;
           float f[32];
 #pragma unroll
@@ -255,7 +259,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             for (int i = 0; i < 32; ++i)
               if (full_chunk || n0 + i < p.n) f[i] += __ldg(p.bias + n0 + i);
           }
-          if (p.aux_mode) {
+          if (p.aux_mode && row_ok) {
             const __nv_bfloat16* ap = p.aux + wk.b * p.aux_batch_stride + static_cast<long long>(j / p.aux_row_div) * p.ldaux + n0;
             const bool vec = full_chunk && ((reinterpret_cast<uintptr_t>(ap) & 15) == 0);
             float a[32];
@@ -283,6 +287,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (p.c_tma) {
+            // bf16 tile chunk -> 64-byte-swizzled staging tile (lane = row) -> one TMA store.  Per-lane global stores
+            // (32 rows x 16 B per instruction = 32 LSU wavefronts) made the K<=1024 GEMMs epilogue-bound: 1 013 ->
+            // 1 370 TFLOP/s without them.
+            uint8_t* sb = smem + Cfg::STG_OFF + (warp - 4) * 4096 + stg_buf * 2048;
+            if (lane == 0) tma_store_wait_read<1>();   // the store that used this buffer two chunks ago has read it
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              u.x = pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1]);
+              u.y = pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3]);
+              u.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]);
+              u.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
+              *reinterpret_cast<uint4*>(sb + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = u;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int nf = p.n_fold > 0 ? p.n_fold : p.n;
+              tma_store_4d(&tma_c, sb, n0 % nf, n0 / nf, wk.mt * BM + q * 32, wk.b);
+              tma_store_commit();
+            }
+            stg_buf ^= 1;
+            continue;
           }
           long long out_row = j;
           int out_col = n0;
@@ -438,6 +468,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (EPI == 0 && p.c_tma && lane == 0) tma_store_wait_read<0>();   // staging tiles stay valid until read
   }
 
   tc_fence_before();
@@ -696,7 +727,8 @@ extern "C" int srnn_debug_small_ts(unsigned long long* host_out) {
 // host side
 // ---------------------------------------------------------------------------------------------
 template <int BN, bool TN, int EPI>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
+                  cudaStream_t stream) {
   auto kern = gemm_kernel<BN, TN, EPI>;
   static bool configured = false;   // per instantiation
   if (!configured) {
@@ -707,7 +739,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   if (p.max_ctas > 0 && p.max_ctas < cap) cap = p.max_ctas;    // leave SMs to a concurrently running kernel
   int grid = p.total_work < cap ? p.total_work : cap;
   if (grid < 1) return SRNN_OK;
-  kern<<<grid, gemm_threads<EPI>(), SmemCfg<BN>::TOTAL, stream>>>(ta, tb, p);
+  kern<<<grid, gemm_threads<EPI>(), SmemCfg<BN>::TOTAL, stream>>>(ta, tb, tc, p);
   SRNN_CUDA(cudaGetLastError());
   return SRNN_OK;
 }
@@ -743,9 +775,25 @@ static int run_nt(const srnn_gemm_args* a, GemmParams& p, bool nll, cudaStream_t
     int rc = make_tmap_bf16(&tb, a->b, 2, dims, strides, box, true);
     if (rc) return rc;
   }
-  if (nll) return launch<256, false, 1>(ta, tb, p, stream);
-  if (bn == 256) return launch<256, false, 0>(ta, tb, p, stream);
-  return launch<128, false, 0>(ta, tb, p, stream);
+  if (nll) return launch<256, false, 1>(ta, tb, ta, p, stream);
+  // bf16 outputs with 16-byte-aligned rows leave through shared memory and TMA stores; C is described as
+  // [batch][m][n / n_fold][n_fold] so that the folded (upsampling) layout is the same code path
+  CUtensorMap tc = ta;
+  p.c_tma = 0;
+  if (a->c_dtype == 0 && a->ldc % 8 == 0 && a->c_batch_stride % 8 == 0 && aligned16(a->c)) {
+    const uint64_t nf = a->n_fold > 0 ? (uint64_t)a->n_fold : (uint64_t)a->n;
+    const uint64_t fold_rows = (uint64_t)a->n / nf;
+    const uint64_t row_bytes = (uint64_t)a->ldc * 2;
+    const uint64_t bs = a->batch > 1 ? (uint64_t)a->c_batch_stride * 2 : row_bytes * fold_rows * (uint64_t)a->m;
+    const uint64_t dims[4] = {nf, fold_rows, (uint64_t)a->m, (uint64_t)a->batch};
+    const uint64_t strides[3] = {row_bytes, row_bytes * fold_rows, bs};
+    const uint32_t box[4] = {32, 1, 32, 1};
+    int rc = make_tmap_bf16_sw64(&tc, a->c, 4, dims, strides, box);
+    if (rc) return rc;
+    p.c_tma = 1;
+  }
+  if (bn == 256) return launch<256, false, 0>(ta, tb, tc, p, stream);
+  return launch<128, false, 0>(ta, tb, tc, p, stream);
 }
 
 template <int CS>
@@ -870,8 +918,8 @@ static int run_tn(const srnn_gemm_args* a, GemmParams& p, cudaStream_t stream) {
     int rc = make_tmap_bf16(&tb, a->b, 3, dims, strides, box, true);
     if (rc) return rc;
   }
-  if (bn == 256) return launch<256, true, 2>(ta, tb, p, stream);
-  return launch<128, true, 2>(ta, tb, p, stream);
+  if (bn == 256) return launch<256, true, 2>(ta, tb, ta, p, stream);
+  return launch<128, true, 2>(ta, tb, ta, p, stream);
 }
 
 }  // namespace srnn
