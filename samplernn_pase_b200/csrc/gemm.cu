@@ -235,44 +235,76 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const Work wk = decode_work<TN>(p, w);
       if (wk.kb_end <= wk.kb_begin) continue;
+      const int j = wk.mt * BM + q * 32 + lane;   // row within the batch (NT) / row of C (TN)
+      const bool row_ok = j < p.m;
+      // Everything the epilogue needs from global memory is requested BEFORE waiting for the accumulator, so its
+      // latency hides behind the MMAs: the bias of this warp's columns (one register per chunk, lane i = column i,
+      // broadcast by shuffles later) and the aux row segment of the first chunk.  (Loading them per chunk after the
+      // TMEM read cost ~1 500 cycles of exposed latency per chunk and made every K <= 1024 GEMM epilogue-bound.)
+      float breg[CHUNKS_PER_WARP];
+      uint4 ax[4];
+      bool ax_ok = false;
+      const __nv_bfloat16* aux_row = nullptr;
+      auto aux_prefetch = [&](int c) {
+        const int n0c = wk.nt * BN + c * 32;
+        ax_ok = false;
+        if (EPI == 0 && p.aux_mode && row_ok && n0c + 32 <= p.n) {
+          const __nv_bfloat16* ap = aux_row + n0c;
+          if ((reinterpret_cast<uintptr_t>(ap) & 15) == 0) {
+            ax_ok = true;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ax[i] = __ldg(reinterpret_cast<const uint4*>(ap) + i);
+          }
+        }
+      };
+      if constexpr (EPI == 0) {
+#pragma unroll
+        for (int c = 0; c < CHUNKS_PER_WARP; ++c) {
+          const int col = wk.nt * BN + (c_begin + c) * 32 + lane;
+          breg[c] = (p.bias && col < p.n) ? __ldg(p.bias + col) : 0.f;
+        }
+        if (p.aux_mode)
+          aux_row = p.aux + wk.b * p.aux_batch_stride + static_cast<long long>(j / p.aux_row_div) * p.ldaux;
+        aux_prefetch(c_begin);
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      const int j = wk.mt * BM + q * 32 + lane;   // row within the batch (NT) / row of C (TN)
-      const bool row_ok = j < p.m;
 
       if constexpr (EPI == 0) {
         const int fold_rows = p.n_fold > 0 ? p.n / p.n_fold : 1;
-        for (int c = c_begin; c < c_end; ++c) {
+#pragma unroll
+        for (int ci = 0; ci < CHUNKS_PER_WARP; ++ci) {
+          const int c = c_begin + ci;
           const int n0 = wk.nt * BN + c * 32;
           if (n0 >= p.n) break;
           uint32_t v[32];
           tmem_ld32(t_addr + c * 32, v);
+          // this chunk's aux values were requested one chunk ago; request the next chunk's before waiting for TMEM
+          uint4 cur[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cur[i] = ax[i];
+          const bool cur_ok = ax_ok;
+          if (c + 1 < c_end) aux_prefetch(c + 1);
           tmem_ld_wait();
-          if (!row_ok && !p.c_tma) continue;           // (the TMA store needs the whole warp; it clips rows >= m itself)
           const bool full_chunk = n0 + 32 <= p.n;
           float f[32];
+          const float bv = breg[ci];                   // lane i holds the bias of column n0 + i
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (p.bias) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (full_chunk || n0 + i < p.n) f[i] += __ldg(p.bias + n0 + i);
-          }
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + __shfl_sync(0xffffffffu, bv, i);
           if (p.aux_mode && row_ok) {
-            const __nv_bfloat16* ap = p.aux + wk.b * p.aux_batch_stride + static_cast<long long>(j / p.aux_row_div) * p.ldaux + n0;
-            const bool vec = full_chunk && ((reinterpret_cast<uintptr_t>(ap) & 15) == 0);
             float a[32];
-            if (vec) {
+            if (cur_ok) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(ap) + i);
+                const uint4 u = cur[i];
                 a[i * 8 + 0] = bf16_lo(u.x); a[i * 8 + 1] = bf16_hi(u.x);
                 a[i * 8 + 2] = bf16_lo(u.y); a[i * 8 + 3] = bf16_hi(u.y);
                 a[i * 8 + 4] = bf16_lo(u.z); a[i * 8 + 5] = bf16_hi(u.z);
                 a[i * 8 + 6] = bf16_lo(u.w); a[i * 8 + 7] = bf16_hi(u.w);
               }
             } else {
+              const __nv_bfloat16* ap = aux_row + n0;
 #pragma unroll
               for (int i = 0; i < 32; ++i) a[i] = (n0 + i < p.n) ? __bfloat162float(ap[i]) : 0.f;
             }
@@ -314,6 +346,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             stg_buf ^= 1;
             continue;
           }
+          if (!row_ok) continue;
           long long out_row = j;
           int out_col = n0;
           if (p.n_fold > 0) {
