@@ -29,7 +29,7 @@ extern "C" {
 #define SRNN_ERR_ARG (-1)     /* bad argument (shape, alignment, null pointer) */
 #define SRNN_ERR_DEVICE (-2)  /* not an sm_100 device / driver entry point missing */
 
-#define SRNN_ABI_VERSION 1
+#define SRNN_ABI_VERSION 2
 
 typedef void* srnn_stream_t; /* cudaStream_t */
 
@@ -136,6 +136,9 @@ typedef struct srnn_gemm_args {
                                  over groups of d rows, e.g. the conditioning of the d samples of one frame) */
   int32_t max_ctas;           /* 0: one persistent CTA per SM; n > 0: at most n CTAs (leaves SMs to a kernel that
                                  runs concurrently on another stream, e.g. the persistent recurrence) */
+  float* colsum;              /* NT only, or NULL: colsum[j] += sum over all rows and batches of the fp32 epilogue
+                                 result C[., j] (a bias gradient without a second pass over C; model.py:201 etc.
+                                 backward); the caller zeroes it */
 } srnn_gemm_args;
 
 int srnn_gemm_bf16(const srnn_gemm_args* args, srnn_stream_t stream);

@@ -40,6 +40,7 @@ struct GemmParams {
   long long ldaux, aux_batch_stride;
   int aux_mode, relu, aux_row_div, max_ctas;
   int c_tma;                       // bf16 C tiles leave through shared memory + TMA stores (tma_c is valid)
+  float* colsum;                   // NT: column sums of the fp32 epilogue result, accumulated with atomics (nullable)
   // schedule
   int tiles_m, tiles_n, kb_per_batch, splits, kb_per_split, total_kb, total_work;
   // NLL epilogue
@@ -96,7 +97,9 @@ __device__ __forceinline__ Work decode_work(const GemmParams& p, int w) {
   return wk;
 }
 
-// EPI: 0 = bias / aux / relu / store, 1 = log-softmax + NLL family, 2 = fp32 atomic accumulate
+// EPI: 0 = bias / aux / relu / store, 1 = log-softmax + NLL family, 2 = fp32 atomic accumulate,
+//      3 = as 0 plus the column sums of the result (fused bias gradient; its own instantiation so that the plain
+//          store epilogue carries neither its registers nor its code)
 template <int BN, bool TN, int EPI>
 __global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -106,6 +109,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   constexpr uint32_t TMEM_COLS = 2 * BN;
   constexpr uint32_t IDESC = idesc_bf16(BM, BN, TN, TN);
   constexpr int THREADS = gemm_threads<EPI>();
+  constexpr bool STORE = EPI == 0 || EPI == 3;
+  constexpr bool CSUM = EPI == 3;
   constexpr int EPI_WARPS = THREADS / 32 - 4;
   constexpr int CHUNKS_PER_WARP = (BN / 32) / (EPI_WARPS / 4);
 
@@ -124,7 +129,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
-    if (EPI == 0 && p.c_tma) tma_prefetch_desc(&tma_c);
+    if (STORE && p.c_tma) tma_prefetch_desc(&tma_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) {
@@ -232,6 +237,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     int acc = 0;
     uint32_t acc_phase = 0;
     int stg_buf = 0;
+    // fused bias gradient (p.colsum): lane i of this warp keeps the running sum of column i of each of its chunks over
+    // the CTA's tiles that share a column tile; flushed with one coalesced atomic per chunk when the column tile changes
+    float csum[CHUNKS_PER_WARP];
+    int cs_nt = -1;
+#pragma unroll
+    for (int i = 0; i < CHUNKS_PER_WARP; ++i) csum[i] = 0.f;
+    auto colsum_flush = [&]() {
+      if (cs_nt < 0) return;
+#pragma unroll
+      for (int ci = 0; ci < CHUNKS_PER_WARP; ++ci) {
+        const int col = cs_nt * BN + (c_begin + ci) * 32 + lane;
+        if (col < p.n) atomicAdd(p.colsum + col, csum[ci]);
+        csum[ci] = 0.f;
+      }
+    };
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const Work wk = decode_work<TN>(p, w);
       if (wk.kb_end <= wk.kb_begin) continue;
@@ -248,7 +268,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       auto aux_prefetch = [&](int c) {
         const int n0c = wk.nt * BN + c * 32;
         ax_ok = false;
-        if (EPI == 0 && p.aux_mode && row_ok && n0c + 32 <= p.n) {
+        if (STORE && p.aux_mode && row_ok && n0c + 32 <= p.n) {
           const __nv_bfloat16* ap = aux_row + n0c;
           if ((reinterpret_cast<uintptr_t>(ap) & 15) == 0) {
             ax_ok = true;
@@ -257,7 +277,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           }
         }
       };
-      if constexpr (EPI == 0) {
+      if constexpr (STORE) {
+        if constexpr (CSUM) {
+          if (wk.nt != cs_nt) {
+            colsum_flush();
+            cs_nt = wk.nt;
+          }
+        }
 #pragma unroll
         for (int c = 0; c < CHUNKS_PER_WARP; ++c) {
           const int col = wk.nt * BN + (c_begin + c) * 32 + lane;
@@ -271,7 +297,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
-      if constexpr (EPI == 0) {
+      if constexpr (STORE) {
         const int fold_rows = p.n_fold > 0 ? p.n / p.n_fold : 1;
 #pragma unroll
         for (int ci = 0; ci < CHUNKS_PER_WARP; ++ci) {
@@ -319,6 +345,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if constexpr (CSUM) {
+            // transposing reduction over the warp's 32 rows: at every step a lane keeps the half of its values whose
+            // column bit matches its lane bit and adds the partner's copy of them; 31 shuffles leave the sum of
+            // column i in lane i
+            float r[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = row_ok ? f[i] : 0.f;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool upper = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < off; ++i) {
+                const float send = upper ? r[i] : r[i + off];
+                const float keep = upper ? r[i + off] : r[i];
+                r[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            csum[ci] += r[0];
           }
           if (p.c_tma) {
             // bf16 tile chunk -> 64-byte-swizzled staging tile (lane = row) -> one TMA store.  Per-lane global stores
@@ -501,7 +546,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (EPI == 0 && p.c_tma && lane == 0) tma_store_wait_read<0>();   // staging tiles stay valid until read
+    if constexpr (CSUM) colsum_flush();
+    if (STORE && p.c_tma && lane == 0) tma_store_wait_read<0>();   // staging tiles stay valid until read
   }
 
   tc_fence_before();
@@ -825,6 +871,10 @@ static int run_nt(const srnn_gemm_args* a, GemmParams& p, bool nll, cudaStream_t
     if (rc) return rc;
     p.c_tma = 1;
   }
+  if (p.colsum) {
+    if (bn == 256) return launch<256, false, 3>(ta, tb, tc, p, stream);
+    return launch<128, false, 3>(ta, tb, tc, p, stream);
+  }
   if (bn == 256) return launch<256, false, 0>(ta, tb, tc, p, stream);
   return launch<128, false, 0>(ta, tb, tc, p, stream);
 }
@@ -975,14 +1025,16 @@ extern "C" int srnn_gemm_bf16(const srnn_gemm_args* a, srnn_stream_t stream_) {
   p.aux_mode = a->aux ? a->aux_mode : 0; p.relu = a->relu;
   p.aux_row_div = a->aux_row_div > 0 ? a->aux_row_div : 1;
   p.max_ctas = a->max_ctas;
+  p.colsum = a->op == 0 ? a->colsum : nullptr;
   if (a->op == 0) {
     SRNN_CHECK_ARG(a->n_fold == 0 || (a->n % a->n_fold == 0 && a->n_fold % 32 == 0 && !a->aux),
                    "gemm NT: n_fold must divide n, be a multiple of 32, and exclude aux");
-    if (a->m <= 512 && a->batch == 1 && a->n_fold == 0 && p.aux_mode != 2 && a->max_ctas == 0)
+    if (a->m <= 512 && a->batch == 1 && a->n_fold == 0 && p.aux_mode != 2 && a->max_ctas == 0 && !a->colsum)
       return run_nt_small(a, p, stream);
     return run_nt(a, p, false, stream);
   }
   SRNN_CHECK_ARG(a->op == 1, "gemm: op must be 0 (NT) or 1 (TN)");
+  SRNN_CHECK_ARG(!a->colsum, "gemm TN: colsum is an NT epilogue option");
   return run_tn(a, p, stream);
 }
 

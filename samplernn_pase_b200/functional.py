@@ -233,10 +233,10 @@ class FrameTierFn(torch.autograd.Function):
             rnn_grads[4 * i: 4 * i + 4] = [dwih, dwhh, ops.colsum(dgi, b * t, ng * h, ng * h),
                                            ops.colsum(dgh, b * t, ng * h, ng * h)]
             dx = _empty(b * t, h, device=dev)
-            ops.gemm_nt(dgi, wih_t, dx, b * t, h, ng * h, ng * h, ng * h, h)
+            d_bias = _zeros(h, dtype=F32, device=dev) if i == 0 else None   # layer 0: dx is du, its column sums the bias gradient
+            ops.gemm_nt(dgi, wih_t, dx, b * t, h, ng * h, ng * h, ng * h, h, colsum=d_bias)
             dh_out = dx
         du = dh_out                       # (B*T, H): gradient of u, hence also of `upper`
-        d_bias = ops.colsum(du, b * t, h, h)
         dwcat = _zeros(h, kp, device=dev)
         ops.gemm_tn(du, ain, dwcat, h, kp, b * t, h, kp, kp)
         d_xv, d_xg = ops.weight_prep_bwd(dwcat, (kp, 1, 0), xv, xg, inv_x, (h, fs, 1))
@@ -371,16 +371,16 @@ class SampleLevelFn(torch.autograd.Function):
         ops.gemm_tn(dlog, h2, dw3, q, h, m, q, h, h)
         d_w3v, d_w3g = ops.weight_prep_bwd(dw3, (h, 1, 0), w3v, w3g, inv_3, (q, h, 1))
         dh2 = _empty(m, h, device=dev)
-        ops.gemm_nt(dlog, w3_t, dh2, m, h, q, q, q, h, aux=h2, ldaux=h, aux_mode=2)
+        d_b2 = _zeros(h, dtype=F32, device=dev)                 # bias gradient = column sums, fused into the GEMM epilogue
+        ops.gemm_nt(dlog, w3_t, dh2, m, h, q, q, q, h, aux=h2, ldaux=h, aux_mode=2, colsum=d_b2)
         # comb_layer_expand
-        d_b2 = ops.colsum(dh2, m, h, h)
         dw2 = _zeros(h, h, device=dev)
         ops.gemm_tn(dh2, h1, dw2, h, h, m, h, h, h)
         d_w2v, d_w2g = ops.weight_prep_bwd(dw2, (h, 1, 0), w2v, w2g, inv_2, (h, h, 1))
         dh1 = _empty(m, h, device=dev)
-        ops.gemm_nt(dh2, w2_t, dh1, m, h, h, h, h, h, aux=h1, ldaux=h, aux_mode=2)
+        d_cbias = _zeros(h, dtype=F32, device=dev)
+        ops.gemm_nt(dh2, w2_t, dh1, m, h, h, h, h, h, aux=h1, ldaux=h, aux_mode=2, colsum=d_cbias)
         # comb_layer: [e | upper] blocks at sample rate, conditioning block at frame rate
-        d_cbias = ops.colsum(dh1, m, h, h)
         d_cw = _zeros(h, 3 * h, device=dev)
         ops.gemm_tn(dh1, cat, d_cw, h, h, m, h, 2 * h, 3 * h)                              # d W_e
         ops.gemm_tn(dh1, cat[:, h:], d_cw[:, 2 * h:], h, h, m, h, 2 * h, 3 * h)           # d W_u

@@ -232,7 +232,7 @@ def repeat_rows_bwd(dout, rows, cols, ld_dout, rep, din, ld_din):
 # GEMMs
 # ----------------------------------------------------------------------------------------------
 def gemm_nt(a, b, c, m, n, k, lda, ldb, ldc, batch=1, a_bs=0, c_bs=0, bias=None, aux=None, ldaux=0, aux_bs=0,
-            aux_mode=0, relu=False, n_fold=0, aux_row_div=1):
+            aux_mode=0, relu=False, n_fold=0, aux_row_div=1, colsum=None):
     """C_i[m,n] = epi(A_i[m,k] . B[n,k]^T); c.dtype selects bf16 / fp32 output."""
     _need(a, BF16, 'gemm A')
     _need(b, BF16, 'gemm B')
@@ -249,6 +249,7 @@ def gemm_nt(a, b, c, m, n, k, lda, ldb, ldc, batch=1, a_bs=0, c_bs=0, bias=None,
     g.relu = int(relu)
     g.aux_row_div = aux_row_div
     g.max_ctas = gemm_max_ctas
+    g.colsum = colsum.data_ptr() if colsum is not None else None
     _lib.profile_note = f'NT m={m}x{batch} n={n} k={k}'
     call('srnn_gemm_bf16', C.byref(g), stream())
     _count()

@@ -150,6 +150,28 @@ def test_gemm_nt_small_m_cluster_split_k(ops, m, n, k):
     assert rel_l2(c2, _gemm_ref(a, b)) < 1e-5 and torch.equal(c2, c3)
 
 
+@pytest.mark.parametrize('m,n,k,batch', [(5000, 1024, 256, 1), (777, 200, 64, 3), (148 * 128 + 5, 512, 128, 1)])
+def test_gemm_nt_fused_column_sums(ops, m, n, k, batch):
+    """colsum: the bias gradient (column sums over all rows and batches of the fp32 epilogue result) comes out of the
+    same launch; rows beyond m and columns beyond n contribute nothing."""
+    a = rnd(batch, m, k).to(BF16)
+    b = rnd(n, k, seed=1).to(BF16)
+    aux = rnd(batch, m, n, seed=3).to(BF16)
+    c = torch.empty(batch, m, n, dtype=BF16, device='cuda')
+    cs = torch.zeros(n, dtype=F32, device='cuda')
+    ops.gemm_nt(a, b, c, m, n, k, k, k, n, batch=batch, a_bs=m * k, c_bs=m * n, aux=aux, ldaux=n, aux_bs=m * n, aux_mode=2,
+                colsum=cs)
+    ref = (a.float() @ b.float().t()) * (aux.float() > 0)
+    assert rel_l2(c, ref) < 4e-3
+    assert rel_l2(cs, ref.sum(dim=(0, 1))) < 1e-4, rel_l2(cs, ref.sum(dim=(0, 1)))
+    cs2 = torch.zeros(n, dtype=F32, device='cuda')                 # plain epilogue, fp32 output, bias
+    bias = rnd(n, seed=5)
+    c32 = torch.empty(batch, m, n, dtype=F32, device='cuda')
+    ops.gemm_nt(a, b, c32, m, n, k, k, k, n, batch=batch, a_bs=m * k, c_bs=m * n, bias=bias, colsum=cs2)
+    ref2 = a.float() @ b.float().t() + bias
+    assert rel_l2(cs2, ref2.sum(dim=(0, 1))) < 1e-4
+
+
 def test_gemm_nt_batched_overlapping_rows_and_strided_c(ops):
     """The sample-level contraction: A rows are overlapping windows of a (B, W, Q) one-hot buffer."""
     bsz, rf, r0, q, h = 3, 200, 4, 256, 64
