@@ -171,7 +171,7 @@ int srnn_gemm_nll(const srnn_nll_args* args, srnn_stream_t stream);
  * One cooperative launch runs all `steps` timesteps; W_hh stays resident in shared memory.
  * ------------------------------------------------------------------------------------------- */
 typedef struct srnn_gru_args {
-  int32_t batch, steps, hidden;   /* batch <= 128, hidden % 8 == 0 */
+  int32_t batch, steps, hidden;   /* batch <= 64 per launch (run larger batches as slot groups), hidden % 8 == 0 */
   int32_t ext_batch;     /* rows per time slot of the TIME-major buffers (>= batch; a launch may cover a
                             sub-range of a larger batch: pass pointers offset to its first row) */
   const void* gi;        /* bf16 [batch*steps, 3H] = W_ih u_t + b_ih, batch-major: row (b,t) = b*steps + t */
@@ -189,10 +189,11 @@ typedef struct srnn_gru_args {
   void* dgh;             /* bf16 [steps, ext_batch, 3H] TIME-major, out (also the per-step exchange buffer) */
   float* dh0;            /* fp32 [batch, H] out: dL/dh_init */
   uint32_t* sync;        /* >= 4*(hidden/8) bytes (one flag per CTA), zeroed by the caller before every launch */
-  int32_t debug_flags;   /* must be 0.  Timing experiments only (results are WRONG when set):
-                            1 = do not wait on the grid counter, 2 = skip TMA loads and MMAs,
-                            4 = skip the per-step global loads/stores of the epilogue;
-                            16 = (results stay correct) add a gpu-scope acquire fence after the grid wait */
+  int32_t debug_flags;   /* must be 0.  Timing experiments only (results are WRONG with 1 or 4):
+                            1 = do not wait on the grid counter, 4 = skip the per-step global loads/stores of the
+                            epilogue; results stay correct with 16 = add a gpu-scope acquire fence after the grid
+                            wait, 32 = one TMA box per K block, 64 = two MMA-issuing warps, 128 = debug_ts receives the
+                            global timer of every CTA at timestep 24, bits 8.. = force a cluster size */
   uint64_t* debug_ts;    /* NULL, or [256][8] clock64 stamps of CTA 0's pipeline events (profiling aid) */
   /* LSTM extension (cell = 1; no reference counterpart, torch.nn.LSTM semantics, gates i,f,g,o): every
    * "3H" above becomes 4H, `gates` is [batch*steps, 5H] (i, f, g, o, c_t). */
@@ -202,6 +203,9 @@ typedef struct srnn_gru_args {
   float* dc0;            /* LSTM bwd out: dL/dc_init */
   int32_t units_per_cta; /* 0 or 8: H/8 CTAs (fastest step); 16: H/16 CTAs, leaving SMs free for kernels that run
                             concurrently on another stream (falls back to 8 if H % 32 != 0) */
+  float* db_ih;          /* bwd, nullable: fp32 [3H] (4H LSTM); db_ih[j] += sum over rows and timesteps of dgi[., j]
+                            (the gradient of b_ih) - accumulated in registers during the loop, no extra pass */
+  float* db_hh;          /* bwd, nullable: same for dgh (the gradient of b_hh) */
 } srnn_gru_args;
 
 int srnn_gru_forward(const srnn_gru_args* args, srnn_stream_t stream);

@@ -58,6 +58,8 @@ struct GruParams {
   float* c_state;                  // LSTM: fp32 [batch, H] cell state, in = c_init, out = c_T
   const float* c_init;             // LSTM backward: the cell state the forward started from
   float* dc0;                      // LSTM backward: dL/dc_init
+  float* db_ih;                    // backward (nullable): += column sums of dgi
+  float* db_hh;                    // backward (nullable): += column sums of dgh
   uint32_t* sync;
   int flags;
   unsigned long long* ts;          // debug timestamps [256][8] of CTA 0 (nullable)
@@ -420,8 +422,11 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
     } else if constexpr (BWD && LSTM) {
       // ---------------- LSTM backward ----------------
       float carry_c[U];
+      float sb[4 * U];                                 // bias gradients: running sums of the 4 gate gradients of this row
 #pragma unroll
       for (int i = 0; i < U; ++i) carry_c[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4 * U; ++i) sb[i] = 0.f;
       for (int s = 0; s <= T; ++s) {
         const int t = T - 1 - s;
         const long long rt = static_cast<long long>(row) * T + t;
@@ -485,6 +490,28 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           store_units<U>(gip + 2 * H, pg);
           store_units<U>(gip + 3 * H, po);
         }
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            sb[i] += pi[i]; sb[U + i] += pf[i]; sb[2 * U + i] += pg[i]; sb[3 * U + i] += po[i];
+          }
+        }
+      }
+      if (p.db_ih || p.db_hh) {                                   // both biases see the same gate gradients
+        float* sred = reinterpret_cast<float*>(hbuf);
+        if (lane_ok) {
+#pragma unroll
+          for (int i = 0; i < 4 * U; ++i) sred[i * GRU_M + row] = row_ok ? sb[i] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int v = threadIdx.x - 64;
+        if (v < 4 * U) {
+          float acc = 0.f;
+          for (int r = 0; r < GRU_M; ++r) acc += sred[v * GRU_M + r];
+          const int g = v / U, i = v % U;
+          if (p.db_ih) p.db_ih[g * H + u0 + i] += acc;
+          if (p.db_hh) p.db_hh[g * H + u0 + i] += acc;
+        }
       }
     } else if constexpr (!BWD) {
       float h[U], bhr[U], bhz[U], bhn[U];
@@ -540,8 +567,11 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       }
     } else {
       float carry[U];
+      float sb[4 * U];                                 // bias gradients: running sums of gr, gz, gn, ghn of this row
 #pragma unroll
       for (int i = 0; i < U; ++i) carry[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4 * U; ++i) sb[i] = 0.f;
       for (int s = 0; s <= T; ++s) {
         const int t = T - 1 - s;
         const long long rt = static_cast<long long>(row) * T + t;
@@ -598,6 +628,29 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           store_units<U>(gip, gr);
           store_units<U>(gip + H, gz);
           store_units<U>(gip + 2 * H, gn);
+        }
+        if (row_ok) {                                           // (rows beyond the batch hold garbage)
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            sb[i] += gr[i]; sb[U + i] += gz[i]; sb[2 * U + i] += gn[i]; sb[3 * U + i] += ghn[i];
+          }
+        }
+      }
+      // bias gradients: sum the per-row sums over the batch rows through shared memory (the operand buffer is free now)
+      if (p.db_ih || p.db_hh) {
+        float* sred = reinterpret_cast<float*>(hbuf);            // [4U][64 rows]
+        if (lane_ok) {
+#pragma unroll
+          for (int i = 0; i < 4 * U; ++i) sred[i * GRU_M + row] = row_ok ? sb[i] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int v = threadIdx.x - 64;                          // epilogue threads 0..127
+        if (v < 4 * U) {
+          float acc = 0.f;
+          for (int r = 0; r < GRU_M; ++r) acc += sred[v * GRU_M + r];
+          const int g = v / U, i = v % U;                        // 0 r, 1 z, 2 n (input side), 3 n (hidden side)
+          if (g < 3 && p.db_ih) p.db_ih[g * H + u0 + i] += acc;
+          if (g != 2 && p.db_hh) p.db_hh[(g == 3 ? 2 : g) * H + u0 + i] += acc;
         }
       }
     }
@@ -726,6 +779,8 @@ static int launch_gru_mw(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   p.c_state = a->c_state;
   p.c_init = a->c_init;
   p.dc0 = a->dc0;
+  p.db_ih = a->db_ih;
+  p.db_hh = a->db_hh;
   p.sync = a->sync;
   p.flags = a->debug_flags;
   p.ts = reinterpret_cast<unsigned long long*>(a->debug_ts);

@@ -219,19 +219,20 @@ class FrameTierFn(torch.autograd.Function):
             dgi = _empty(b * t, ng * h, device=dev)            # batch-major
             dgh = _empty(t * b, ng * h, device=dev)            # time-major (exchange buffer)
             dh0_i = _empty(b, h, dtype=F32, device=dev)
+            db_ih = _zeros(ng * h, device=dev)                 # bias gradients come out of the recurrent kernel itself
+            db_hh = _zeros(ng * h, device=dev)
             if lstm:
                 dc0_i = _empty(b, h, dtype=F32, device=dev)
-                ops.lstm_backward(whh_t, h_ext, gates, c0_i, dh_out, dgi, dgh, dh0_i, dc0_i, b, t, h)
+                ops.lstm_backward(whh_t, h_ext, gates, c0_i, dh_out, dgi, dgh, dh0_i, dc0_i, b, t, h, db_ih, db_hh)
                 dc0[i] = dc0_i
             else:
-                ops.gru_backward(whh_t, h_ext, gates, dh_out, dgi, dgh, dh0_i, b, t, h)
+                ops.gru_backward(whh_t, h_ext, gates, dh_out, dgi, dgh, dh0_i, b, t, h, db_ih, db_hh)
             dh0[i] = dh0_i
             dwhh = _zeros(ng * h, h, device=dev)               # both operands time-major: rows (t, b)
             ops.gemm_tn(dgh, h_ext, dwhh, ng * h, h, t * b, ng * h, h, h)
             dwih = _zeros(ng * h, h, device=dev)
             ops.gemm_tn(dgi, x_l, dwih, ng * h, h, b * t, ng * h, h, h)
-            rnn_grads[4 * i: 4 * i + 4] = [dwih, dwhh, ops.colsum(dgi, b * t, ng * h, ng * h),
-                                           ops.colsum(dgh, b * t, ng * h, ng * h)]
+            rnn_grads[4 * i: 4 * i + 4] = [dwih, dwhh, db_ih, db_hh]
             dx = _empty(b * t, h, device=dev)
             d_bias = _zeros(h, dtype=F32, device=dev) if i == 0 else None   # layer 0: dx is du, its column sums the bias gradient
             ops.gemm_nt(dgi, wih_t, dx, b * t, h, ng * h, ng * h, ng * h, h, colsum=d_bias)

@@ -339,12 +339,13 @@ def gru_forward(gi, w_hh, b_hh, h_ext, hall, h_state, gates, batch, steps, hidde
               h_ext=(h_ext, h), hall=(hall, steps * h), h_state=(h_state, h), gates=(gates, steps * 4 * h))
 
 
-def gru_backward(w_hh_t, h_ext, gates, dh_out, dgi, dgh, dh0, batch, steps, hidden):
-    """dgh: bf16 [steps, batch, 3H] time-major; dgi: bf16 [batch*steps, 3H] batch-major."""
+def gru_backward(w_hh_t, h_ext, gates, dh_out, dgi, dgh, dh0, batch, steps, hidden, db_ih=None, db_hh=None):
+    """dgh: bf16 [steps, batch, 3H] time-major; dgi: bf16 [batch*steps, 3H] batch-major; db_ih / db_hh: optional fp32
+    [3H] bias gradients, ACCUMULATED into (the caller zeroes them)."""
     h = hidden
     _gru_call('srnn_gru_backward', batch, steps, h, w_hh=(w_hh_t, 0), h_ext=(h_ext, h),
               gates=(gates, steps * 4 * h), dh_out=(dh_out, steps * h), dgi=(dgi, steps * 3 * h),
-              dgh=(dgh, 3 * h), dh0=(dh0, h))
+              dgh=(dgh, 3 * h), dh0=(dh0, h), db_ih=(db_ih, 0), db_hh=(db_hh, 0))
 
 
 def lstm_forward(gi, w_hh, b_hh, h_ext, hall, h_state, c_state, gates, batch, steps, hidden):
@@ -355,12 +356,12 @@ def lstm_forward(gi, w_hh, b_hh, h_ext, hall, h_state, c_state, gates, batch, st
               gates=(gates, steps * 5 * h))
 
 
-def lstm_backward(w_hh_t, h_ext, gates, c_init, dh_out, dgi, dgh, dh0, dc0, batch, steps, hidden):
+def lstm_backward(w_hh_t, h_ext, gates, c_init, dh_out, dgi, dgh, dh0, dc0, batch, steps, hidden, db_ih=None, db_hh=None):
     """w_hh_t [H, 4H]; dgh [steps, batch, 4H] time-major; dgi [batch*steps, 4H] batch-major."""
     h = hidden
     _gru_call('srnn_gru_backward', batch, steps, h, cell=1, w_hh=(w_hh_t, 0), h_ext=(h_ext, h),
               gates=(gates, steps * 5 * h), c_init=(c_init, h), dh_out=(dh_out, steps * h),
-              dgi=(dgi, steps * 4 * h), dgh=(dgh, 4 * h), dh0=(dh0, h), dc0=(dc0, h))
+              dgi=(dgi, steps * 4 * h), dgh=(dgh, 4 * h), dh0=(dh0, h), dc0=(dc0, h), db_ih=(db_ih, 0), db_hh=(db_hh, 0))
 
 
 def state_select(carried, h0, use_carry, batch, hidden):

@@ -323,9 +323,14 @@ def test_gru_backward(ops, bsz, t, h):
     dgi = torch.empty(bsz * t, 3 * h, dtype=BF16, device='cuda')
     dgh = torch.empty(bsz * t, 3 * h, dtype=BF16, device='cuda')
     dh0 = torch.empty(bsz, h, dtype=F32, device='cuda')
-    ops.gru_backward(w_hh.t().contiguous(), h_ext, gates, dh_out.view(bsz * t, h), dgi, dgh, dh0, bsz, t, h)
+    db_ih = torch.full((3 * h,), 0.5, dtype=F32, device='cuda')       # accumulated INTO: start from a known value
+    db_hh = torch.zeros(3 * h, dtype=F32, device='cuda')
+    ops.gru_backward(w_hh.t().contiguous(), h_ext, gates, dh_out.view(bsz * t, h), dgi, dgh, dh0, bsz, t, h, db_ih, db_hh)
     assert rel_l2(dgi.view(bsz, t, 3 * h), gi_r.grad) < 3e-2, rel_l2(dgi.view(bsz, t, 3 * h), gi_r.grad)
     assert rel_l2(dh0, h0_r.grad) < 3e-2, rel_l2(dh0, h0_r.grad)
+    # fused bias gradients = column sums of the gate gradients the kernel wrote (fp32 sums of the unrounded values)
+    assert rel_l2(db_ih - 0.5, dgi.float().sum(0)) < 1e-2, rel_l2(db_ih - 0.5, dgi.float().sum(0))
+    assert rel_l2(db_hh, dgh.float().sum(0)) < 1e-2, rel_l2(db_hh, dgh.float().sum(0))
 
 
 def test_gru_grid_handshake_stress_bit_exact(ops):
