@@ -40,6 +40,7 @@ struct GemmParams {
   long long ldaux, aux_batch_stride;
   int aux_mode, relu, aux_row_div, max_ctas;
   int c_tma;                       // bf16 C tiles leave through shared memory + TMA stores (tma_c is valid)
+  int tn_4d;                       // TN: operands described as [batch][MN/64][k][64] - one TMA box per operand and K block
   float* colsum;                   // NT: column sums of the fp32 epilogue result, accumulated with atomics (nullable)
   // schedule
   int tiles_m, tiles_n, kb_per_batch, splits, kb_per_split, total_kb, total_work;
@@ -172,12 +173,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           } else {
             const int bi = kb / p.kb_per_batch;
             const int r0 = (kb - bi * p.kb_per_batch) * BK;
+            if (p.tn_4d) {                             // 2 TMA issues per K block instead of 6 (the producer thread
+              tma_load_4d(sa, &tma_a, &full[stage], 0, r0 + p.a_row_offset, wk.mt * (BM / 64), bi);   // was the limit)
+              tma_load_4d(sb, &tma_b, &full[stage], 0, r0 + p.b_row_offset, wk.nt * (BN / 64), bi);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_3d(sa + j * 8192, &tma_a, &full[stage], wk.mt * BM + j * 64, r0 + p.a_row_offset, bi);
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_3d(sa + j * 8192, &tma_a, &full[stage], wk.mt * BM + j * 64, r0 + p.a_row_offset, bi);
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_3d(sb + j * 8192, &tma_b, &full[stage], wk.nt * BN + j * 64, r0 + p.b_row_offset, bi);
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_3d(sb + j * 8192, &tma_b, &full[stage], wk.nt * BN + j * 64, r0 + p.b_row_offset, bi);
+            }
           }
           if (++stage == S) {
             stage = 0;
@@ -985,20 +991,42 @@ static int run_tn(const srnn_gemm_args* a, GemmParams& p, cudaStream_t stream) {
   p.splits = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.total_work = tiles * p.splits;
   CUtensorMap ta, tb;
+  // MN-major operands: smem wants [MN block of 64][k row][64 elements = 128 B].  When M and N are whole numbers of
+  // 64-element blocks the matrix is viewed as [batch][MN/64][k][64] (non-monotonic strides) and ONE box brings all
+  // blocks of a tile; otherwise one box per 64-element block.
+  p.tn_4d = (a->m % 64 == 0 && a->n % 64 == 0) ? 1 : 0;
   {
-    const uint64_t dims[3] = {(uint64_t)a->m, (uint64_t)(a->a_row_offset + a->k), (uint64_t)a->batch};
-    const uint64_t bs = a->batch > 1 ? (uint64_t)a->a_batch_stride : (uint64_t)a->lda * dims[1];
-    const uint64_t strides[2] = {(uint64_t)a->lda * 2, bs * 2};
-    const uint32_t box[3] = {64, 64, 1};
-    int rc = make_tmap_bf16(&ta, a->a, 3, dims, strides, box, true);
+    const uint64_t rows = (uint64_t)(a->a_row_offset + a->k);
+    const uint64_t bs = a->batch > 1 ? (uint64_t)a->a_batch_stride : (uint64_t)a->lda * rows;
+    int rc;
+    if (p.tn_4d) {
+      const uint64_t dims[4] = {64, rows, (uint64_t)a->m / 64, (uint64_t)a->batch};
+      const uint64_t strides[3] = {(uint64_t)a->lda * 2, 128, bs * 2};
+      const uint32_t box[4] = {64, 64, BM / 64, 1};
+      rc = make_tmap_bf16(&ta, a->a, 4, dims, strides, box, true);
+    } else {
+      const uint64_t dims[3] = {(uint64_t)a->m, rows, (uint64_t)a->batch};
+      const uint64_t strides[2] = {(uint64_t)a->lda * 2, bs * 2};
+      const uint32_t box[3] = {64, 64, 1};
+      rc = make_tmap_bf16(&ta, a->a, 3, dims, strides, box, true);
+    }
     if (rc) return rc;
   }
   {
-    const uint64_t dims[3] = {(uint64_t)a->n, (uint64_t)(a->b_row_offset + a->k), (uint64_t)a->batch};
-    const uint64_t bs = a->batch > 1 ? (uint64_t)a->b_batch_stride : (uint64_t)a->ldb * dims[1];
-    const uint64_t strides[2] = {(uint64_t)a->ldb * 2, bs * 2};
-    const uint32_t box[3] = {64, 64, 1};
-    int rc = make_tmap_bf16(&tb, a->b, 3, dims, strides, box, true);
+    const uint64_t rows = (uint64_t)(a->b_row_offset + a->k);
+    const uint64_t bs = a->batch > 1 ? (uint64_t)a->b_batch_stride : (uint64_t)a->ldb * rows;
+    int rc;
+    if (p.tn_4d) {
+      const uint64_t dims[4] = {64, rows, (uint64_t)a->n / 64, (uint64_t)a->batch};
+      const uint64_t strides[3] = {(uint64_t)a->ldb * 2, 128, bs * 2};
+      const uint32_t box[4] = {64, 64, (uint32_t)bn / 64, 1};
+      rc = make_tmap_bf16(&tb, a->b, 4, dims, strides, box, true);
+    } else {
+      const uint64_t dims[3] = {(uint64_t)a->n, rows, (uint64_t)a->batch};
+      const uint64_t strides[2] = {(uint64_t)a->ldb * 2, bs * 2};
+      const uint32_t box[3] = {64, 64, 1};
+      rc = make_tmap_bf16(&tb, a->b, 3, dims, strides, box, true);
+    }
     if (rc) return rc;
   }
   if (bn == 256) return launch<256, true, 2>(ta, tb, ta, p, stream);
