@@ -204,6 +204,17 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
   tc_fence_after();
   if (C > 1) cluster_sync_all();                     // every CTA's barriers exist before remote arrivals
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    // resident weight slice: static data, so under programmatic dependent launch (single-step launches of
+    // generation) it is fetched while the kernel that produces gi / h is still running
+    mbar_expect_tx(wfull, static_cast<uint32_t>(KBC * WBLOCK));
+    for (int kb = 0; kb < KBC; ++kb)
+      for (int g = 0; g < NG; ++g)
+        tma_load_2d(sw + kb * WBLOCK + g * UC * 128, &tma_w, wfull, (kb0 + kb) * 64,
+                    (BWD ? 0 : g * H) + cluster_id * UC);   // gate g rows of W_hh (fwd)
+  }
+  pdl_launch_dependents();
+  pdl_wait();                                        // no-ops for the cooperative multi-step launches of training
 
   if (warp == 0 || warp == 1 || warp >= 6) {
     // ------------------------------ TMA producer + MMA issuers ------------------------------
@@ -213,13 +224,6 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
     // own partial accumulator (summed by the epilogue).
     if (lane == 0) {
       const int mw = warp < 2 ? warp : warp - 4;
-      if (mw == 0) {
-        mbar_expect_tx(wfull, static_cast<uint32_t>(KBC * WBLOCK));
-        for (int kb = 0; kb < KBC; ++kb)
-          for (int g = 0; g < NG; ++g)
-            tma_load_2d(sw + kb * WBLOCK + g * UC * 128, &tma_w, wfull, (kb0 + kb) * 64,
-                        (BWD ? 0 : g * H) + cluster_id * UC);   // gate g rows of W_hh (fwd)
-      }
       const uint32_t bytes = static_cast<uint32_t>(KBC) * static_cast<uint32_t>(B) * 128u;
       mbar_wait(wfull, 0);
       const uint64_t a_base = smem_desc_sw128(smem_u32(hbuf), 16, 1024);
@@ -792,11 +796,19 @@ static int launch_gru_mw(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   cfg.blockDim = dim3(GRU_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[2];
+  cudaLaunchAttribute attrs[3];
   int na = 0;
-  attrs[na].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident: they spin on one another
-  attrs[na].val.cooperative = 1;
-  ++na;
+  if (T > 1 || C > 1 || (a->debug_flags & 2)) {        // (flag 2: experiment, force the cooperative launch)
+    attrs[na].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: they spin on one another
+    attrs[na].val.cooperative = 1;
+    ++na;
+  } else if (pdl_enabled()) {
+    // one timestep without clusters never waits on another CTA: a plain launch, whose set-up and weight fetch may
+    // overlap the previous kernel in the stream
+    attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   if (C > 1) {
     attrs[na].id = cudaLaunchAttributeClusterDimension;
     attrs[na].val.clusterDim.x = C;

@@ -203,7 +203,8 @@ def generate(model, utt_conds, info, return_logp=False, generator=None, use_grap
 
     The FS sample steps of one top-tier frame always run the same kernels on the same buffers (which tier
     fires and which upsampled vector is read depends only on ``xi % FS``), so after an eager first frame the
-    FS step programs are captured once as CUDA graphs and replayed for every later frame.  The uniforms of
+    FS step programs are captured once as ONE CUDA graph and replayed for every later frame (one replay per FS
+    samples keeps the host out of the way: a replay per sample was host-bound at ~40 us per step).  The uniforms of
     the draws are produced once per frame outside the graphs, so any ``generator`` works with them."""
     dev = utt_conds.device
     b, t, _ = utt_conds.shape
@@ -245,18 +246,13 @@ def _generate_frames(model, st, states, cstates, tiers, sw, lut, conds, y, t, b,
         if not _GREEDY:
             st.u_frame.uniform_(generator=generator)                         # the frame's FS x B uniforms (outside the graphs)
         if graphed and f == 1:                                               # frame 0 ran eagerly (lazy init done)
-            graphs = []
-            pool = None
             torch.cuda.synchronize()
-            for p in range(fs_top):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool):
+            graphs = torch.cuda.CUDAGraph()                                  # ONE graph = the FS step programs of a frame
+            with torch.cuda.graph(graphs):
+                for p in range(fs_top):
                     _frame_phase(p, tiers, sw, lut, st, states, cstates)
-                pool = g.pool()
-                graphs.append(g)
         if graphs is not None:
-            for g in graphs:
-                g.replay()
+            graphs.replay()
         else:
             for p in range(fs_top):
                 _frame_phase(p, tiers, sw, lut, st, states, cstates)

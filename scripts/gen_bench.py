@@ -16,8 +16,10 @@ ap.add_argument('--batch', type=int, default=256)
 ap.add_argument('--frames', type=int, default=8)
 ap.add_argument('--profile', action='store_true')
 ap.add_argument('--eager', action='store_true')
+ap.add_argument('--gru-flags', type=int, default=0)
 a = ap.parse_args()
 torch.manual_seed(0)
+ops.gru_debug_flags = a.gru_flags
 model = SampleRNNModel(**bench.model_kwargs(a.frames)).cuda()
 utt = torch.randn(a.batch, a.frames, 43).cuda()
 info = [{'speaker': {'index': i % 126}} for i in range(a.batch)]
