@@ -29,7 +29,7 @@ extern "C" {
 #define SRNN_ERR_ARG (-1)     /* bad argument (shape, alignment, null pointer) */
 #define SRNN_ERR_DEVICE (-2)  /* not an sm_100 device / driver entry point missing */
 
-#define SRNN_ABI_VERSION 2
+#define SRNN_ABI_VERSION 3
 
 typedef void* srnn_stream_t; /* cudaStream_t */
 
@@ -139,6 +139,9 @@ typedef struct srnn_gemm_args {
   float* colsum;              /* NT only, or NULL: colsum[j] += sum over all rows and batches of the fp32 epilogue
                                  result C[., j] (a bias gradient without a second pass over C; model.py:201 etc.
                                  backward); the caller zeroes it */
+  /* NT only, optional second A operand: A_i = [ A_i[m, k1] | A2_i[m, k - k1] ] concatenated along K without being
+   * materialised (comb_layer's input [one-hot windows | upper conditioning], model.py:196-199).  k1 % 64 == 0. */
+  const void* a2; int64_t lda2; int64_t a2_batch_stride; int32_t k1;
 } srnn_gemm_args;
 
 int srnn_gemm_bf16(const srnn_gemm_args* args, srnn_stream_t stream);

@@ -40,6 +40,7 @@ struct GemmParams {
   long long ldaux, aux_batch_stride;
   int aux_mode, relu, aux_row_div, max_ctas;
   int c_tma;                       // bf16 C tiles leave through shared memory + TMA stores (tma_c is valid)
+  int kb_a1;                       // NT: K blocks taken from the first A operand (the rest from tma_a2); total if single
   int tn_4d;                       // TN: operands described as [batch][MN/64][k][64] - one TMA box per operand and K block
   float* colsum;                   // NT: column sums of the fp32 epilogue result, accumulated with atomics (nullable)
   // schedule
@@ -104,7 +105,7 @@ __device__ __forceinline__ Work decode_work(const GemmParams& p, int w) {
 template <int BN, bool TN, int EPI>
 __global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const __grid_constant__ CUtensorMap tma_c, const GemmParams p) {
+            const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_a2, const GemmParams p) {
   using Cfg = SmemCfg<BN>;
   constexpr int S = Cfg::STAGES;
   constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -131,6 +132,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     if (STORE && p.c_tma) tma_prefetch_desc(&tma_c);
+    if (!TN && p.kb_a1 < p.kb_per_batch) tma_prefetch_desc(&tma_a2);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) {
@@ -168,7 +170,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_expect_tx(&full[stage], Cfg::STAGE);
           if (!TN) {
-            tma_load_3d(sa, &tma_a, &full[stage], kb * BK, wk.mt * BM, wk.b);
+            if (kb < p.kb_a1) {
+              tma_load_3d(sa, &tma_a, &full[stage], kb * BK, wk.mt * BM, wk.b);
+            } else {                                   // second A operand: columns [k1, k) of the concatenation
+              tma_load_3d(sa, &tma_a2, &full[stage], (kb - p.kb_a1) * BK, wk.mt * BM, wk.b);
+            }
             tma_load_2d(sb, &tma_b, &full[stage], kb * BK, wk.nt * BN);
           } else {
             const int bi = kb / p.kb_per_batch;
@@ -812,8 +818,8 @@ extern "C" int srnn_debug_small_ts(unsigned long long* host_out) {
 // host side
 // ---------------------------------------------------------------------------------------------
 template <int BN, bool TN, int EPI>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
-                  cudaStream_t stream) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& ta2,
+                  const GemmParams& p, cudaStream_t stream) {
   auto kern = gemm_kernel<BN, TN, EPI>;
   static bool configured = false;   // per instantiation
   if (!configured) {
@@ -824,7 +830,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   if (p.max_ctas > 0 && p.max_ctas < cap) cap = p.max_ctas;    // leave SMs to a concurrently running kernel
   int grid = p.total_work < cap ? p.total_work : cap;
   if (grid < 1) return SRNN_OK;
-  kern<<<grid, gemm_threads<EPI>(), SmemCfg<BN>::TOTAL, stream>>>(ta, tb, tc, p);
+  kern<<<grid, gemm_threads<EPI>(), SmemCfg<BN>::TOTAL, stream>>>(ta, tb, tc, ta2, p);
   SRNN_CUDA(cudaGetLastError());
   return SRNN_OK;
 }
@@ -844,13 +850,27 @@ static int run_nt(const srnn_gemm_args* a, GemmParams& p, bool nll, cudaStream_t
   p.kb_per_split = p.kb_per_batch;
   p.total_kb = p.kb_per_batch;
   p.total_work = a->batch * p.tiles_m * p.tiles_n;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, ta2;
+  const int k_a1 = a->a2 ? a->k1 : a->k;               // columns of the first A operand
+  p.kb_a1 = a->a2 ? a->k1 / BK : p.kb_per_batch;
   {
-    const uint64_t dims[3] = {(uint64_t)a->k, (uint64_t)a->m, (uint64_t)a->batch};
+    const uint64_t dims[3] = {(uint64_t)k_a1, (uint64_t)a->m, (uint64_t)a->batch};
     const uint64_t bs = a->batch > 1 ? (uint64_t)a->a_batch_stride : (uint64_t)a->lda * (uint64_t)a->m;
     const uint64_t strides[2] = {(uint64_t)a->lda * 2, bs * 2};
     const uint32_t box[3] = {BK, BM, 1};
     int rc = make_tmap_bf16(&ta, a->a, 3, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  ta2 = ta;
+  if (a->a2) {
+    SRNN_CHECK_ARG(a->k1 > 0 && a->k1 < a->k && a->k1 % BK == 0, "gemm NT: k1 must be a multiple of 64 inside (0, k)");
+    SRNN_CHECK_ARG(a->lda2 % 8 == 0 && a->a2_batch_stride % 8 == 0 && aligned16(a->a2),
+                   "gemm NT: second A operand must be 16-byte aligned with strides in multiples of 8 elements");
+    const uint64_t dims[3] = {(uint64_t)(a->k - a->k1), (uint64_t)a->m, (uint64_t)a->batch};
+    const uint64_t bs = a->batch > 1 ? (uint64_t)a->a2_batch_stride : (uint64_t)a->lda2 * (uint64_t)a->m;
+    const uint64_t strides[2] = {(uint64_t)a->lda2 * 2, bs * 2};
+    const uint32_t box[3] = {BK, BM, 1};
+    int rc = make_tmap_bf16(&ta2, a->a2, 3, dims, strides, box, true);
     if (rc) return rc;
   }
   {
@@ -860,7 +880,7 @@ static int run_nt(const srnn_gemm_args* a, GemmParams& p, bool nll, cudaStream_t
     int rc = make_tmap_bf16(&tb, a->b, 2, dims, strides, box, true);
     if (rc) return rc;
   }
-  if (nll) return launch<256, false, 1>(ta, tb, ta, p, stream);
+  if (nll) return launch<256, false, 1>(ta, tb, ta, ta, p, stream);
   // bf16 outputs with 16-byte-aligned rows leave through shared memory and TMA stores; C is described as
   // [batch][m][n / n_fold][n_fold] so that the folded (upsampling) layout is the same code path
   CUtensorMap tc = ta;
@@ -878,11 +898,11 @@ static int run_nt(const srnn_gemm_args* a, GemmParams& p, bool nll, cudaStream_t
     p.c_tma = 1;
   }
   if (p.colsum) {
-    if (bn == 256) return launch<256, false, 3>(ta, tb, tc, p, stream);
-    return launch<128, false, 3>(ta, tb, tc, p, stream);
+    if (bn == 256) return launch<256, false, 3>(ta, tb, tc, ta2, p, stream);
+    return launch<128, false, 3>(ta, tb, tc, ta2, p, stream);
   }
-  if (bn == 256) return launch<256, false, 0>(ta, tb, tc, p, stream);
-  return launch<128, false, 0>(ta, tb, tc, p, stream);
+  if (bn == 256) return launch<256, false, 0>(ta, tb, tc, ta2, p, stream);
+  return launch<128, false, 0>(ta, tb, tc, ta2, p, stream);
 }
 
 template <int CS>
@@ -1029,8 +1049,8 @@ static int run_tn(const srnn_gemm_args* a, GemmParams& p, cudaStream_t stream) {
     }
     if (rc) return rc;
   }
-  if (bn == 256) return launch<256, true, 2>(ta, tb, ta, p, stream);
-  return launch<128, true, 2>(ta, tb, ta, p, stream);
+  if (bn == 256) return launch<256, true, 2>(ta, tb, ta, ta, p, stream);
+  return launch<128, true, 2>(ta, tb, ta, ta, p, stream);
 }
 
 }  // namespace srnn
@@ -1057,7 +1077,7 @@ extern "C" int srnn_gemm_bf16(const srnn_gemm_args* a, srnn_stream_t stream_) {
   if (a->op == 0) {
     SRNN_CHECK_ARG(a->n_fold == 0 || (a->n % a->n_fold == 0 && a->n_fold % 32 == 0 && !a->aux),
                    "gemm NT: n_fold must divide n, be a multiple of 32, and exclude aux");
-    if (a->m <= 512 && a->batch == 1 && a->n_fold == 0 && p.aux_mode != 2 && a->max_ctas == 0 && !a->colsum)
+    if (a->m <= 512 && a->batch == 1 && a->n_fold == 0 && p.aux_mode != 2 && a->max_ctas == 0 && !a->colsum && !a->a2)
       return run_nt_small(a, p, stream);
     return run_nt(a, p, false, stream);
   }

@@ -172,6 +172,21 @@ def test_gemm_nt_fused_column_sums(ops, m, n, k, batch):
     assert rel_l2(cs2, ref2.sum(dim=(0, 1))) < 1e-4
 
 
+@pytest.mark.parametrize('m,n,k1,k2,batch', [(1000, 512, 128, 200, 1), (700, 256, 1024, 64, 2), (130, 64, 64, 16, 1)])
+def test_gemm_nt_two_a_operands_concatenated_along_k(ops, m, n, k1, k2, batch):
+    """A = [A1 | A2] without materialising the concatenation (comb_layer's [one-hot windows | upper] input)."""
+    a1 = rnd(batch, m, k1, scale=0.5).to(BF16)
+    a2 = rnd(batch, m, round_up8(k2), scale=0.5, seed=1).to(BF16)
+    b = rnd(n, k1 + k2, seed=2, scale=0.5).to(BF16)
+    bp = torch.zeros(n, round_up8(k1 + k2), dtype=BF16, device='cuda')
+    bp[:, :k1 + k2] = b
+    c = torch.empty(batch, m, n, dtype=F32, device='cuda')
+    ops.gemm_nt(a1, bp, c, m, n, k1 + k2, k1, bp.shape[1], n, batch=batch, a_bs=m * k1, c_bs=m * n,
+                a2=a2, lda2=a2.shape[2], a2_bs=m * a2.shape[2], k1=k1)
+    ref = torch.cat([a1.float(), a2[..., :k2].float()], dim=2) @ b.float().t()
+    assert rel_l2(c, ref) < 1e-5, rel_l2(c, ref)
+
+
 def test_gemm_nt_batched_overlapping_rows_and_strided_c(ops):
     """The sample-level contraction: A rows are overlapping windows of a (B, W, Q) one-hot buffer."""
     bsz, rf, r0, q, h = 3, 200, 4, 256, 64
