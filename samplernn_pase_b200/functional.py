@@ -286,29 +286,30 @@ class SampleLevelFn(torch.autograd.Function):
         we_t = _empty(q, r0 * h, device=dev)                                 # We^T[q', k*H+o]
         inv_e = _empty(h, dtype=F32, device=dev)
         ops.weight_prep(ev, eg, (h, q, r0), we, (r0 * q, 1, q), we_t, (1, r0 * h, h), inv_norm=inv_e)
-        table = _empty(h, r0 * q, device=dev)
+        # tt[k*Q+q, o] = sum_q' E[q,q'] We[o,q',k]: the embedding + conv output for code q at tap k (the transposed table)
+        tt = _empty(r0 * q, h, device=dev)
         for k in range(r0):
-            ops.gemm_nt(we[:, k * q:], e_b, table[:, k * q:], h, q, q, r0 * q, q, r0 * q)
-        # operand buffer [emb-conv | upper]; the tier below may already have written the upper block
-        shared_cat = (upper.dim() == 3 and upper.stride(2) == 1 and upper.stride(1) == 2 * h and
-                      upper.stride(0) == rf * 2 * h and upper.storage_offset() == h and
-                      upper.untyped_storage().nbytes() >= m * 2 * h * 2)
-        if shared_cat:
-            cat = torch.as_strided(upper, (m, 2 * h), (2 * h, 1), 0)
-        else:
-            cat = _empty(m, 2 * h, device=dev)
-            cat[:, h:] = upper.reshape(m, h)
-        ops.gemm_nt(onehot, table, cat, rf, h, r0 * q, q, r0 * q, 2 * h, batch=b, a_bs=w * q, c_bs=rf * 2 * h)
+            ops.gemm_nt(e_b, we[:, k * q:], tt[k * q:], q, h, q, q, r0 * q, h)
 
-        # comb_layer weights: [W_e | W_u] (H, 2H) K-major, W_c (H, H), and the transposes for backward
+        # comb_layer weights: W_e, W_u, W_c blocks (K-major) and the transposes for backward
         cwc = cw.contiguous()
-        w_eu = _empty(h, 2 * h, device=dev)
+        w_e = _empty(h, h, device=dev)
         w_c = _empty(h, h, device=dev)
         wcomb_t = _empty(3 * h, h, device=dev)                               # rows: e | c | upper blocks of W^T
         ops.weight_prep(cwc, None, (h, 3 * h, 1), wcomb_t, (1, h, 0))
-        ops.weight_prep(cwc[:, :h].contiguous(), None, (h, h, 1), w_eu, (2 * h, 1, 0))
-        ops.weight_prep(cwc[:, 2 * h:].contiguous(), None, (h, h, 1), w_eu[:, h:], (2 * h, 1, 0))
+        ops.weight_prep(cwc[:, :h].contiguous(), None, (h, h, 1), w_e, (h, 1, 0))
         ops.weight_prep(cwc[:, h:2 * h].contiguous(), None, (h, h, 1), w_c, (h, 1, 0))
+        # The embedding, the conv AND comb_layer's embedding block are linear in the one-hot codes, so they fold into
+        # ONE table T' = W_e . table (H x r0*Q); comb_layer's sample-rate input is then [one-hot windows | upper] and its
+        # weight [T' | W_u]: the (B*RF, H) embedding activation, its GEMM and - in backward - its data and weight
+        # gradient GEMMs over B*RF rows never exist.  (model.py:192-200)
+        kc = r0 * q + h
+        w_cat = _empty(h, kc, device=dev)
+        ops.gemm_nt(w_e, tt, w_cat, h, r0 * q, h, h, h, kc)                   # T'[o', k*Q+q] = sum_o W_e[o',o] tt[k*Q+q,o]
+        ops.weight_prep(cwc[:, 2 * h:].contiguous(), None, (h, h, 1), w_cat[:, r0 * q:], (kc, 1, 0))
+        upper_c = upper.reshape(m, h)
+        if not upper_c.is_contiguous() or upper_c.data_ptr() % 16:
+            upper_c = upper_c.contiguous()
 
         # conditioning at frame rate: c_frame = conds_expand(conds) (model.py:194), cterm = c_frame W_c^T + b
         conds_b = _empty(b * l, cp, device=dev)
@@ -323,8 +324,9 @@ class SampleLevelFn(torch.autograd.Function):
 
         h1 = _empty(m, h, device=dev)
         with ops.timed('comb_layer_fwd'):
-            ops.gemm_nt(cat, w_eu, h1, m, h, 2 * h, 2 * h, 2 * h, h, aux=cterm, ldaux=h, aux_mode=1, aux_row_div=fsz,
-                        relu=True)
+            # A = [overlapping one-hot windows (row stride Q, row length r0*Q) | upper], batched per slot
+            ops.gemm_nt(onehot, w_cat, h1, rf, h, kc, q, kc, h, batch=b, a_bs=w * q, c_bs=rf * h, aux=cterm, ldaux=h,
+                        aux_bs=l * h, aux_mode=1, aux_row_div=fsz, relu=True, a2=upper_c, lda2=h, a2_bs=rf * h, k1=r0 * q)
         w2 = _empty(h, h, device=dev)
         w2_t = _empty(h, h, device=dev)
         inv_2 = _empty(h, dtype=F32, device=dev)
@@ -350,13 +352,13 @@ class SampleLevelFn(torch.autograd.Function):
             ops.gemm_nll(1, h2, w3, b3c, target_u8, m, h, h, h, lse=lse, logp_target=logp_t, logp=logp)
             out = logp.view(b, rf, q)
         ctx.dims = (b, w, l, c, h, q, r0, rf, m, fsz, cp, fused)
-        ctx.save_for_backward(onehot, e_b, we_t, inv_e, conds_b, wcs_t, c_frame, cat, wcomb_t, h1, w2, w2_t, inv_2, h2, w3,
-                              w3_t, inv_3, target_u8, b3c, eg, ev, w2g, w2v, w3g, w3v)
+        ctx.save_for_backward(onehot, e_b, we_t, inv_e, conds_b, wcs_t, c_frame, upper_c, tt, wcomb_t, h1, w2, w2_t, inv_2,
+                              h2, w3, w3_t, inv_3, target_u8, b3c, eg, ev, w2g, w2v, w3g, w3v)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        (onehot, e_b, we_t, inv_e, conds_b, wcs_t, c_frame, cat, wcomb_t, h1, w2, w2_t, inv_2, h2, w3, w3_t, inv_3,
+        (onehot, e_b, we_t, inv_e, conds_b, wcs_t, c_frame, upper_c, tt, wcomb_t, h1, w2, w2_t, inv_2, h2, w3, w3_t, inv_3,
          target_u8, b3c, eg, ev, w2g, w2v, w3g, w3v) = ctx.saved_tensors
         b, w, l, c, h, q, r0, rf, m, fsz, cp, fused = ctx.dims
         dev = gout.device
@@ -383,14 +385,11 @@ class SampleLevelFn(torch.autograd.Function):
         ops.gemm_nt(dh2, w2_t, dh1, m, h, h, h, h, h, aux=h1, ldaux=h, aux_mode=2, colsum=d_cbias)
         # comb_layer: [e | upper] blocks at sample rate, conditioning block at frame rate
         d_cw = _zeros(h, 3 * h, device=dev)
-        ops.gemm_tn(dh1, cat, d_cw, h, h, m, h, 2 * h, 3 * h)                              # d W_e
-        ops.gemm_tn(dh1, cat[:, h:], d_cw[:, 2 * h:], h, h, m, h, 2 * h, 3 * h)           # d W_u
+        ops.gemm_tn(dh1, upper_c, d_cw[:, 2 * h:], h, h, m, h, h, 3 * h)                   # d W_u
         seg = _empty(b * l, h, device=dev)                                   # sum of dh1 over the FS samples of a frame
         ops.repeat_rows_bwd(dh1, b * l, h, h, fsz, seg, h)
         ops.gemm_tn(seg, c_frame, d_cw[:, h:], h, h, b * l, h, h, 3 * h)                   # d W_c
-        de = _empty(m, h, device=dev)
         dupper = _empty(m, h, device=dev)
-        ops.gemm_nt(dh1, wcomb_t, de, m, h, h, h, h, h)
         ops.gemm_nt(dh1, wcomb_t[2 * h:], dupper, m, h, h, h, h, h)
         dc_frame = _empty(b * l, h, device=dev)
         ops.gemm_nt(seg, wcomb_t[h:], dc_frame, b * l, h, h, h, h, h)
@@ -400,10 +399,19 @@ class SampleLevelFn(torch.autograd.Function):
         ops.gemm_tn(dc_frame, conds_b, dwcs, h, cp, b * l, h, cp, cp)
         dconds = _empty(b * l, c, dtype=F32, device=dev)
         ops.gemm_nt(dc_frame, wcs_t, dconds, b * l, c, h, h, h, c)
-        # embedding + conv: G[q, k*H+o] = sum_{j: x[j+k]=q} de[j,o]
-        g = _zeros(q, r0 * h, device=dev)
+        # folded table: dT'[o', k*Q+q] = sum_{j: x[j+k]=q} dh1[j,o'], held as gt[q, k*H+o'] (one TN GEMM per tap over the
+        # overlapping one-hot windows).  T' = W_e . table, so d W_e = dT' . table^T and d table = W_e^T . dT' are
+        # H x H x r0*Q contractions - no GEMM over the B*RF rows for the embedding side.
+        gt = _zeros(q, r0 * h, device=dev)
         for k in range(r0):
-            ops.gemm_tn(onehot, de, g[:, k * h:], q, h, rf, q, h, r0 * h, batch=b, a_bs=w * q, b_bs=rf * h, a_off=k)
+            ops.gemm_tn(onehot, dh1, gt[:, k * h:], q, h, rf, q, h, r0 * h, batch=b, a_bs=w * q, b_bs=rf * h, a_off=k)
+        gtb = ops.to_bf16(gt)
+        for k in range(r0):                                                   # d W_e[o',o] += sum_q gt[q,kH+o'] tt[kQ+q,o]
+            ops.gemm_tn(gtb[:, k * h:], tt[k * q:], d_cw, h, h, q, r0 * h, h, 3 * h)
+        # G[q, k*H+o] = sum_o' gt[q,kH+o'] W_e[o',o]: the gradient w.r.t. the (transposed) embedding + conv table
+        g = _empty(q, r0 * h, dtype=F32, device=dev)
+        for k in range(r0):
+            ops.gemm_nt(gtb[:, k * h:], wcomb_t, g[:, k * h:], q, h, h, r0 * h, h, r0 * h)
         gb = ops.to_bf16(g)
         d_emb = _empty(q, q, dtype=F32, device=dev)
         ops.gemm_nt(gb, we_t, d_emb, q, q, r0 * h, r0 * h, r0 * h, q)

@@ -292,7 +292,7 @@ class SampleRNNModel(torch.nn.Module):
             if layer.rnn_cell == 'lstm':
                 c_init = layer.initial_cell(self._state_c[n] if any(use) else None, use_t)
             upper, hn, cn = layer._tier(xq8, fs_top - layer.input_samples, lut, None, conds, upper, h_init,
-                                        into_cat=(n == 0), c_init=c_init)
+                                        into_cat=False, c_init=c_init)
             self._state[n] = hn.detach()
             self._state_c[n] = cn.detach() if layer.rnn_cell == 'lstm' else None
             self._state_valid[n] = [r in (0, 1) for r in reset_l]               # model.py:245-250
