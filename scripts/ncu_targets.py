@@ -26,10 +26,22 @@ def timed(name, fn, flops=None, nbytes=None):
 cat = torch.randn(m, 2 * h, device=dev).to(bf)
 w = (torch.randn(h, 2 * h, device=dev) * 0.02).to(bf)
 bias = torch.zeros(h, device=dev)
-cterm = torch.randn(m // 16, h, device=dev).to(bf)
 h1 = torch.empty(m, h, dtype=bf, device=dev)
-timed('NT comb fwd  m x 1024 x 2048', lambda: ops.gemm_nt(cat, w, h1, m, h, 2 * h, 2 * h, 2 * h, h, aux=cterm, ldaux=h, aux_mode=1,
-                                                           aux_row_div=16, relu=True), flops=2.0 * m * h * 2 * h)
+# comb_layer forward as the model runs it: A = [overlapping one-hot windows (K1 = 4*256) | upper (K2 = H)], weight [T' | W_u],
+# frame-rate conditioning term + ReLU in the epilogue
+nb = max(1, m // 16000)
+rf = m // nb // 16 * 16
+win = rf + 3
+codes = torch.randint(0, 256, (nb, win), dtype=torch.uint8, device=dev)
+onehot_c = ops.onehot_rows(codes)
+upper_c = torch.randn(nb * rf, h, device=dev).to(bf)
+kc = 4 * q + h
+w_cat = (torch.randn(h, kc, device=dev) * 0.02).to(bf)
+cterm = torch.randn(nb * (rf // 16), h, device=dev).to(bf)
+h1c = torch.empty(nb * rf, h, dtype=bf, device=dev)
+timed('NT comb fwd  m x 1024 x (1024 one-hot + 1024)', lambda: ops.gemm_nt(
+    onehot_c, w_cat, h1c, rf, h, kc, q, kc, h, batch=nb, a_bs=win * q, c_bs=rf * h, aux=cterm, ldaux=h, aux_bs=(rf // 16) * h,
+    aux_mode=1, aux_row_div=16, relu=True, a2=upper_c, lda2=h, a2_bs=rf * h, k1=4 * q), flops=2.0 * nb * rf * h * kc)
 w2 = (torch.randn(h, h, device=dev) * 0.03).to(bf)
 h2 = torch.empty(m, h, dtype=bf, device=dev)
 timed('NT expand    m x 1024 x 1024', lambda: ops.gemm_nt(h1, w2, h2, m, h, h, h, h, h, bias=bias, relu=True),
