@@ -399,19 +399,18 @@ class SampleLevelFn(torch.autograd.Function):
         ops.gemm_tn(dc_frame, conds_b, dwcs, h, cp, b * l, h, cp, cp)
         dconds = _empty(b * l, c, dtype=F32, device=dev)
         ops.gemm_nt(dc_frame, wcs_t, dconds, b * l, c, h, h, h, c)
-        # folded table: dT'[o', k*Q+q] = sum_{j: x[j+k]=q} dh1[j,o'], held as gt[q, k*H+o'] (one TN GEMM per tap over the
-        # overlapping one-hot windows).  T' = W_e . table, so d W_e = dT' . table^T and d table = W_e^T . dT' are
-        # H x H x r0*Q contractions - no GEMM over the B*RF rows for the embedding side.
-        gt = _zeros(q, r0 * h, device=dev)
-        for k in range(r0):
-            ops.gemm_tn(onehot, dh1, gt[:, k * h:], q, h, rf, q, h, r0 * h, batch=b, a_bs=w * q, b_bs=rf * h, a_off=k)
+        # folded table: dT'[o', k*Q+q] = sum_{j: x[j+k]=q} dh1[j,o'].  T' = W_e . table, so d W_e = dT' . table^T and
+        # d table = W_e^T . dT' are H x H x r0*Q contractions - no GEMM over the B*RF rows for the embedding side ...
+        # ... as ONE TN GEMM over the overlapping windows: gt[k*Q+q, o'] = sum_j window_j[k*Q+q] dh1[j, o'] (A rows are
+        # the r0*Q-wide windows at a row stride of Q, read in place)
+        gt = _zeros(r0 * q, h, device=dev)
+        ops.gemm_tn(onehot, dh1, gt, r0 * q, h, rf, q, h, h, batch=b, a_bs=w * q, b_bs=rf * h)
         gtb = ops.to_bf16(gt)
-        for k in range(r0):                                                   # d W_e[o',o] += sum_q gt[q,kH+o'] tt[kQ+q,o]
-            ops.gemm_tn(gtb[:, k * h:], tt[k * q:], d_cw, h, h, q, r0 * h, h, 3 * h)
-        # G[q, k*H+o] = sum_o' gt[q,kH+o'] W_e[o',o]: the gradient w.r.t. the (transposed) embedding + conv table
+        ops.gemm_tn(gtb, tt, d_cw, h, h, r0 * q, h, h, 3 * h)                # d W_e[o',o] = sum_{kQ+q} gt[.,o'] tt[.,o]
+        # G[q, k*H+o] = sum_o' gt[kQ+q,o'] W_e[o',o]: the gradient w.r.t. the (transposed) embedding + conv table
         g = _empty(q, r0 * h, dtype=F32, device=dev)
         for k in range(r0):
-            ops.gemm_nt(gtb[:, k * h:], wcomb_t, g[:, k * h:], q, h, h, r0 * h, h, r0 * h)
+            ops.gemm_nt(gtb[k * q:], wcomb_t, g[:, k * h:], q, h, h, h, h, r0 * h)
         gb = ops.to_bf16(g)
         d_emb = _empty(q, q, dtype=F32, device=dev)
         ops.gemm_nt(gb, we_t, d_emb, q, q, r0 * h, r0 * h, r0 * h, q)
