@@ -35,7 +35,8 @@ typedef void* srnn_stream_t; /* cudaStream_t */
 
 const char* srnn_last_error(void);
 int srnn_abi_version(void);
-/* sm count and compute capability of the current device */
+/* sm count and compute capability of the current device.  Host-side state of the library (SM count, function
+ * attributes, occupancy answers) is cached per CUDA device and may be used from several host threads. */
 int srnn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* ---------------------------------------------------------------------------------------------
@@ -191,12 +192,13 @@ typedef struct srnn_gru_args {
   void* dgi;             /* bf16 [batch*steps, 3H] batch-major, out */
   void* dgh;             /* bf16 [steps, ext_batch, 3H] TIME-major, out (also the per-step exchange buffer) */
   float* dh0;            /* fp32 [batch, H] out: dL/dh_init */
-  uint32_t* sync;        /* >= 4*(hidden/8) bytes (one flag per CTA), zeroed by the caller before every launch */
-  int32_t debug_flags;   /* must be 0.  Timing experiments only (results are WRONG with 1 or 4):
-                            1 = do not wait on the grid counter, 4 = skip the per-step global loads/stores of the
-                            epilogue; results stay correct with 16 = add a gpu-scope acquire fence after the grid
-                            wait, 32 = one TMA box per K block, 64 = two MMA-issuing warps, 128 = debug_ts receives the
-                            global timer of every CTA at timestep 24, bits 8.. = force a cluster size */
+  uint32_t* sync;        /* >= 1 KB, zeroed by the caller before every launch (grid-wide arrival counters) */
+  int32_t tuning_flags;  /* 0 = defaults.  Every documented bit leaves the results unchanged:
+                            2 = force a cooperative launch for steps == 1, 16 = add a gpu-scope acquire fence after the
+                            grid wait, 32 = land the per-step operand as ONE TMA box (default: one box per K block,
+                            pipelined with the MMAs), 64 = two MMA-issuing warps, 128 = debug_ts receives the global
+                            timer of every CTA at timestep 24, bits 8.. = force a cluster size.  Bits 1 and 4 exist only
+                            in instrumented (-DSRNN_DEBUG) builds and are rejected with SRNN_ERR_ARG otherwise. */
   uint64_t* debug_ts;    /* NULL, or [256][8] clock64 stamps of CTA 0's pipeline events (profiling aid) */
   /* LSTM extension (cell = 1; no reference counterpart, torch.nn.LSTM semantics, gates i,f,g,o): every
    * "3H" above becomes 4H, `gates` is [batch*steps, 5H] (i, f, g, o, c_t). */

@@ -49,7 +49,7 @@ class GruArgs(C.Structure):
         ('gi', C.c_void_p), ('w_hh', C.c_void_p), ('b_hh', C.c_void_p),
         ('h_ext', C.c_void_p), ('hall', C.c_void_p), ('h_state', C.c_void_p), ('gates', C.c_void_p),
         ('dh_out', C.c_void_p), ('dgi', C.c_void_p), ('dgh', C.c_void_p), ('dh0', C.c_void_p),
-        ('sync', C.c_void_p), ('debug_flags', C.c_int32), ('debug_ts', C.c_void_p),
+        ('sync', C.c_void_p), ('tuning_flags', C.c_int32), ('debug_ts', C.c_void_p),
         ('cell', C.c_int32), ('c_state', C.c_void_p), ('c_init', C.c_void_p), ('dc0', C.c_void_p),
         ('units_per_cta', C.c_int32), ('db_ih', C.c_void_p), ('db_hh', C.c_void_p),
     ]

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/srnn_b200.h"
 
 namespace srnn {
@@ -32,7 +34,16 @@ int cuda_fail(cudaError_t e, const char* what);
     if (e__ != cudaSuccess) return ::srnn::cuda_fail(e__, #call);    \
   } while (0)
 
-int sm_count();
+// All host-side caches are keyed by the CUDA device current at the call (function attributes, occupancy answers and
+// the SM count are per device) and are safe to fill from several host threads: entries are idempotent and atomic.
+constexpr int kMaxDevices = 64;
+int current_device();            // cudaGetDevice(), clamped to [0, kMaxDevices)
+int sm_count();                  // of the current device
+struct DeviceOnce {              // "has this one-off per-device set-up been done?"
+  std::atomic<unsigned char> done[kMaxDevices];
+  bool test() const { return done[current_device()].load(std::memory_order_acquire) != 0; }
+  void set() { done[current_device()].store(1, std::memory_order_release); }
+};
 // Programmatic dependent launch (srnn_set_pdl): kernels that support it are launched so that the NEXT kernel in the
 // stream may start while they still run; such kernels call pdl_wait() before their first global-memory access.
 bool pdl_enabled();

@@ -821,10 +821,10 @@ template <int BN, bool TN, int EPI>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& ta2,
                   const GemmParams& p, cudaStream_t stream) {
   auto kern = gemm_kernel<BN, TN, EPI>;
-  static bool configured = false;   // per instantiation
-  if (!configured) {
+  static DeviceOnce configured;     // per instantiation and device
+  if (!configured.test()) {
     SRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemCfg<BN>::TOTAL));
-    configured = true;
+    configured.set();
   }
   int cap = sm_count();
   if (p.max_ctas > 0 && p.max_ctas < cap) cap = p.max_ctas;    // leave SMs to a concurrently running kernel
@@ -908,10 +908,10 @@ static int run_nt(const srnn_gemm_args* a, GemmParams& p, bool nll, cudaStream_t
 template <int CS>
 static int launch_small(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   auto kern = gemm_small_kernel<CS>;
-  static bool configured = false;   // per instantiation
-  if (!configured) {
+  static DeviceOnce configured;     // per instantiation and device
+  if (!configured.test()) {
     SRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S_TOTAL));
-    configured = true;
+    configured.set();
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.tiles_m * p.tiles_n * CS);

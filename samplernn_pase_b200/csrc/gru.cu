@@ -28,6 +28,8 @@
 // issuers + running descriptors 5.0/5.35 -> no gpu-scope acquire fence on the consumer 4.5/4.8.
 //
 // The fp32 recurrent state of a unit never leaves the registers of its owner thread.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace srnn {
@@ -39,6 +41,7 @@ constexpr int gru_threads(int mw) { return 32 * (4 + mw); }
 // half of the SMs free for GEMMs running concurrently on another stream)
 constexpr int GRU_M = 64;          // batch rows per launch (MMA M)
 constexpr int GRU_SLOT = GRU_M * 128;   // one [64 rows][64 bf16] K block
+constexpr int GRU_MAX_KBC = 32;         // K blocks of the exchanged operand per CTA (one landing barrier each)
 
 struct GruParams {
   int batch, steps, hidden, ext_batch;
@@ -138,12 +141,39 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
 // counter or one per thread index) made the step shorter: the release path (store ack + MEMBAR.GPU + RED), not the
 // polling granularity, sets the ~1.2 us from the last publish to the first release.  Publishing per epilogue warp
 // (4 release arrivals per CTA and step instead of a CTA barrier + one) is slower: 4.55 / 5.43 us per step.
+// Watchdog: a protocol bug must end the launch with an error instead of hanging the GPU, but a spin COUNT can fire
+// spuriously when the kernel is time-sliced (debugger, profiler replay, MPS), so the limit is wall-clock: 20 s without
+// progress on one handshake (a timestep takes microseconds).
 __device__ __forceinline__ void grid_wait(const uint32_t* counter, uint32_t target, bool acquire_fence) {
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (ld_relaxed_gpu(counter) < target) {
-    if (++spins > (1u << 24)) __trap();
+    if ((++spins & 0xFFFFu) == 0) {
+      const unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) __trap();
+    }
   }
   if (acquire_fence) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
+// Instrumented builds only (-DSRNN_DEBUG): timing experiments that produce WRONG results.  bit 0: do not wait on the
+// grid counter; bit 2: skip the per-step global loads/stores of the epilogue.  A release build rejects both bits.
+__device__ __forceinline__ bool grid_wait_skipped(int flags) {
+#ifdef SRNN_DEBUG
+  return (flags & 1) != 0;
+#else
+  (void)flags;
+  return false;
+#endif
+}
+__device__ __forceinline__ bool epilogue_io_skipped(int flags) {
+#ifdef SRNN_DEBUG
+  return (flags & 4) != 0;
+#else
+  (void)flags;
+  return false;
+#endif
 }
 
 // LSTM = false: GRU (gates r,z,n; 3H pre-activations).  LSTM = true: LSTM (gates i,f,g,o; 4H), an
@@ -172,10 +202,10 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
   float* part = reinterpret_cast<float*>(hbuf + KBC * GRU_SLOT);        // [NCOLS][64] fp32 partial tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(part + NCOLS * GRU_M);
   uint64_t* wfull = bars;
-  uint64_t* full = bars + 1;
-  uint64_t* acc_full = bars + 2;
-  uint64_t* part_ready = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* acc_full = bars + 1;
+  uint64_t* part_ready = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* full = bars + 4;                                            // [GRU_MAX_KBC]: one per K block of the operand
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -191,7 +221,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
     tma_prefetch_desc(&tma_w);
     tma_prefetch_desc(&tma_x);
     mbar_init(wfull, 1);
-    mbar_init(full, 1);
+    for (int kb = 0; kb < GRU_MAX_KBC; ++kb) mbar_init(full + kb, 1);
     mbar_init(acc_full, MW);
     mbar_init(part_ready, 1);
     fence_barrier_init();
@@ -233,43 +263,50 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       const uint32_t d_tmem = tmem_base + mw * NCOLS;
       const uint32_t hslot16 = static_cast<uint32_t>(p.hslot) >> 4;
       uint32_t phase = 0;
+      const uint32_t a_lo0 = static_cast<uint32_t>(a_base), b_lo0 = static_cast<uint32_t>(b_base);
+      const uint32_t blk_bytes = static_cast<uint32_t>(B) * 128u;
       for (int s = 0; s < rounds; ++s) {
         if (BWD && s == 0) continue;                 // the last timestep has no recurrent input
         if (mw == 0) {
-          if (s > 0 && !(p.flags & 1)) {
+          if (s > 0 && !grid_wait_skipped(p.flags)) {
             grid_wait(p.sync, G * static_cast<uint32_t>(s), (p.flags & 16) != 0);
             GRU_TS(0, s);
           }
           asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy writes -> TMA reads (free: measured)
           const int slot = BWD ? (T - s) : s;        // time slot of the exchange buffer
-          mbar_expect_tx(full, bytes);
           if (p.one_box) {
+            mbar_expect_tx(full, bytes);
             tma_load_4d(hbuf, &tma_x, full, 0, 0, kb0, slot);
           } else {
-            for (int kb = 0; kb < KBC; ++kb)
-              tma_load_3d(hbuf + kb * GRU_SLOT, &tma_x, full, (kb0 + kb) * 64, 0, slot);
+            // One box and one barrier per K block, issued back to back by this thread (~80 cycles apart, about the time
+            // the TMA unit needs to turn one 8 KB box into L2 requests), so the blocks LAND in issue order and the MMAs
+            // of block i run while blocks i+1.. are still in flight.
+            for (int kb = 0; kb < KBC; ++kb) {
+              mbar_expect_tx(full + kb, blk_bytes);
+              tma_load_3d(hbuf + kb * GRU_SLOT, &tma_x, full + kb, (kb0 + kb) * 64, 0, slot);
+            }
           }
           GRU_TS(1, s);
         }
-        // (splitting the operand into 4 boxes with their own barriers so the MMAs could start on the first
-        // part was measured useless: the TMA unit services the boxes interleaved and they all land together;
-        // so was TMA multicast in clusters of 4 - every CTA fetching 16 batch rows for all four: bit-identical
-        // results, 3.96 us per step either way, i.e. the landing is bound by the SM's own ingest; 16 clusters of 8
-        // cannot be co-resident on this part)
-        mbar_wait(full, phase);
-        phase ^= 1;
-        if (mw == 0) GRU_TS(2, s);
-        tc_fence_after();
-        // K steps (16 columns = 32 bytes inside a 64-column block) are dealt round-robin: issuer mw takes steps
-        // mw, mw + MW, ...  Only the 14-bit start-address field (low descriptor word) changes.
-        const uint32_t a_lo0 = static_cast<uint32_t>(a_base), b_lo0 = static_cast<uint32_t>(b_base);
-#pragma unroll 4
-        for (int ks = mw; ks < KBC * 4; ks += MW) {
-          const uint32_t kb = static_cast<uint32_t>(ks) >> 2, j = static_cast<uint32_t>(ks) & 3u;
-          const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo0 + kb * hslot16 + j * 2u);
-          const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo0 + kb * (WBLOCK >> 4) + j * 2u);
-          umma_bf16(d_tmem, ad, bd, IDESC, ks >= MW ? 1u : 0u);
+        // K steps (16 columns = 32 bytes inside a 64-column block) are dealt round-robin inside every K block: issuer mw
+        // takes steps mw, mw + MW, ... of each block.  Only the 14-bit start-address field (low descriptor word) changes.
+        uint32_t first = 0u;
+        for (int kb = 0; kb < KBC; ++kb) {
+          if (kb == 0 || !p.one_box) {
+            mbar_wait(full + (p.one_box ? 0 : kb), phase);
+            tc_fence_after();
+            if (C == 1 && mw == 0 && kb == 0) GRU_TS(7, s);    // first block landed (slot 7 = partials pushed when C > 1)
+          }
+#pragma unroll
+          for (int j = mw; j < 4; j += MW) {
+            const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo0 + static_cast<uint32_t>(kb) * hslot16 + j * 2u);
+            const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo0 + static_cast<uint32_t>(kb) * (WBLOCK >> 4) + j * 2u);
+            umma_bf16(d_tmem, ad, bd, IDESC, first);
+            first = 1u;
+          }
         }
+        phase ^= 1;
+        if (mw == 0) GRU_TS(2, s);                   // last block landed (and its MMAs issued)
         umma_commit(acc_full);
         if (mw == 0) GRU_TS(3, s);
       }
@@ -281,7 +318,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
     const int row = q * 16 + lane;                   // M=64: rows 16q..16q+15 live in lanes 32q..32q+15
     const bool lane_ok = lane < 16;
     const bool row_ok = lane_ok && row < B;
-    const bool io = row_ok && !(p.flags & 4);
+    const bool io = row_ok && !epilogue_io_skipped(p.flags);
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t part_addr = smem_u32(part);
     const uint32_t ready_addr = smem_u32(part_ready);
@@ -677,7 +714,7 @@ template <bool BWD, int C, bool LSTM, int U>
 static size_t gru_smem_bytes(int kbc) {
   const int ncols = (BWD ? 1 : (LSTM ? 4 : 3)) * U * C;
   return static_cast<size_t>(kbc) * ncols * 128 + static_cast<size_t>(kbc) * GRU_SLOT +
-         static_cast<size_t>(ncols) * GRU_M * 4 + 256 + 1024;
+         static_cast<size_t>(ncols) * GRU_M * 4 + (8 + GRU_MAX_KBC) * 8 + 1024;
 }
 
 // MMA issuing warps: 4 when the 4 partial accumulators fit the 512 TMEM columns, else 2
@@ -752,7 +789,9 @@ static int launch_gru_mw(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   // number of 64-column blocks and the batch a whole number of 8-row swizzle atoms, the buffer is viewed as
   // [slot][K block][row][64] (strides not monotonic: legal for a tiled map) so that ONE box brings the CTA's
   // whole [batch, K slice] operand, K block by K block, in the layout the MMA reads (8 TMA issues -> 1).
-  const bool one_box = K % 64 == 0 && B % 8 == 0 && kbc * B * 128 <= 160 * 1024 && !(a->debug_flags & 32);
+  // Landing of the per-step operand: by default one TMA box and one barrier per K block (pipelined with the MMAs);
+  // tuning flag 32 selects the older single 4-D box (one issue, everything lands together).
+  const bool one_box = (a->tuning_flags & 32) && K % 64 == 0 && B % 8 == 0 && kbc * B * 128 <= 160 * 1024;
   {
     const uint64_t slots = BWD ? (uint64_t)T : (uint64_t)T + 1;
     const void* base = BWD ? (const void*)a->dgh : (const void*)a->h_ext;
@@ -790,7 +829,7 @@ static int launch_gru_mw(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   p.db_ih = a->db_ih;
   p.db_hh = a->db_hh;
   p.sync = a->sync;
-  p.flags = a->debug_flags;
+  p.flags = a->tuning_flags;
   p.ts = reinterpret_cast<unsigned long long*>(a->debug_ts);
 
   auto kern = gru_kernel<BWD, C, LSTM, U, MW>;
@@ -802,7 +841,7 @@ static int launch_gru_mw(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   cfg.stream = stream;
   cudaLaunchAttribute attrs[3];
   int na = 0;
-  if (T > 1 || C > 1 || (a->debug_flags & 2)) {        // (flag 2: experiment, force the cooperative launch)
+  if (T > 1 || C > 1 || (a->tuning_flags & 2)) {        // (flag 2: experiment, force the cooperative launch)
     attrs[na].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: they spin on one another
     attrs[na].val.cooperative = 1;
     ++na;
@@ -830,10 +869,32 @@ template <bool BWD, int C, bool LSTM, int U>
 static int launch_gru(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   constexpr int MW = gru_mw<BWD, C, LSTM, U>();
   if constexpr (MW != 2 && U == 8 && !LSTM) {          // experiments: debug flag 64 = two issuing warps
-    if (a->debug_flags & 64) return launch_gru_mw<BWD, C, LSTM, U, 2>(a, kbc, stream);
+    if (a->tuning_flags & 64) return launch_gru_mw<BWD, C, LSTM, U, 2>(a, kbc, stream);
   }
   return launch_gru_mw<BWD, C, LSTM, U, MW>(a, kbc, stream);
 }
+
+// The occupancy answer behind pick_cluster() depends on the device and on H only: remembered per (device, hidden),
+// guarded by a mutex so that several host threads (one per device, or several on one) may call concurrently.
+struct PickCache {
+  std::mutex mu;
+  int hidden[kMaxDevices];
+  int c[kMaxDevices];
+  int kbc[kMaxDevices];
+  PickCache() { for (int i = 0; i < kMaxDevices; ++i) hidden[i] = -1; }
+  int get(int h, int* kbc_out) {                       // -> cluster size (0 = nothing fits), or -1 if unknown
+    const int d = current_device();
+    std::lock_guard<std::mutex> lock(mu);
+    if (hidden[d] != h) return -1;
+    *kbc_out = kbc[d];
+    return c[d];
+  }
+  void put(int h, int c_, int kbc_) {
+    const int d = current_device();
+    std::lock_guard<std::mutex> lock(mu);
+    hidden[d] = h; c[d] = c_; kbc[d] = kbc_;
+  }
+};
 
 // Cluster size: K split in whole K blocks, units tile H, slice fits smem, all clusters co-resident.
 template <bool BWD, bool LSTM, int U>
@@ -849,6 +910,7 @@ static int pick_cluster(int H, int* kbc_out) {
     const int c = BWD ? bwd_order[i] : fwd_order[i];
     if (kb_total % c != 0 || H % (U * c) != 0) continue;
     const int kbc = kb_total / c;
+    if (kbc > GRU_MAX_KBC) continue;
     bool fits = false;
     if constexpr (U == 8) {
       switch (c) {
@@ -873,17 +935,17 @@ static int pick_cluster(int H, int* kbc_out) {
 
 template <bool BWD, bool LSTM, int U>
 static int dispatch_gru_u(const srnn_gru_args* a, cudaStream_t stream) {
-  static int cached_h = -1, cached_c = 0, cached_kbc = 0;      // per instantiation
-  if (cached_h != a->hidden) {
-    cached_c = pick_cluster<BWD, LSTM, U>(a->hidden, &cached_kbc);
-    cached_h = a->hidden;
+  static PickCache cache;                              // per instantiation; keyed by (device, hidden)
+  int kbc = 0;
+  int c = cache.get(a->hidden, &kbc);
+  if (c < 0) {
+    c = pick_cluster<BWD, LSTM, U>(a->hidden, &kbc);
+    cache.put(a->hidden, c, kbc);
   }
-  int kbc = cached_kbc;
-  int c = cached_c;
-  if (a->debug_flags >> 8) {                         // experiments: force a cluster size (bits 8..)
-    const int forced = a->debug_flags >> 8;
+  if (a->tuning_flags >> 8) {                         // experiments: force a cluster size (bits 8..)
+    const int forced = a->tuning_flags >> 8;
     const int kb_total = ((BWD ? (LSTM ? 4 : 3) : 1) * a->hidden + 63) / 64;
-    if (kb_total % forced == 0 && a->hidden % (U * forced) == 0) {
+    if (kb_total % forced == 0 && a->hidden % (U * forced) == 0 && kb_total / forced <= GRU_MAX_KBC) {
       c = forced;
       kbc = kb_total / forced;
     }
@@ -909,11 +971,12 @@ static int dispatch_gru(const srnn_gru_args* a, cudaStream_t stream) {
   // 16 units per CTA when asked for (and possible), else 8; more than the SM count of CTAs never fits
   bool wide = a->units_per_cta == 16 && a->hidden % 32 == 0;
   if (wide) {                                          // fall back to 8 units when the wide slice does not fit
-    static int probed_h = -1, probed_c = 0;
-    if (probed_h != a->hidden) {
-      int kbc = 0;
+    static PickCache probe;
+    int kbc = 0;
+    int probed_c = probe.get(a->hidden, &kbc);
+    if (probed_c < 0) {
       probed_c = pick_cluster<BWD, LSTM, 16>(a->hidden, &kbc);
-      probed_h = a->hidden;
+      probe.put(a->hidden, probed_c, kbc);
     }
     wide = probed_c > 0;
   }
@@ -940,6 +1003,10 @@ static int check_common(const srnn_gru_args* a) {
   SRNN_CHECK_ARG(a->cell == 0 || a->cell == 1, "gru: cell must be 0 (GRU) or 1 (LSTM)");
   SRNN_CHECK_ARG(a->units_per_cta == 0 || a->units_per_cta == 8 || a->units_per_cta == 16,
                  "gru: units_per_cta must be 0, 8 or 16");
+#ifndef SRNN_DEBUG
+  SRNN_CHECK_ARG((a->tuning_flags & (1 | 4)) == 0,
+                 "gru: tuning_flags 1 and 4 select instrumented modes that exist only in -DSRNN_DEBUG builds");
+#endif
   return SRNN_OK;
 }
 

@@ -24,9 +24,13 @@ class NegSumFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logp_target):
         flat = logp_target.contiguous().view(-1)
+        ctx.shape = logp_target.shape
+        if flat.numel() == 0:
+            # a rank whose slots are all empty (reset == 2, the tail of an epoch): zero loss that still belongs to
+            # the graph, so backward runs (with zero gradients) and the bucket all-reduces stay matched across ranks
+            return flat.new_zeros(())
         one = torch.ones(1, dtype=torch.uint8, device=flat.device)
         out = ops.masked_nll_mean(flat, one, flat.numel())          # [-mean, count]
-        ctx.shape = logp_target.shape
         return out[0] * out[1]
 
     @staticmethod

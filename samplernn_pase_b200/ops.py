@@ -299,7 +299,7 @@ def gemm_nll(mode, a, w, bias, target, m, k, lda, ldw, lse=None, logp_target=Non
 # recurrence
 # ----------------------------------------------------------------------------------------------
 GRU_MAX_BATCH = 64
-gru_debug_flags = 0      # timing experiments only (scripts/gru_microbench.py)
+gru_tuning_flags = 0     # srnn_gru_args.tuning_flags (scripts/gru_microbench.py sweeps them)
 gru_debug_ts = None      # int64 [256, 8] tensor receiving CTA 0's pipeline timestamps
 gru_units_per_cta = 8    # 16 halves the recurrent kernels' CTA count (SMs left free for concurrent GEMMs)
 
@@ -320,14 +320,16 @@ def _gru_call(name, batch, steps, hidden, cell=0, **bufs):
             else:
                 setattr(a, key, t.data_ptr() + b0 * per_row * t.element_size())
         dev = bufs['h_ext'][0].device
-        if steps == 1:                     # a single timestep never waits on the arrival counter: no zeroing needed
+        if steps == 1 and name == 'srnn_gru_forward':
+            # a single FORWARD timestep never waits on the arrival counter: no zeroing needed.  (The backward kernel
+            # runs steps + 1 rounds and does wait at round 1, so it always gets a freshly zeroed counter.)
             sync = _gru_scratch.get(dev)
             if sync is None:
                 sync = _gru_scratch[dev] = torch.zeros(256, dtype=torch.int32, device=dev)
         else:
             sync = torch.zeros(256, dtype=torch.int32, device=dev)
         a.sync = sync.data_ptr()
-        a.debug_flags = gru_debug_flags
+        a.tuning_flags = gru_tuning_flags
         a.units_per_cta = gru_units_per_cta
         a.debug_ts = gru_debug_ts.data_ptr() if gru_debug_ts is not None else None
         _lib.profile_note = f'B={nb} T={steps} H={hidden}' + (' lstm' if cell else '')

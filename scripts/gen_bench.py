@@ -19,7 +19,7 @@ ap.add_argument('--eager', action='store_true')
 ap.add_argument('--gru-flags', type=int, default=0)
 a = ap.parse_args()
 torch.manual_seed(0)
-ops.gru_debug_flags = a.gru_flags
+ops.gru_tuning_flags = a.gru_flags
 model = SampleRNNModel(**bench.model_kwargs(a.frames)).cuda()
 utt = torch.randn(a.batch, a.frames, 43).cuda()
 info = [{'speaker': {'index': i % 126}} for i in range(a.batch)]

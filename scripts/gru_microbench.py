@@ -14,9 +14,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=64)
 ap.add_argument('--steps', type=int, default=1000)
 ap.add_argument('--hidden', type=int, default=1024)
-ap.add_argument('--flags', default='0,1024,512,256,1,4')   # bits 8.. force a cluster size
+ap.add_argument('--flags', default='0,32,16')   # 32 = single-box landing, 16 = acquire fence, bits 8.. force a cluster size
 ap.add_argument('--reps', type=int, default=3)
-ap.add_argument('--ts-flags', default='0')              # timeline(s) of CTA 0 for these flag values
+ap.add_argument('--ts-flags', default='0,32')              # timeline(s) of CTA 0 for these flag values
 ap.add_argument('--units', type=int, default=0)          # units per CTA (0 = default 8)
 a = ap.parse_args()
 b, t, h = a.batch, a.steps, a.hidden
@@ -43,7 +43,7 @@ def run(kind):
 
 
 for flags in [int(f) for f in a.flags.split(',')]:
-    ops.gru_debug_flags = flags
+    ops.gru_tuning_flags = flags
     for kind in ('fwd', 'bwd'):
         try:
             run(kind)
@@ -59,12 +59,12 @@ for flags in [int(f) for f in a.flags.split(',')]:
             best = min(best, e0.elapsed_time(e1))
         print(f'flags={flags} {kind}: {best:8.3f} ms  {1e3 * best / t:6.2f} us/step   (B={b} T={t} H={h})')
 # pipeline timestamps of CTA 0 (forward): cycles relative to the end of the grid wait
-names = ['wait_done', 'tma_issued', 'mma_full', 'mma_commit', 'epi_acc_full', 'epi_arrived', 'epi_part_rdy', 'epi_publish']
+names = ['wait_done', 'tma_issued', 'last_landed', 'mma_commit', 'epi_acc_full', 'pushed/1st_land', 'epi_part_rdy', 'epi_publish']
 order = [0, 1, 2, 3, 4, 7, 5, 6]
 for flags in [int(f) for f in a.ts_flags.split(',') if f]:
     for kind in ('fwd', 'bwd'):
         ts = torch.zeros(256, 8, dtype=torch.int64, device='cuda')
-        ops.gru_debug_flags = flags
+        ops.gru_tuning_flags = flags
         ops.gru_debug_ts = ts
         run(kind)
         torch.cuda.synchronize()
@@ -75,15 +75,15 @@ for flags in [int(f) for f in a.ts_flags.split(',') if f]:
         for s_ in range(20, 26):
             base = int(t_[s_, 0])
             print(f'{s_:4d}  ' + '  '.join(f'{int(t_[s_, i]) - base:12d}' for i in order) + f'   {int(t_[s_ + 1, 0]) - base:10d}')
-ops.gru_debug_flags = 0
+ops.gru_tuning_flags = 0
 # skew between CTAs: global timer (ns) of every CTA at timestep 24 of the forward kernel
 ts = torch.zeros(256, 8, dtype=torch.int64, device='cuda')
-ops.gru_debug_flags = 128
+ops.gru_tuning_flags = 128
 ops.gru_debug_ts = ts
 run('fwd')
 torch.cuda.synchronize()
 ops.gru_debug_ts = None
-ops.gru_debug_flags = 0
+ops.gru_tuning_flags = 0
 t_ = ts.cpu()
 n_cta = int((t_[:, 0] > 0).sum())
 t0 = int(t_[:n_cta, 0].min())

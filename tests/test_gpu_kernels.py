@@ -361,7 +361,7 @@ def test_gru_grid_handshake_stress_bit_exact(ops):
     dh_out = rnd(bsz, t, h, scale=0.1, seed=4).to(BF16)
 
     def run(flags):
-        ops.gru_debug_flags = flags
+        ops.gru_tuning_flags = flags
         try:
             h_ext = torch.zeros(t + 1, bsz, h, dtype=BF16, device='cuda')
             h_ext[0] = h0.to(BF16)
@@ -375,7 +375,7 @@ def test_gru_grid_handshake_stress_bit_exact(ops):
             ops.gru_backward(w_hh.t().contiguous(), h_ext, gates, dh_out.view(bsz * t, h), dgi, dgh, dh0, bsz, t, h)
             return hall, h_state, dgi, dh0
         finally:
-            ops.gru_debug_flags = 0
+            ops.gru_tuning_flags = 0
 
     ref = run(16)                       # flag 16: keep the consumer-side acquire fence
     for i in range(20):
