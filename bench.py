@@ -13,8 +13,12 @@ Printed JSON (one line, rank 0):
   value     audio samples/s over all GPUs, inputs already resident in HBM, no host sync per step
   e2e       the same metric through the public module API with pinned HOST buffers: H2D copies of
             x / y / conds and the D2H read of the loss are inside the timed region
-  roofline  the dominant kernel (comb_layer forward GEMM, tcgen05) timed live with CUDA events
-  cpu_baseline  the CPU oracle port timed on this box's host cores on a bounded sample
+  roofline  the DOMINANT kernel of the step - the persistent recurrent kernel - timed live with CUDA events: us per
+            timestep, share of the step and achieved algorithmic HBM rate vs the measured copy peak
+  roofline_gemm  the largest contraction (comb_layer forward, tcgen05) vs the measured sustained and burst bf16 peaks
+  recurrence     all recurrent launches of the step (direction x timesteps)
+  cpu_baseline   the CPU oracle port timed on this box's host cores on a bounded sample of the same workload
+  gpu_eager_baseline  informational: the oracle port (plain torch ops) on the same GPU, fp32 and bf16 autocast
 
 ``--impl reference`` times the reference's CPU path (the oracle port; the reference is pure Python
 and cannot travel to the GPU box) on the host cores with the same metric/unit.
@@ -36,8 +40,6 @@ RATIOS, LAYERS, HIDDEN = [4, 4], [1, 1], [1024, 1024]
 SLOTS_PER_GPU, SEQ_LEN = 64, 1000
 N_SPEAKERS = 126
 METRIC = 'teacher-forced training audio samples/sec'
-# dram bytes (read+write) of the comb_layer forward GEMM (m x 1024 x 2048) measured by ncu at m = 262 144; None = not captured
-NCU_BYTES_AT_262144 = 0.7090e9 + 0.5026e9      # read + write, profiles/r01_hot_kernels_ncu.txt [3]
 WORKLOAD = ('config2: 3-tier SampleRNN GRU ratios [4,4] H=1024, 64 slots/GPU x 1 s chunks (L=1000, RF=16000) '
             'of 8 s utterances with hidden-state carry, acoustic conds U=43, 126 speakers')
 
@@ -98,40 +100,109 @@ def flops_per_sample_fwd():
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU reference arm (oracle port)
+# CPU reference arm (oracle port) and the informational GPU-eager leg
 # --------------------------------------------------------------------------------------------------
-def cpu_reference(steps, warmup, batch=8, seq_len=64):
+CPU_SAMPLE_SLOTS = 8         # slots of the workload's chunk the CPU arm runs per step (a bounded sample: same model, same
+                             # chunk length L, carry across chunks; per-sample CPU cost does not depend on the slot count)
+
+
+def config_dict(world=1, slots=None):
+    """The workload description BOTH arms print (same keys, same values)."""
+    slots = SLOTS_PER_GPU if slots is None else slots
+    fs = 1
+    for r in RATIOS:
+        fs *= r
+    return dict(workload=WORKLOAD, ratios=RATIOS, hidden=HIDDEN[0], seq_len=seq_len_default(),
+                samples_per_chunk=seq_len_default() * fs, chunks_per_utterance=CHUNKS, slots_per_gpu=slots,
+                cell=EXTRA.get('rnn_cell', 'gru'))
+
+
+def reference_trainer(device, batch, steps, warmup, autocast=False):
+    """The oracle port (plain torch ops, the reference's operator choice: fused GRU, Conv1d, ConvTranspose1d, Linear;
+    fp32, default TF32 flags) running the workload's model on ``batch`` slots of its chunk (same L) on ``device``.
+    step = forward + NLL + backward + AdamClipped, hidden state carried.  -> dict(value, ms_per_step, steps)."""
     from oracle import samplernn_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    seq_len = seq_len_default()
     spec = O.ModelSpec(RATIOS, LAYERS, HIDDEN, seq_len, cell=EXTRA.get('rnn_cell', 'gru'))
-    params = O.init_params(spec, conds_speaker_n=N_SPEAKERS)
+    params = {k: v.to(device) for k, v in O.init_params(spec, conds_speaker_n=N_SPEAKERS).items()}
     trainer = O.CpuTrainer(spec, params)
     wav, conds, spk = O.synthetic_utterances(spec, batch, warmup + steps)
+    wav, conds, spk = wav.to(device), conds.to(device), spk.to(device)
+    cuda = torch.device(device).type == 'cuda'
     times = []
     for k in range(warmup + steps):
         x, y, c = O.chunk_of(spec, wav, conds, k)
+        if cuda:
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        trainer.step(x, y, c, spk, [1] * batch if k == 0 else [0] * batch)
+        if autocast:
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                trainer.step(x, y, c, spk, [1] * batch if k == 0 else [0] * batch)
+        else:
+            trainer.step(x, y, c, spk, [1] * batch if k == 0 else [0] * batch)
+        if cuda:
+            torch.cuda.synchronize()
         if k >= warmup:
             times.append(time.perf_counter() - t0)
     per_step = batch * spec.receptive_field
     total = sum(times)
-    return dict(value=per_step * len(times) / total, ms_per_step=1e3 * total / len(times), cores=torch.get_num_threads(),
-                sample=f'oracle port (torch CPU fp32), same model, batch {batch} x L={seq_len} (RF={spec.receptive_field}) '
-                       f'chunks with carry, {len(times)} timed steps')
+    return dict(value=per_step * len(times) / total, ms_per_step=1e3 * total / len(times), steps=len(times),
+                rf=spec.receptive_field, seq_len=seq_len)
+
+
+def cpu_reference(steps, warmup, batch=CPU_SAMPLE_SLOTS):
+    torch.set_num_threads(os.cpu_count() or 1)
+    batch = min(batch, SLOTS_PER_GPU)
+    r = reference_trainer('cpu', batch, steps, warmup)
+    r['cores'] = torch.get_num_threads()
+    r['sample'] = (f'oracle port (torch CPU fp32, the reference\'s operators), the workload\'s model on {batch} of its '
+                   f'{SLOTS_PER_GPU} slots x its own chunk length L={r["seq_len"]} (RF={r["rf"]}) with carry, '
+                   f'{warmup} warm-up + {r["steps"]} timed steps of {batch * r["rf"]} samples')
+    return r
+
+
+def gpu_eager_baseline(dev, slots):
+    """Informational: the same oracle port moved to the GPU (``.to('cuda')`` is all the reference does, runner.py:27,50):
+    fp32, torch's default flags (matmul TF32 off, cuDNN TF32 on), cuDNN GRU, the full per-GPU chunk of the workload.
+    This is the 'reference-GPU-eager' denominator of BASELINE.json's target; it runs after every timed region."""
+    out = {}
+    for key, autocast in (('fp32', False), ('bf16_autocast', True)):
+        try:
+            torch.cuda.empty_cache()
+            r = reference_trainer(dev, slots, 2, 1, autocast=autocast)
+            out[key] = dict(value=r['value'], unit='samples/s', ms_per_step=r['ms_per_step'], steps=r['steps'],
+                            slots=slots)
+        except Exception as e:                                          # noqa: BLE001  (informational leg only)
+            out[key] = dict(unavailable=f'{type(e).__name__}: {str(e)[:160]}')
+    out['what'] = ('oracle port of the reference (plain torch ops: cuDNN GRU / Conv1d / ConvTranspose1d, cuBLAS Linear) on '
+                   'cuda:0, default torch flags, same chunk and slot count as the GPU arm, 1 warm-up + 2 timed steps; '
+                   'kind = port (the reference itself cannot travel to the GPU box)')
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    r = cpu_reference(max(1, min(args.steps, 6)), max(1, min(args.warmup, 2)))
+    r = cpu_reference(max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
     line = dict(impl='reference', metric=METRIC, value=r['value'], unit='samples/s', n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='weak',
-                vs_baseline=None, dtype='f32', data='synthetic', config=dict(workload=WORKLOAD),
+                warmup=args.warmup, ms_per_step=r['ms_per_step'], higher_is_better=True, scaling=scaling_kind(args),
+                vs_baseline=None, dtype='f32', data='synthetic', config=config_dict(args.gpus, slots_for(args)),
                 cpu_baseline=dict(value=r['value'], unit='samples/s', cores=r['cores'], kind='port', sample=r['sample']),
                 e2e=dict(value=r['value'], unit='samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
+
+
+def scaling_kind(args):
+    return 'strong' if args.global_batch else 'weak'
+
+
+def slots_for(args):
+    if args.global_batch:
+        if args.global_batch % args.gpus:
+            raise SystemExit(f'--global-batch {args.global_batch} is not divisible by --gpus {args.gpus}')
+        return args.global_batch // args.gpus
+    return SLOTS_PER_GPU
 
 
 # --------------------------------------------------------------------------------------------------
@@ -175,6 +246,32 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
+def recurrence_report(events, steps_timed, step_ms, b, hidden, lstm, peak_gbs):
+    """Per recurrent launch kind (direction x timesteps): time inside the step, us per timestep, share of the step and
+    the achieved algorithmic HBM rate.  Algorithmic bytes per (slot, timestep), bf16:
+      forward : read the 3H (4H LSTM) input pre-activations + write H outputs                      = 8 KB at H=1024
+      backward: read dL/dh (H) + the saved gates (4H; 5H LSTM) + h_{t-1} (H; LSTM c_{t-1} instead),
+                write both gate-gradient copies (2 x 3H; 2 x 4H LSTM)                                 = 24 KB at H=1024."""
+    g = 4 if lstm else 3
+    per = {'fwd': 2.0 * (g * hidden + hidden), 'bwd': 2.0 * (hidden + (g + 1) * hidden + hidden + 2 * g * hidden)}
+    out = []
+    for tag, evs in sorted(events.items()):
+        if not tag.startswith('rnn_'):
+            continue
+        kind, t = tag[4:7], int(tag.split('_T')[1])
+        ms = [a.elapsed_time(b_) for a, b_ in evs]
+        per_step_ms = sum(ms) / steps_timed                    # all launches of this kind in one training step
+        groups = max(1, round(len(ms) / steps_timed))          # slot groups (batch > 64) run one after the other
+        rows = min(b, 64 * groups) if groups > 1 else b
+        bytes_launch = per[kind] * (b / groups) * t
+        avg = sum(ms) / len(ms)
+        out.append(dict(kernel=f'gru_kernel<{kind}> T={t}' + (' (LSTM)' if lstm else ''), launches_per_step=groups,
+                        avg_launch_ms=avg, us_per_timestep=1e3 * avg / t, ms_per_step=per_step_ms,
+                        share_of_step=per_step_ms / step_ms, algorithmic_bytes_per_launch=bytes_launch,
+                        achieved_gbs=bytes_launch / (avg * 1e-3) / 1e9, frac_of_hbm_peak=bytes_launch / (avg * 1e-3) / 1e9 / peak_gbs))
+    return sorted(out, key=lambda d: -d['ms_per_step'])
+
+
 def run_gpu(args):
     import torch.distributed as dist
     from samplernn_pase_b200 import SampleRNNModel, ops, synthetic
@@ -195,7 +292,7 @@ def run_gpu(args):
     trainer = DataParallelTrainer(model, lr=1e-4)
     fs = int(model.frame_size)
     rf = int(model.receptive_field)
-    b = SLOTS_PER_GPU
+    b = slots_for(args)
     chunks = CHUNKS
     seq_len = seq_len_default()
     wav, conds, spk = synthetic.synthetic_utterances(fs, rf, seq_len, b, chunks, seed=4321 + rank, n_speakers=N_SPEAKERS)
@@ -237,23 +334,39 @@ def run_gpu(args):
         last = loop(n_steps, e2e, first)
         t1.record()
         barrier()
-        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        own = t0.elapsed_time(t1)
+        ms = torch.tensor([own], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms), float(last)
+        return float(ms), float(last), own
 
     loop(args.warmup, False, 0)
     sampler = ClockSampler(local) if rank == 0 else None
     ops.launch_count = 0
     ops.event_log = {}
-    ms, loss = timed(args.steps, False, args.warmup)
+    ms, loss, own_ms = timed(args.steps, False, args.warmup)
     launches = ops.launch_count
     events = ops.event_log
     ops.event_log = None
     clocks = sampler.stop() if sampler else None
     kernel_ms = [a.elapsed_time(b_) for a, b_ in events.get('comb_layer_fwd', [])]
     loop(1, True, args.warmup + args.steps)
-    ms_e2e, loss_e2e = timed(args.steps, True, args.warmup + args.steps + 1)
+    ms_e2e, loss_e2e, _ = timed(args.steps, True, args.warmup + args.steps + 1)
+
+    # data-parallel consistency: every rank must hold bit-identical parameters after the timed steps, and the per-rank
+    # step times show whether the max-over-ranks is one slow rank (clock skew) or all of them
+    ranks_equal, rank_ms = None, None
+    if world > 1:
+        chk = trainer.flat.flat_param.view(torch.int32).to(torch.int64).sum().reshape(1)
+        gathered = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(gathered, chk)
+        ranks_equal = all(int(g) == int(gathered[0]) for g in gathered)
+        t_own = torch.tensor([own_ms / args.steps], device=dev)
+        t_all = [torch.zeros_like(t_own) for _ in range(world)]
+        dist.all_gather(t_all, t_own)
+        rank_ms = [round(float(t), 3) for t in t_all]
+        if not ranks_equal:
+            raise SystemExit(f'rank parameter checksums differ after the timed steps: {[int(g) for g in gathered]}')
 
     if rank == 0:
         peaks = {}
@@ -261,47 +374,78 @@ def run_gpu(args):
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except OSError:
             pass
-        peak = peaks.get('bf16_tflops_sustained', 1400.0)
+        # fallbacks stated in /opt/skills/guides/B200_PROFILING.md when the driver-written file is absent
+        peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+        peak_tf_burst = peaks.get('bf16_tflops', 1700.0)
+        peak_gbs = peaks.get('hbm_gbs', 6500.0)
         m_rows, h = b * rf, HIDDEN[0]
         r0 = RATIOS[0]
+        step_ms = ms / args.steps
+        total = args.steps * global_rows
+        f_fwd = flops_per_sample_fwd()
+        lstm = EXTRA.get('rnn_cell') == 'lstm'
+        rec = recurrence_report(events, args.steps, own_ms / args.steps, b, h, lstm, peak_gbs)
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch from an `ncu --set full` capture AT THE BENCHED
+        # SIZE (profiles/r02_ncu_traffic.json, written by scripts/ncu_traffic.py from the capture); null if not captured
+        ncu = {}
+        try:
+            ncu = json.load(open(os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')))
+        except (OSError, ValueError):
+            pass
+        top = rec[0] if rec else None
+        roofline = None
+        if top:
+            roofline = dict(bound='hbm', kernel=top['kernel'] + f', {b} slots, H={h}: the dominant kernel '
+                            f'({100 * top["share_of_step"]:.1f} % of the step; all recurrent launches together '
+                            f'{100 * sum(r["share_of_step"] for r in rec):.1f} %)',
+                            achieved=top['achieved_gbs'], peak=peak_gbs, unit='GB/s', frac=top['frac_of_hbm_peak'],
+                            traffic=ncu.get(top['kernel'].split(' (')[0]) if args.workload == 'config2' and not args.global_batch else None,
+                            traffic_algorithmic=top['algorithmic_bytes_per_launch'], avg_launch_ms=top['avg_launch_ms'],
+                            us_per_timestep=top['us_per_timestep'], share_of_step=top['share_of_step'],
+                            note='latency-bound by construction (one grid-wide exchange of h per timestep): us_per_timestep is '
+                                 'the figure of merit, the HBM fraction shows how far from bandwidth-bound it is',
+                            peak_source='MEASURED_PEAKS.json hbm_gbs' if peaks else 'B200_PROFILING.md fallback')
         kc = r0 * 256 + h                                         # comb_layer forward GEMM as executed: A = [one-hot windows | upper]
         gemm_flops = 2.0 * m_rows * h * kc
         avg_ms = sum(kernel_ms) / max(len(kernel_ms), 1)
         achieved = gemm_flops / (avg_ms * 1e-3) / 1e12 if avg_ms else None
-        total = args.steps * global_rows
-        f_fwd = flops_per_sample_fwd()
-        cpu = cpu_reference(3, 1)
+        roofline_gemm = dict(
+            bound='tensor', kernel=f'gemm_kernel<256,NT,frame-term+relu epilogue> (comb_layer forward, m x {h} x {kc}: '
+                                   f'A = [one-hot windows | upper], tcgen05)',
+            achieved=achieved, peak=peak_tf, unit='TFLOP/s', frac=(achieved / peak_tf) if achieved else None,
+            frac_of_burst_peak=(achieved / peak_tf_burst) if achieved else None, peak_burst=peak_tf_burst,
+            traffic=ncu.get('comb_layer_fwd') if args.workload == 'config2' and not args.global_batch else None,
+            traffic_algorithmic=512.0 * m_rows + 2.0 * m_rows * 2 * h + 2.0 * (m_rows // r0) * h + 2.0 * h * kc,
+            launches_timed=len(kernel_ms), avg_launch_ms=avg_ms, share_of_step=avg_ms / step_ms if avg_ms else None,
+            note='half of the A operand is one-hot (1 non-zero in 256): it draws less power than the dense random operands '
+                 'the peaks were measured with, so the sustained-relative fraction can exceed 1; the burst-relative one cannot')
+        del trainer, model, resident
+        cpu = cpu_reference(2, 1)
+        eager = gpu_eager_baseline(dev, b) if not args.no_eager else None
         line = dict(
             metric=METRIC, value=total / (ms * 1e-3), unit='samples/s', n_gpus=world, steps=args.steps,
-            warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+            warmup=args.warmup, ms_per_step=step_ms, higher_is_better=True, scaling=scaling_kind(args), vs_baseline=None,
             dtype='bf16', data='synthetic',
-            config=dict(workload=WORKLOAD, slots_per_gpu=b, samples_per_step_per_gpu=b * rf, parallelism=f'dp{world}',
-                        l2_policy='inputs and activations per step (>10 GB) exceed the 126 MB L2; no flush needed',
-                        loss_mode='fused log-softmax+NLL epilogue', final_loss=loss,
-                        model_train_mflop_per_sample=3 * f_fwd / 1e6,
-                        model_tflops_achieved=3 * f_fwd * total / (ms * 1e-3) / 1e12),
+            config=config_dict(world, b),
+            run=dict(samples_per_step_per_gpu=b * rf, parallelism=f'dp{world}', global_batch=b * world,
+                     l2_policy='inputs and activations per step (>10 GB) exceed the 126 MB L2; no flush needed',
+                     loss_mode='fused log-softmax+NLL epilogue', final_loss=loss,
+                     model_train_mflop_per_sample=3 * f_fwd / 1e6,
+                     model_tflops_achieved=3 * f_fwd * total / (ms * 1e-3) / 1e12,
+                     model_tflops_frac_of_sustained_peak=3 * f_fwd * total / (ms * 1e-3) / 1e12 / peak_tf / world,
+                     rank_params_identical=ranks_equal, rank_ms_per_step=rank_ms),
             clocks=clocks,
             e2e=dict(value=total / (ms_e2e * 1e-3), unit='samples/s', ms_per_step=ms_e2e / args.steps,
                      h2d_bytes_per_step=sum(t.numel() * t.element_size() for t in host[0]), d2h_bytes_per_step=8,
                      final_loss=loss_e2e),
             gpu_launches=launches,
-            roofline=dict(bound='tensor', kernel=f'gemm_kernel<256,NT,epilogue frame-term+relu> (comb_layer forward, m x {h} x {kc}: A = [one-hot windows | upper], tcgen05)',
-                          achieved=achieved, peak=peak, unit='TFLOP/s', frac=(achieved / peak) if achieved else None,
-                          # dram__bytes_read+write of this kernel from `ncu --set full` at 262 144 rows
-                          # (profiles/r01_hot_kernels_ncu.txt [3]) scaled to this launch's rows; algorithmic = A + C + W
-                          traffic=NCU_BYTES_AT_262144 * m_rows / 262144.0 if NCU_BYTES_AT_262144 else None,
-                          # algorithmic = one-hot codes (512 B per sample, the r0 overlapping windows re-read them through L2) +
-                          # upper + C + frame-rate term + weights
-                          traffic_algorithmic=512.0 * m_rows + 2.0 * m_rows * 2 * h + 2.0 * (m_rows // r0) * h + 2.0 * h * kc,
-                          launches_timed=len(kernel_ms), avg_launch_ms=avg_ms,
-                          peak_source='MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step); half of this '
-                                      'GEMM\'s A operand is one-hot (1 non-zero in 256), which draws less power than the dense random '
-                                      'operands the peak was measured with, so frac can exceed 1 (burst peak: 1694)'
-                          if peaks else 'fallback'),
+            roofline=roofline, roofline_gemm=roofline_gemm, recurrence=rec,
             cpu_baseline=dict(value=cpu['value'], unit='samples/s', cores=cpu['cores'], kind='port', sample=cpu['sample']),
+            gpu_eager_baseline=eager,
         )
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -312,6 +456,10 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='config2', choices=['config1', 'config2', 'config3', 'config4'])
+    ap.add_argument('--global-batch', type=int, default=0,
+                    help='fix the GLOBAL number of slots (strong scaling: slots per GPU = global / N) instead of the '
+                         'per-GPU slot count of the workload')
+    ap.add_argument('--no-eager', action='store_true', help='skip the informational GPU-eager leg')
     args = ap.parse_args()
     select_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup

@@ -29,7 +29,7 @@ extern "C" {
 #define SRNN_ERR_ARG (-1)     /* bad argument (shape, alignment, null pointer) */
 #define SRNN_ERR_DEVICE (-2)  /* not an sm_100 device / driver entry point missing */
 
-#define SRNN_ABI_VERSION 3
+#define SRNN_ABI_VERSION 4
 
 typedef void* srnn_stream_t; /* cudaStream_t */
 
@@ -48,9 +48,10 @@ int srnn_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * q_levels (the reference would raise an index error downstream; SURVEY trap 3). */
 int srnn_quantize_ulaw(const float* x, int64_t n, int64_t* idx_i64, uint8_t* idx_u8, int32_t* overflow_count,
                        srnn_stream_t stream);
-/* quantize_linear (utils.py:48-54) with per-row min/max; rows x cols input. */
-int srnn_quantize_linear(const float* x, int64_t rows, int64_t cols, int64_t* idx_i64, uint8_t* idx_u8,
-                         srnn_stream_t stream);
+/* quantize_linear (utils.py:48-54) with per-row min/max; rows x cols input; idx = long(norm * (q_levels - 1e-2) +
+ * 0.005) with every step rounded to fp32 like the reference.  A constant row (0/0 in the reference) maps to 0. */
+int srnn_quantize_linear(const float* x, int64_t rows, int64_t cols, int32_t q_levels, int64_t* idx_i64,
+                         uint8_t* idx_u8, srnn_stream_t stream);
 /* dequantize (utils.py:56-57,67-73) through a 256(+1)-entry table: out[i] = lut[idx[i]].
  * Exactly one of idx_i64 / idx_u8 is non-null; exactly one of out_f32 / out_bf16 is non-null. */
 int srnn_dequantize_lut(const int64_t* idx_i64, const uint8_t* idx_u8, int64_t n, const float* lut, float* out_f32,
@@ -76,6 +77,11 @@ int srnn_weight_prep_bwd(const float* dw, const int64_t* s, const float* v, cons
 /* fp32 (rows, cols) with leading dim ld_in -> bf16 (rows, cols_pad) zero padded, leading dim ld_out */
 int srnn_pad_cast_bf16(const float* in, int64_t rows, int32_t cols, int64_t ld_in, void* out_bf16, int32_t cols_pad,
                        int64_t ld_out, srnn_stream_t stream);
+/* fp32 (rows, cols) -> two bf16 matrices with in = hi + lo up to 2^-17 relative (hi = bf16(in), lo = bf16(in - hi)),
+ * both (rows, cols_pad) zero padded with leading dim ld_out.  Used where an fp32 intermediate feeds another tensor-core
+ * contraction and a single bf16 rounding would be the dominant error (the folded embedding-table gradients). */
+int srnn_split_bf16(const float* in, int64_t rows, int32_t cols, int64_t ld_in, void* hi_bf16, void* lo_bf16,
+                    int32_t cols_pad, int64_t ld_out, srnn_stream_t stream);
 /* bf16 (rows, cols) -> fp32, out[r, c] (+)= in[r, c]  (accumulate != 0 adds) */
 int srnn_bf16_to_f32(const void* in_bf16, int64_t rows, int32_t cols, int64_t ld_in, float* out, int64_t ld_out,
                      int32_t accumulate, srnn_stream_t stream);

@@ -213,9 +213,16 @@ def frame_tier(p: Params, n: int, frames: Tensor, conds: Tensor, upper: Optional
     b, t, _ = frames.shape
     rep = t // conds.shape[1]
     c = conds.repeat_interleave(rep, dim=1) if rep != 1 else conds                  # model.py:142-145
-    wx = weight_norm(p[pre + 'x_expand.weight_g'], p[pre + 'x_expand.weight_v'])[:, :, 0]
-    wc = weight_norm(p[pre + 'conds_expand.weight_g'], p[pre + 'conds_expand.weight_v'])[:, :, 0]
-    u = frames @ wx.t() + p[pre + 'x_expand.bias'] + c @ wc.t() + p[pre + 'conds_expand.bias']  # :146-147
+    lib = fast == 'library'          # the operators the reference itself launches (Conv1d / ConvTranspose1d -> cuDNN / oneDNN)
+    if lib:
+        wx3 = weight_norm(p[pre + 'x_expand.weight_g'], p[pre + 'x_expand.weight_v'])
+        wc3 = weight_norm(p[pre + 'conds_expand.weight_g'], p[pre + 'conds_expand.weight_v'])
+        u = F.conv1d(frames.permute(0, 2, 1), wx3, p[pre + 'x_expand.bias']).permute(0, 2, 1) + \
+            F.conv1d(c.permute(0, 2, 1), wc3, p[pre + 'conds_expand.bias']).permute(0, 2, 1)      # model.py:146-147
+    else:
+        wx = weight_norm(p[pre + 'x_expand.weight_g'], p[pre + 'x_expand.weight_v'])[:, :, 0]
+        wc = weight_norm(p[pre + 'conds_expand.weight_g'], p[pre + 'conds_expand.weight_v'])[:, :, 0]
+        u = frames @ wx.t() + p[pre + 'x_expand.bias'] + c @ wc.t() + p[pre + 'conds_expand.bias']  # :146-147
     if upper is not None:
         u = u + upper                                                                # model.py:148
     layers = h0.shape[0]
@@ -238,8 +245,13 @@ def frame_tier(p: Params, n: int, frames: Tensor, conds: Tensor, upper: Optional
     # learned upsampling: ConvTranspose1d(H,H,r,stride=r) + upsample_bias(H,r)   model.py:153-155
     wu = weight_norm(p[pre + 'upsample.weight_g'], p[pre + 'upsample.weight_v'])     # (H_in, H_out, r)
     r = wu.shape[2]
-    up = torch.einsum('bti,ioj->btjo', u, wu) + p[pre + 'upsample_bias'].t()         # (B,T,r,H)
-    up = up.reshape(b, t * r, -1)
+    if lib:
+        bias = p[pre + 'upsample_bias'].unsqueeze(0).unsqueeze(2).expand(b, wu.shape[1], t, r).contiguous() \
+            .view(b, wu.shape[1], t * r)                                             # model.py:153-154
+        up = (F.conv_transpose1d(u.permute(0, 2, 1), wu, stride=r) + bias).permute(0, 2, 1)   # model.py:155
+    else:
+        up = torch.einsum('bti,ioj->btjo', u, wu) + p[pre + 'upsample_bias'].t()     # (B,T,r,H)
+        up = up.reshape(b, t * r, -1)
     if cell == 'gru':
         return up, torch.stack(hn)
     return up, torch.stack(hn), torch.stack(cn)
@@ -248,10 +260,26 @@ def frame_tier(p: Params, n: int, frames: Tensor, conds: Tensor, upper: Optional
 # --------------------------------------------------------------------------------------
 # Sample-level MLP (model.py:159-203)
 # --------------------------------------------------------------------------------------
-def sample_level(p: Params, xs: Tensor, conds: Tensor, upper: Tensor) -> Tensor:
-    """``xs`` (B,RF+r0-1) int64, ``conds`` (B,L,C), ``upper`` (B,RF,H) -> log-probs (B,RF,Q)."""
+def sample_level(p: Params, xs: Tensor, conds: Tensor, upper: Tensor, fast=False) -> Tensor:
+    """``xs`` (B,RF+r0-1) int64, ``conds`` (B,L,C), ``upper`` (B,RF,H) -> log-probs (B,RF,Q).
+    ``fast == 'library'``: the same arithmetic through the operators the reference launches (Conv1d for the
+    embedding conv and every 1x1 projection, Linear for comb_layer; model.py:188-203) - used for timing."""
     pre = 'sample_layer.'
     b, rf, h = upper.shape
+    if fast == 'library':
+        emb = p[pre + 'emb_layer.weight'][xs.reshape(-1)].view(b, -1, p[pre + 'emb_layer.weight'].shape[1])
+        we = weight_norm(p[pre + 'emb_layer_expand.weight_g'], p[pre + 'emb_layer_expand.weight_v'])
+        e = F.conv1d(emb.permute(0, 2, 1), we)                                       # model.py:193  (B,H,RF)
+        rep = rf // conds.shape[1]
+        c = conds.unsqueeze(2).expand(b, conds.shape[1], rep, conds.shape[2]).reshape(b, rf, conds.shape[2])
+        c = F.conv1d(c.permute(0, 2, 1), p[pre + 'conds_expand.weight'], p[pre + 'conds_expand.bias'])
+        cat = torch.cat((e.permute(0, 2, 1), c.permute(0, 2, 1), upper), dim=2)
+        h1 = F.relu(F.linear(cat, p[pre + 'comb_layer.weight'], p[pre + 'comb_layer.bias']))
+        w2 = weight_norm(p[pre + 'comb_layer_expand.weight_g'], p[pre + 'comb_layer_expand.weight_v'])
+        h2 = F.relu(F.conv1d(h1.permute(0, 2, 1), w2, p[pre + 'comb_layer_expand.bias']))
+        w3 = weight_norm(p[pre + 'adapt.weight_g'], p[pre + 'adapt.weight_v'])
+        logits = F.conv1d(h2, w3, p[pre + 'adapt.bias'])
+        return F.log_softmax(logits.permute(0, 2, 1), dim=2)
     emb = p[pre + 'emb_layer.weight'][xs]                                            # model.py:192
     we = weight_norm(p[pre + 'emb_layer_expand.weight_g'], p[pre + 'emb_layer_expand.weight_v'])  # (H,Q,r0)
     r0 = we.shape[2]
@@ -355,7 +383,7 @@ def forward_indices(p: Params, spec: ModelSpec, xq: Tensor, yq: Tensor, utt_cond
         new_state.h[n] = hn.detach()                                                 # model.py:276
         new_state.valid[n] = [r in (0, 1) for r in reset]                            # model.py:245-250
     xs = xq[:, fs_top - spec.ratios[0]:]                                             # model.py:279
-    logp = sample_level(p, xs, conds, upper)                                         # model.py:280
+    logp = sample_level(p, xs, conds, upper, fast=fast)                              # model.py:280
     keep = torch.tensor([r != 2 for r in reset])
     return logp[keep], yq[keep], new_state, {'xq': xq, 'yq': yq, 'conds': conds, 'upper': upper}  # :283-284
 
@@ -485,10 +513,13 @@ def chunk_of(spec: ModelSpec, wav: Tensor, conds: Tensor, k: int):
 
 
 class CpuTrainer:
-    """forward + NLL + backward + AdamClipped on CPU, for the ``cpu_baseline`` timing."""
+    """forward + NLL + backward + AdamClipped with plain torch ops on whatever device the parameters live on:
+    the ``cpu_baseline`` / ``--impl reference`` timing (CPU) and the informational GPU-eager leg (cuda) of bench.py.
+    ``fast='library'`` runs the reference's own operator choice (fused GRU, Conv1d, ConvTranspose1d, Linear)."""
 
-    def __init__(self, spec: ModelSpec, params: Params, lr: float = 1e-4):
+    def __init__(self, spec: ModelSpec, params: Params, lr: float = 1e-4, fast='library'):
         self.spec = spec
+        self.fast = fast if spec.cell == 'gru' else True
         self.params = {k: v.clone().requires_grad_(True) for k, v in params.items()}
         self.m = [torch.zeros_like(v) for v in self.params.values()]
         self.v = [torch.zeros_like(v) for v in self.params.values()]
@@ -500,7 +531,7 @@ class CpuTrainer:
         for v in self.params.values():
             v.grad = None
         logp, tgt, self.state, _ = forward(self.params, self.spec, x, y, conds, speakers, reset, self.state,
-                                            carry=True, fast=True)
+                                            carry=True, fast=self.fast)
         loss = nll(logp, tgt)
         loss.backward()
         self.t += 1

@@ -62,12 +62,13 @@ SIGNATURES = {
     'srnn_abi_version': [],
     'srnn_device_info': [P, P, P],
     'srnn_quantize_ulaw': [P, I64, P, P, P, P],
-    'srnn_quantize_linear': [P, I64, I64, P, P, P],
+    'srnn_quantize_linear': [P, I64, I64, I32, P, P, P],
     'srnn_dequantize_lut': [P, P, I64, P, P, P, P],
     'srnn_onehot_rows': [P, I64, I32, P, P],
     'srnn_weight_prep': [P, P, I32, I32, I32, P, P, P, P, P, P],
     'srnn_weight_prep_bwd': [P, P, P, P, P, I32, I32, I32, P, P, P],
     'srnn_pad_cast_bf16': [P, I64, I32, I64, P, I32, I64, P],
+    'srnn_split_bf16': [P, I64, I32, I64, P, P, I32, I64, P],
     'srnn_bf16_to_f32': [P, I64, I32, I64, P, I64, I32, P],
     'srnn_mixer_input': [P, P, P, I32, I32, I32, I32, P, I32, P],
     'srnn_mixer_input_bwd': [P, P, I32, I32, I32, I32, P, P],
@@ -109,7 +110,7 @@ def load(path=None):
         fn.restype = C.c_int
     lib.srnn_last_error.argtypes = []
     lib.srnn_last_error.restype = C.c_char_p
-    if lib.srnn_abi_version() != 3:
+    if lib.srnn_abi_version() != 4:
         raise RuntimeError('libsrnn_b200.so ABI version mismatch')
     _lib = lib
     return lib

@@ -73,7 +73,7 @@ __global__ void quantize_ulaw_kernel(const float* __restrict__ x, long long n, l
 }
 
 // quantize_linear (utils.py:48-54) with per-row min/max: one CTA per row.
-__global__ void quantize_linear_kernel(const float* __restrict__ x, long long cols, long long* __restrict__ o64,
+__global__ void quantize_linear_kernel(const float* __restrict__ x, long long cols, float scale, long long* __restrict__ o64,
                                        uint8_t* __restrict__ o8) {
   __shared__ float smin[32], smax[32];
   const float* row = x + blockIdx.x * cols;
@@ -101,9 +101,10 @@ __global__ void quantize_linear_kernel(const float* __restrict__ x, long long co
   for (long long i = threadIdx.x; i < cols; i += blockDim.x) {
     float y = __fsub_rn(row[i], lo);
     y = __fdiv_rn(y, range);
-    y = __fmul_rn(y, 255.99f);              // q_levels - 1e-2 as fp32
+    y = __fmul_rn(y, scale);                // q_levels - 1e-2, rounded to fp32 like the reference's in-place multiply
     y = __fadd_rn(y, 0.005f);
-    const long long q = static_cast<long long>(y);
+    // a constant row is 0/0 in the reference (NaN -> an undefined integer); here it maps to index 0
+    const long long q = range > 0.f ? static_cast<long long>(y) : 0ll;
     if (o64) o64[blockIdx.x * cols + i] = q;
     if (o8) o8[blockIdx.x * cols + i] = static_cast<uint8_t>(q < 0 ? 0 : (q > 255 ? 255 : q));
   }
@@ -218,6 +219,20 @@ __global__ void pad_cast_kernel(const float* __restrict__ in, long long rows, in
   if (r >= rows) return;
   const int c = static_cast<int>(g - r * cols_pad);
   out[r * ld_out + c] = __float2bfloat16_rn(c < cols ? in[r * ld_in + c] : 0.f);
+}
+
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): two bf16 terms carry 16 mantissa bits of an fp32 value
+__global__ void split_bf16_kernel(const float* __restrict__ in, long long rows, int cols, long long ld_in,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int cols_pad,
+                                  long long ld_out) {
+  const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long r = g / cols_pad;
+  if (r >= rows) return;
+  const int c = static_cast<int>(g - r * cols_pad);
+  const float x = c < cols ? in[r * ld_in + c] : 0.f;
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  hi[r * ld_out + c] = h;
+  lo[r * ld_out + c] = __float2bfloat16_rn(x - __bfloat162float(h));
 }
 
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, long long rows, int cols, long long ld_in,
@@ -460,10 +475,13 @@ extern "C" int srnn_quantize_ulaw(const float* x, int64_t n, int64_t* o64, uint8
   return SRNN_OK;
 }
 
-extern "C" int srnn_quantize_linear(const float* x, int64_t rows, int64_t cols, int64_t* o64, uint8_t* o8,
+extern "C" int srnn_quantize_linear(const float* x, int64_t rows, int64_t cols, int32_t q_levels, int64_t* o64, uint8_t* o8,
                                     srnn_stream_t s) {
   SRNN_CHECK_ARG(x && rows > 0 && cols > 0 && (o64 || o8), "quantize_linear: bad arguments");
-  quantize_linear_kernel<<<static_cast<unsigned>(rows), 256, 0, ST(s)>>>(x, cols, reinterpret_cast<long long*>(o64), o8);
+  SRNN_CHECK_ARG(q_levels >= 2 && (o8 == nullptr || q_levels <= 256),
+                 "quantize_linear: q_levels must be >= 2 (and <= 256 when uint8 indices are requested), got %d", q_levels);
+  const float scale = static_cast<float>(static_cast<double>(q_levels) - 1e-2);
+  quantize_linear_kernel<<<static_cast<unsigned>(rows), 256, 0, ST(s)>>>(x, cols, scale, reinterpret_cast<long long*>(o64), o8);
   SRNN_CUDA(cudaGetLastError());
   return SRNN_OK;
 }
@@ -516,6 +534,16 @@ extern "C" int srnn_pad_cast_bf16(const float* in, int64_t rows, int32_t cols, i
   if (rows == 0) return SRNN_OK;
   pad_cast_kernel<<<blocks_for(rows * cols_pad, 256), 256, 0, ST(s)>>>(in, rows, cols, ld_in,
                                                                       static_cast<__nv_bfloat16*>(out), cols_pad, ld_out);
+  SRNN_CUDA(cudaGetLastError());
+  return SRNN_OK;
+}
+
+extern "C" int srnn_split_bf16(const float* in, int64_t rows, int32_t cols, int64_t ld_in, void* hi, void* lo,
+                               int32_t cols_pad, int64_t ld_out, srnn_stream_t s) {
+  SRNN_CHECK_ARG(in && hi && lo && rows >= 0 && cols > 0 && cols_pad >= cols, "split_bf16: bad arguments");
+  if (rows == 0) return SRNN_OK;
+  split_bf16_kernel<<<blocks_for(rows * cols_pad, 256), 256, 0, ST(s)>>>(
+      in, rows, cols, ld_in, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), cols_pad, ld_out);
   SRNN_CUDA(cudaGetLastError());
   return SRNN_OK;
 }

@@ -409,18 +409,26 @@ class SampleLevelFn(torch.autograd.Function):
         # the r0*Q-wide windows at a row stride of Q, read in place)
         gt = _zeros(r0 * q, h, device=dev)
         ops.gemm_tn(onehot, dh1, gt, r0 * q, h, rf, q, h, h, batch=b, a_bs=w * q, b_bs=rf * h)
-        gtb = ops.to_bf16(gt)
-        ops.gemm_tn(gtb, tt, d_cw, h, h, r0 * q, h, h, 3 * h)                # d W_e[o',o] = sum_{kQ+q} gt[.,o'] tt[.,o]
+        # gt and G are fp32 sums over up to B*RF rows that feed further contractions: they enter those as hi + lo bf16
+        # pairs (two accumulating passes / a K-concatenated operand), so no extra bf16 rounding sits in the chain
+        gt_hi, gt_lo = ops.split_bf16(gt)
+        for part in (gt_hi, gt_lo):
+            ops.gemm_tn(part, tt, d_cw, h, h, r0 * q, h, h, 3 * h)           # d W_e[o',o] = sum_{kQ+q} gt[.,o'] tt[.,o]
         # G[q, k*H+o] = sum_o' gt[kQ+q,o'] W_e[o',o]: the gradient w.r.t. the (transposed) embedding + conv table
         g = _empty(q, r0 * h, dtype=F32, device=dev)
+        gt2 = torch.cat((gt_hi, gt_lo), dim=1)                               # (r0*Q, 2H): [hi | lo] along K
+        we_t2 = torch.cat((wcomb_t[:h], wcomb_t[:h]), dim=1)                 # (H, 2H): W_e^T twice
         for k in range(r0):
-            ops.gemm_nt(gtb[k * q:], wcomb_t, g[:, k * h:], q, h, h, h, h, r0 * h)
-        gb = ops.to_bf16(g)
+            ops.gemm_nt(gt2[k * q:], we_t2, g[:, k * h:], q, h, 2 * h, 2 * h, 2 * h, r0 * h)
+        g_hi, g_lo = ops.split_bf16(g)
         d_emb = _empty(q, q, dtype=F32, device=dev)
-        ops.gemm_nt(gb, we_t, d_emb, q, q, r0 * h, r0 * h, r0 * h, q)
+        g2 = torch.cat((g_hi, g_lo), dim=1)                                  # (Q, 2*r0*H)
+        we_t_2 = torch.cat((we_t, we_t), dim=1)
+        ops.gemm_nt(g2, we_t_2, d_emb, q, q, 2 * r0 * h, 2 * r0 * h, 2 * r0 * h, q)
         dwe = _zeros(h, r0 * q, device=dev)
-        for k in range(r0):
-            ops.gemm_tn(gb[:, k * h:], e_b, dwe[:, k * q:], h, q, q, r0 * h, q, r0 * q)
+        for part in (g_hi, g_lo):
+            for k in range(r0):
+                ops.gemm_tn(part[:, k * h:], e_b, dwe[:, k * q:], h, q, q, r0 * h, q, r0 * q)
         d_ev, d_eg = ops.weight_prep_bwd(dwe, (r0 * q, 1, q), ev, eg, inv_e, (h, q, r0))
         return (None, dconds.view(b, l, c), dupper.view(b, rf, h), None, None,
                 d_emb, d_eg.view_as(eg), d_ev, dwcs[:, :c].contiguous().view(h, c, 1), d_csb, d_cw, d_cbias,

@@ -18,15 +18,29 @@ import torch
 
 
 class SequentialChunkLoader:
-    def __init__(self, dataset, batch_size, frame_size, sequence_length, conds_width=43, pin_memory=True, seed=None):
+    """``shuffle=True`` reproduces the reference's epoch order: the utterance order is shuffled in place at the start of
+    every epoch (``dataset.shuffle_utterances()``, loader.py:37 / dataset.py:56-57) and free slots are drawn with
+    ``random.choice`` BEFORE the next item is fetched (loader.py:55-57), with the same generator calls in the same
+    order - so ``SequentialChunkLoader(..., shuffle=True, seed=s)`` yields exactly the batches of the reference loader
+    after ``random.seed(s)`` (``tests/golden/loader_schedule.npz``, generated from the imported reference).
+
+    ``device``: slot buffers live on that device - an utterance is copied host->device ONCE when it enters a slot and
+    every step's ``(x, y, utt_conds)`` is assembled there by three gather launches, so the training loop issues no
+    per-step host->device copy at all; ``reset`` stays a CPU int64 tensor as the model expects (loader.py:67,81)."""
+
+    def __init__(self, dataset, batch_size, frame_size, sequence_length, conds_width=43, pin_memory=True, seed=None,
+                 shuffle=False, device=None):
         self.dataset = dataset
         self.batch_size = batch_size
         self.frame_size = frame_size
         self.sequence_length = sequence_length
         self.receptive_field = frame_size * sequence_length
         self.conds_width = conds_width
-        self.pin_memory = pin_memory and torch.cuda.is_available()
+        self.device = torch.device(device) if device is not None else None
+        self.pin_memory = pin_memory and torch.cuda.is_available() and self.device is None
         self.rng = random.Random(seed)
+        self.shuffle = shuffle
+        self.order = list(range(len(dataset))) if shuffle else None
 
     def iteration_sizes(self):
         """loader.py:83-84."""
@@ -36,12 +50,28 @@ class SequentialChunkLoader:
         t = torch.zeros(*shape)
         return t.pin_memory() if self.pin_memory else t
 
+    def _items(self):
+        if self.order is None:
+            return iter(self.dataset)
+        self.rng.shuffle(self.order)                # loader.py:37: before any slot is drawn; in place and cumulative
+        return (self.dataset[i] for i in list(self.order))     # over epochs like dataset.py:56-57
+
+    def _to_slot(self, wav, conds, info):
+        wav = torch.as_tensor(wav, dtype=torch.float32)
+        conds = torch.as_tensor(conds, dtype=torch.float32)
+        if self.device is not None:
+            wav, conds = wav.to(self.device, non_blocking=True), conds.to(self.device, non_blocking=True)
+        return [wav, conds, info]
+
     def __iter__(self):
         x_len, y_len, l = self.iteration_sizes()
-        it = iter(self.dataset)
+        it = self._items()
         slots = [None] * self.batch_size          # [wav, conds, info] per slot
         flags = [None] * self.batch_size          # True new / False continuing / None empty
         exhausted = False
+        if self.device is not None:
+            zx = torch.zeros(x_len, device=self.device)
+            zc = torch.zeros(l, self.conds_width, device=self.device)
         while True:
             # loader.py:43-50: continuing slots lose the reset flag; drained slots are freed
             for i, item in enumerate(slots):
@@ -50,32 +80,40 @@ class SequentialChunkLoader:
                 flags[i] = False
                 if item[1].shape[0] < l:
                     slots[i], flags[i] = None, None
-            # loader.py:52-60: refill random free slots
+            # loader.py:52-60: refill random free slots (the slot is drawn before the item is fetched, like the reference)
             while not exhausted and any(s is None for s in slots):
+                free = [i for i, s in enumerate(slots) if s is None]
+                i = self.rng.choice(free)
                 try:
                     wav, conds, info = next(it)
                 except StopIteration:
                     exhausted = True
                     break
-                if conds.shape[0] < l:
+                if conds.shape[0] < l:              # (the reference would fail in torch.stack on such an item)
                     continue
-                free = [i for i, s in enumerate(slots) if s is None]
-                i = self.rng.choice(free)
-                slots[i] = [torch.as_tensor(wav, dtype=torch.float32), torch.as_tensor(conds, dtype=torch.float32), info]
+                slots[i] = self._to_slot(wav, conds, info)
                 flags[i] = True
             if all(s is None for s in slots):
                 return                              # the reference never gets here (loader.py:29-34)
-            x = self._alloc(self.batch_size, x_len)
-            y = self._alloc(self.batch_size, y_len)
-            c = self._alloc(self.batch_size, l, self.conds_width)
             reset = torch.tensor([2 if f is None else int(f) for f in flags])
             info = [s[2] if s is not None else None for s in slots]
+            if self.device is not None:
+                # device-resident slots: three gathers, no host->device traffic in the step
+                x = torch.stack([s[0][:x_len] if s is not None else zx for s in slots])                    # loader.py:76
+                y = torch.stack([s[0][self.frame_size:self.frame_size + y_len] if s is not None else zx[:y_len]
+                                 for s in slots])                                                           # loader.py:77
+                c = torch.stack([s[1][:l] if s is not None else zc for s in slots])
+            else:
+                x = self._alloc(self.batch_size, x_len)
+                y = self._alloc(self.batch_size, y_len)
+                c = self._alloc(self.batch_size, l, self.conds_width)
             for i, item in enumerate(slots):
                 if item is None:
                     continue
-                x[i] = item[0][:x_len]                                              # loader.py:76
-                y[i] = item[0][self.frame_size:self.frame_size + y_len]             # loader.py:77
-                c[i] = item[1][:l]
+                if self.device is None:
+                    x[i] = item[0][:x_len]                                              # loader.py:76
+                    y[i] = item[0][self.frame_size:self.frame_size + y_len]             # loader.py:77
+                    c[i] = item[1][:l]
                 item[0] = item[0][y_len:]                                           # loader.py:79-80
                 item[1] = item[1][l:]
             yield x, y, c, reset, info

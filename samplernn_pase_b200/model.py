@@ -267,6 +267,30 @@ class SampleRNNModel(torch.nn.Module):
     def reset_states(self):
         self._init_rnn_states(0)
 
+    # The carried hidden state is plain module state in the reference (model.py:210,237), so a Skeltorch checkpoint
+    # (runner.py:41-45) loses it and a resumed run restarts every stream from ``rnn_h0``.  These two calls let a runner
+    # persist it NEXT TO ``state_dict()`` (opt-in: the parameter state_dict keeps exactly the reference's keys).
+    def carry_state_dict(self):
+        out = {}
+        for n in range(len(self.frames_layers)):
+            if self._state[n] is not None:
+                out[f'frames_layers.{n}.h'] = self._state[n].detach().cpu()
+            if self._state_c[n] is not None:
+                out[f'frames_layers.{n}.c'] = self._state_c[n].detach().cpu()
+            out[f'frames_layers.{n}.valid'] = torch.tensor(self._state_valid[n], dtype=torch.bool)
+        return out
+
+    def load_carry_state_dict(self, sd):
+        dev = next(self.parameters()).device
+        batch = len(sd['frames_layers.0.valid']) if 'frames_layers.0.valid' in sd else 0
+        self._init_rnn_states(batch)
+        for n in range(len(self.frames_layers)):
+            h, c = sd.get(f'frames_layers.{n}.h'), sd.get(f'frames_layers.{n}.c')
+            self._state[n] = h.to(dev, torch.float32).contiguous() if h is not None else None
+            self._state_c[n] = c.to(dev, torch.float32).contiguous() if c is not None else None
+            if f'frames_layers.{n}.valid' in sd:
+                self._state_valid[n] = [bool(v) for v in sd[f'frames_layers.{n}.valid'].tolist()]
+
     def forward(self, x, y, utt_conds, info, reset):
         b, t, _ = utt_conds.size()
         dev = utt_conds.device

@@ -75,14 +75,14 @@ def quantize_ulaw(x, want_i64=True, want_u8=False, overflow=None):
     return o64, o8
 
 
-def quantize_linear(x, want_i64=True, want_u8=False):
+def quantize_linear(x, want_i64=True, want_u8=False, q_levels=256):
     _need(x, F32, 'quantize_linear x')
     x = x.contiguous()
     cols = x.shape[-1]
     rows = x.numel() // cols
     o64 = torch.empty(x.shape, dtype=torch.int64, device=x.device) if want_i64 else None
     o8 = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_u8 else None
-    call('srnn_quantize_linear', ptr(x), rows, cols, ptr(o64), ptr(o8), stream())
+    call('srnn_quantize_linear', ptr(x), rows, cols, int(q_levels), ptr(o64), ptr(o8), stream())
     _count()
     return o64, o8
 
@@ -172,6 +172,19 @@ def to_bf16(x):
     out = torch.empty(x.shape, dtype=BF16, device=x.device)
     pad_cast_bf16(x, rows, cols, cols, out, cols, cols)
     return out
+
+
+def split_bf16(x):
+    """fp32 (rows, cols) contiguous -> (hi, lo) bf16 tensors with x = hi + lo to 16 mantissa bits."""
+    x = x.contiguous()
+    _need(x, F32, 'split_bf16 x')
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    hi = torch.empty(x.shape, dtype=BF16, device=x.device)
+    lo = torch.empty(x.shape, dtype=BF16, device=x.device)
+    call('srnn_split_bf16', ptr(x), rows, cols, cols, ptr(hi), ptr(lo), cols, cols, stream())
+    _count()
+    return hi, lo
 
 
 def bf16_to_f32(x, rows, cols, ld_in, out, ld_out, accumulate=False):
@@ -333,7 +346,8 @@ def _gru_call(name, batch, steps, hidden, cell=0, **bufs):
         a.units_per_cta = gru_units_per_cta
         a.debug_ts = gru_debug_ts.data_ptr() if gru_debug_ts is not None else None
         _lib.profile_note = f'B={nb} T={steps} H={hidden}' + (' lstm' if cell else '')
-        call(name, C.byref(a), stream())
+        with timed(f"{'rnn_fwd' if name == 'srnn_gru_forward' else 'rnn_bwd'}_T{steps}"):
+            call(name, C.byref(a), stream())
         _count(1 if steps == 1 else 2)
 
 

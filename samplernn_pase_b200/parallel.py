@@ -63,6 +63,64 @@ class FlatBuffers:
         self.flat_grad.zero_()
 
 
+class FlatAdamClipped(torch.optim.Optimizer):
+    """``AdamClipped`` (optimizer.py:6-14) over the flat buffers: clamp + Adam for ALL parameters in one launch.
+
+    It is a real ``torch.optim.Optimizer``: ``param_groups[0]['lr']`` is read at every step, so
+    ``ReduceLROnPlateau(trainer.optimizer)`` (runner.py:34-39,58-59) works, and ``state_dict()`` /
+    ``load_state_dict()`` use torch.optim.Adam's layout (per-parameter ``step``, ``exp_avg``, ``exp_avg_sq``), so a
+    checkpoint written by the reference's ``AdamClipped`` resumes here and vice versa.  The per-parameter moments are
+    views of two flat buffers."""
+
+    def __init__(self, flat: 'FlatBuffers', lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
+                        capturable=False, differentiable=False, fused=None)
+        super().__init__(flat.params, defaults)
+        self.flat = flat
+        self.exp_avg = torch.zeros_like(flat.flat_param)
+        self.exp_avg_sq = torch.zeros_like(flat.flat_param)
+        self.steps = 0
+        self._bind_state()
+
+    def _bind_state(self):
+        self._step_t = torch.tensor(float(self.steps))            # one shared CPU scalar: a single increment per step
+        for p, off in zip(self.flat.params, self.flat.offsets):
+            n = p.numel()
+            self.state[p] = dict(step=self._step_t, exp_avg=self.exp_avg[off: off + n].view_as(p),
+                                 exp_avg_sq=self.exp_avg_sq[off: off + n].view_as(p))
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale=1.0):
+        from . import ops
+        group = self.param_groups[0]
+        if group.get('amsgrad') or group.get('weight_decay') or group.get('maximize'):
+            raise RuntimeError('AdamClipped: amsgrad / weight_decay / maximize are not part of the reference path')
+        self.steps += 1
+        self._step_t += 1
+        ops.adam_clipped(self.flat.flat_param, self.flat.flat_grad, self.exp_avg, self.exp_avg_sq, float(group['lr']),
+                         group['betas'][0], group['betas'][1], group['eps'], self.steps, grad_scale=grad_scale)
+
+    def state_dict(self):
+        sd = super().state_dict()
+        for st in sd['state'].values():                           # un-share the step scalar in the saved copy
+            st['step'] = st['step'].clone()
+        return sd
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)                       # torch re-creates the state tensors: copy them back
+        steps = 0
+        for p, off in zip(self.flat.params, self.flat.offsets):
+            st = self.state.get(p)
+            if not st:
+                continue
+            n = p.numel()
+            self.exp_avg[off: off + n].copy_(st['exp_avg'].reshape(-1))
+            self.exp_avg_sq[off: off + n].copy_(st['exp_avg_sq'].reshape(-1))
+            steps = max(steps, int(st['step']))
+        self.steps = steps
+        self._bind_state()
+
+
 class DataParallelTrainer:
     """forward + NLL + backward + bucketed all-reduce + fused AdamClipped for one rank.
 
@@ -74,10 +132,7 @@ class DataParallelTrainer:
         self.flat = FlatBuffers(model)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.lr, self.betas, self.eps = lr, betas, eps
-        self.exp_avg = torch.zeros_like(self.flat.flat_param)
-        self.exp_avg_sq = torch.zeros_like(self.flat.flat_param)
-        self.steps = 0
+        self.optimizer = FlatAdamClipped(self.flat, lr=lr, betas=betas, eps=eps)
         self._pending: List = []
         self._ready = None
         self._install_hooks()
@@ -133,7 +188,6 @@ class DataParallelTrainer:
         ``global_count``: the number of valid target rows over ALL ranks when the caller already knows
         it (e.g. no empty slots); the step then needs no device->host read and the returned loss is a
         device tensor.  Otherwise the (sum, count) pair is all-reduced and read back."""
-        from . import ops
         self._begin()
         self.flat.zero_grad()
         y_hat, tgt = self.model(x, y, utt_conds, info, reset)
@@ -148,13 +202,34 @@ class DataParallelTrainer:
         if self.world > 1:
             dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)
         self._finish_reduce()
-        self.steps += 1
         if global_count is None:
             total, count = stats.tolist()
             loss = total / max(count, 1.0)
         else:
             count = float(global_count)
             loss = stats[0] / count
-        ops.adam_clipped(self.flat.flat_param, self.flat.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr,
-                         self.betas[0], self.betas[1], self.eps, self.steps, grad_scale=1.0 / max(count, 1.0))
+        self.optimizer.step(grad_scale=1.0 / max(count, 1.0))
         return loss, int(count)
+
+    # optimizer state in torch.optim.Adam layout (checkpoint interop with the reference's AdamClipped)
+    @property
+    def lr(self):
+        return self.optimizer.param_groups[0]['lr']
+
+    @property
+    def steps(self):
+        return self.optimizer.steps
+
+    @property
+    def exp_avg(self):
+        return self.optimizer.exp_avg
+
+    @property
+    def exp_avg_sq(self):
+        return self.optimizer.exp_avg_sq
+
+    def state_dict(self):
+        return self.optimizer.state_dict()
+
+    def load_state_dict(self, state_dict):
+        self.optimizer.load_state_dict(state_dict)

@@ -31,7 +31,9 @@ class SampleRNNQuantizer:
         self._overflow = {}
 
     def _build_table(self):
-        idx = torch.arange(self.q_levels + 1)
+        if self.q_levels > 256:
+            raise RuntimeError('the dequantisation table kernel holds 257 entries: q_levels must be <= 256')
+        idx = torch.arange(257)                                                # the kernel always stages 257 entries
         if self.q_type == self.LINEAR_QUANT:
             return idx.float() / (self.q_levels / 2) - 1                       # utils.py:56-57
         y = idx.float() * 2.0 / self.q_levels - 1.0                            # utils.py:69
@@ -59,7 +61,7 @@ class SampleRNNQuantizer:
     def quantize_both(self, samples, want_i64=True):
         """(int64 indices or None, uint8 indices) - the uint8 copy feeds the fused kernels."""
         if self.q_type == self.LINEAR_QUANT:
-            return ops.quantize_linear(samples, want_i64=want_i64, want_u8=True)
+            return ops.quantize_linear(samples, want_i64=want_i64, want_u8=self.q_levels <= 256, q_levels=self.q_levels)
         if self.q_levels != 256:
             raise RuntimeError('the mu-law kernel is built for q_levels == 256 (config.default.json:40)')
         return ops.quantize_ulaw(samples, want_i64=want_i64, want_u8=True,
@@ -70,7 +72,7 @@ class SampleRNNQuantizer:
 
     # explicit names kept for API parity with the reference class
     def quantize_linear(self, samples):
-        return ops.quantize_linear(samples)[0]
+        return ops.quantize_linear(samples, q_levels=self.q_levels)[0]
 
     def dequantize_linear(self, samples):
         assert self.q_type == self.LINEAR_QUANT

@@ -51,3 +51,38 @@ def test_first_chunk_has_reset_one_and_leading_zeros():
     ds = make_dataset([2], fs, l)
     x, y, c, reset, info = next(iter(SequentialChunkLoader(ds, 1, fs, l, pin_memory=False)))
     assert reset.tolist() == [1] and float(x[0, :fs].abs().sum()) == 0
+
+
+def test_replays_the_reference_loader_schedule_exactly():
+    """tests/golden/loader_schedule.npz was recorded from the imported reference loader (make_loader_golden.py:
+    loader.py:29-84 + dataset.shuffle_utterances, global ``random.seed(7)``, two epochs).  With ``shuffle=True`` and
+    the same seed this loader must yield the same batches, reset flags and slot occupancy, step by step, and - unlike
+    the reference - stop at the end of each epoch."""
+    import os
+
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'loader_schedule.npz'))
+    fs, l, width, batch, seed = (int(z[k]) for k in ('fs', 'l', 'width', 'batch', 'seed'))
+    lengths = [int(v) for v in z['lengths']]
+
+    class Dataset:
+        def __len__(self):
+            return len(lengths)
+
+        def __getitem__(self, u):
+            n = lengths[u]
+            wav = np.concatenate([np.zeros(fs, dtype=np.float32),
+                                  (np.arange(n * fs * l, dtype=np.float32) + 1000 * u) / 8192])
+            conds = np.full((n * l, width), float(u), dtype=np.float32) + np.arange(n * l, dtype=np.float32)[:, None] / 64
+            return wav, conds, {'speaker': {'index': u}, 'utt': u}
+
+    loader = SequentialChunkLoader(Dataset(), batch, fs, l, conds_width=width, pin_memory=False, seed=seed, shuffle=True)
+    for epoch in range(2):
+        steps = list(loader)
+        assert len(steps) == int(z[f'e{epoch}.steps'])
+        for k, (x, y, c, reset, info) in enumerate(steps):
+            pre = f'e{epoch}.s{k}.'
+            assert reset.tolist() == z[pre + 'reset'].tolist(), (epoch, k)
+            assert [-1 if i is None else i['utt'] for i in info] == z[pre + 'utt'].tolist(), (epoch, k)
+            assert np.array_equal(x.numpy(), z[pre + 'x']) and np.array_equal(y.numpy(), z[pre + 'y'])
+            assert np.array_equal(c.numpy(), z[pre + 'c'])

@@ -92,3 +92,82 @@ def test_bucketed_allreduce_matches_single_process():
         assert torch.allclose(grad, flat.flat_grad, atol=1e-5)             # sum over ranks == single-process gradient
         assert abs(float(stats[0]) - float(loss)) < 1e-4 and int(stats[1]) == 8
         assert launched == [0, 1, 2, 3]                                    # one all-reduce per bucket
+
+
+def _worker_empty_shard(rank, world, port, results):
+    """Rank 1 holds only empty slots (reset == 2 everywhere: the tail of every epoch, slot ownership is sticky): its
+    filtered log-probability tensor has zero rows.  The loss path must still produce a graph-connected zero so that
+    backward runs and every bucket all-reduce is matched on both ranks (no hang, no exception)."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from samplernn_pase_b200.functional import NegSumFn
+    torch.manual_seed(0)
+    m = Tiny()
+    trainer = DataParallelTrainer(m)
+    gen = torch.Generator().manual_seed(1)
+    x_all = torch.randn(8, 5, generator=gen)
+    lo, hi = shard_slots(8, world, rank)
+    keep = torch.arange(hi - lo) if rank == 0 else torch.zeros(0, dtype=torch.int64)
+    trainer._begin()
+    trainer.flat.zero_grad()
+    logp_t = m(x_all[lo:hi])[:, :1].index_select(0, keep).unsqueeze(2)        # (B_valid, 1, 1) like fused-loss forward
+    if logp_t.numel():
+        local_sum = -logp_t.sum()          # (the CUDA reduction kernel is not available on CPU; same value)
+    else:
+        local_sum = NegSumFn.apply(logp_t)                                     # the path under test
+    assert local_sum.requires_grad
+    local_sum.backward()
+    stats = torch.tensor([float(local_sum), float(logp_t.numel())])
+    dist.all_reduce(stats)
+    trainer._finish_reduce()
+    results[rank] = (trainer.flat.flat_grad.clone(), stats.clone(), sorted(trainer._launched))
+    dist.destroy_process_group()
+
+
+def test_rank_with_only_empty_slots_keeps_collectives_matched():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker_empty_shard, args=(2, port, results), nprocs=2, join=True)
+    torch.manual_seed(0)
+    m = Tiny()
+    flat = FlatBuffers(m)
+    gen = torch.Generator().manual_seed(1)
+    x_all = torch.randn(8, 5, generator=gen)
+    loss = -m(x_all[:4])[:, :1].sum()                                          # only rank 0's slots are valid
+    loss.backward()
+    for rank in range(2):
+        grad, stats, launched = results[rank]
+        assert torch.allclose(grad, flat.flat_grad, atol=1e-5)
+        assert abs(float(stats[0]) - float(loss)) < 1e-4 and int(stats[1]) == 4
+        assert launched == [0, 1, 2, 3]
+
+
+def test_flat_adam_clipped_state_dict_uses_torch_adam_layout():
+    """The trainer's optimizer is a torch Optimizer: lr is read from param_groups (ReduceLROnPlateau works on it,
+    runner.py:34-39) and its state_dict has torch.optim.Adam's layout, loadable by / from a plain Adam."""
+    from samplernn_pase_b200.parallel import FlatAdamClipped
+    torch.manual_seed(0)
+    m = Tiny()
+    flat = FlatBuffers(m)
+    opt = FlatAdamClipped(flat, lr=1e-3)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, factor=0.5, patience=0)
+    sched.step(1.0); sched.step(2.0)
+    assert abs(opt.param_groups[0]['lr'] - 5e-4) < 1e-12
+    ref = torch.optim.Adam(Tiny().parameters(), lr=1e-3)
+    sd = opt.state_dict()
+    assert set(sd.keys()) == set(ref.state_dict().keys())
+    assert set(sd['state'][0].keys()) == {'step', 'exp_avg', 'exp_avg_sq'}
+    # round trip through a plain Adam state (moments as separate tensors) back into the flat buffers
+    for i, st in sd['state'].items():
+        st['exp_avg'] = torch.full_like(st['exp_avg'], float(i + 1))
+        st['exp_avg_sq'] = torch.full_like(st['exp_avg_sq'], 0.5)
+        st['step'] = torch.tensor(7.0)
+    opt.load_state_dict(sd)
+    assert opt.steps == 7
+    for i, (p, off) in enumerate(zip(flat.params, flat.offsets)):
+        assert bool((opt.exp_avg[off: off + p.numel()] == i + 1).all())
+        assert opt.state[p]['exp_avg'].data_ptr() == opt.exp_avg[off: off + p.numel()].data_ptr()
