@@ -198,11 +198,12 @@ typedef struct srnn_gru_args {
   void* dgi;             /* bf16 [batch*steps, 3H] batch-major, out */
   void* dgh;             /* bf16 [steps, ext_batch, 3H] TIME-major, out (also the per-step exchange buffer) */
   float* dh0;            /* fp32 [batch, H] out: dL/dh_init */
-  uint32_t* sync;        /* >= 1 KB, zeroed by the caller before every launch (grid-wide arrival counters) */
+  uint32_t* sync;        /* >= 1 KB, zeroed by the caller before every launch: [0] grid-wide arrival counter; on return
+                            [32] holds the number of exchange attempts the kernel rejected and repeated (see below) */
   int32_t tuning_flags;  /* 0 = defaults.  Every documented bit leaves the results unchanged:
-                            2 = force a cooperative launch for steps == 1, 16 = add a gpu-scope acquire fence after the
-                            grid wait, 32 = land the per-step operand as ONE TMA box (default: one box per K block,
-                            pipelined with the MMAs), 64 = two MMA-issuing warps, 128 = debug_ts receives the global
+                            2 = force a cooperative launch for steps == 1, 16 = strict exchange protocol (release
+                            increment + acquire fence instead of relaxed increment + validated read), 32 = land the
+                            per-step operand as one TMA box per K block instead of ONE box, 64 = two MMA-issuing warps, 128 = debug_ts receives the global
                             timer of every CTA at timestep 24, bits 8.. = force a cluster size.  Bits 1 and 4 exist only
                             in instrumented (-DSRNN_DEBUG) builds and are rejected with SRNN_ERR_ARG otherwise. */
   uint64_t* debug_ts;    /* NULL, or [256][8] clock64 stamps of CTA 0's pipeline events (profiling aid) */
@@ -219,6 +220,14 @@ typedef struct srnn_gru_args {
   float* db_hh;          /* bwd, nullable: same for dgh (the gradient of b_hh) */
 } srnn_gru_args;
 
+/* Exchange protocol.  Every timestep each CTA publishes its slice of h_t (backward: of the gate gradients) to the
+ * time-major buffer and increments the arrival counter; every CTA then reads the whole matrix back through TMA.  By
+ * default the increment is RELAXED (no gpu-scope fence between the data stores and the counter): the entry points first
+ * fill the slots the kernel is going to write with bf16 NaN (0xFFFF) - forward: slots 1..steps of h_ext, backward: all
+ * of dgh - and the kernel validates what it read (a missing element leaves NaN in every accumulator of its batch row)
+ * and repeats the read if needed.  Results are bit-identical to the strict protocol (tuning flag 16: release increment
+ * + acquire fence, no sentinel fill), which costs ~1 us more per timestep.  A state that genuinely contains NaN is
+ * accepted after 256 repeats. */
 int srnn_gru_forward(const srnn_gru_args* args, srnn_stream_t stream);
 int srnn_gru_backward(const srnn_gru_args* args, srnn_stream_t stream);
 

@@ -198,7 +198,8 @@ def _fast_gru(x, h0_layers, weights):
     """Library-fused equivalent of stacking ``gru_sequence`` (used only for timing the
     CPU baseline; tests check it equals the written-out loop)."""
     flat = [w for layer in weights for w in layer]
-    out, hn = torch._VF.gru(x, h0_layers, flat, True, len(weights), 0.0, False, False, True)
+    # (train=True only selects cuDNN's training workspace - its backward refuses to run otherwise; dropout is 0)
+    out, hn = torch._VF.gru(x, h0_layers, flat, True, len(weights), 0.0, True, False, True)
     return out, hn
 
 

@@ -157,6 +157,55 @@ __device__ __forceinline__ void grid_wait(const uint32_t* counter, uint32_t targ
   if (acquire_fence) asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
+// Producer side of the grid handshake: one arrival per CTA and published timestep, after a CTA barrier behind the data
+// stores.  Default: RELAXED - the data stores and the increment travel to L2 concurrently and consumers validate what
+// they read (see exchange()).  Tuning flag 16 = strict protocol: release increment (MEMBAR.ALL.GPU + RED) here and an
+// acquire fence after the consumer's wait.
+__device__ __forceinline__ void publish(uint32_t* counter, int flags) {
+  if (flags & 16) {
+    red_release_gpu_add(counter, 1u);
+  } else {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+  }
+}
+constexpr uint32_t GRU_MAX_RETRIES = 256;
+
+// CTA-wide OR over a named barrier (the epilogue warps only)
+template <int ID, int THREADS>
+__device__ __forceinline__ uint32_t bar_red_or(bool pred) {
+  uint32_t out;
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.u32 q, %1, 0;\n"
+      "barrier.cta.red.or.pred p, %2, %3, q;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(out)
+      : "r"(static_cast<uint32_t>(pred)), "n"(ID), "n"(THREADS)
+      : "memory");
+  return out;
+}
+// remote arrival on a peer CTA's mbarrier / wait with cluster-scope acquire (the retry acknowledgement)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
 // Instrumented builds only (-DSRNN_DEBUG): timing experiments that produce WRONG results.  bit 0: do not wait on the
 // grid counter; bit 2: skip the per-step global loads/stores of the epilogue.  A release build rejects both bits.
 __device__ __forceinline__ bool grid_wait_skipped(int flags) {
@@ -205,7 +254,9 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
   uint64_t* acc_full = bars + 1;
   uint64_t* part_ready = bars + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-  uint64_t* full = bars + 4;                                            // [GRU_MAX_KBC]: one per K block of the operand
+  uint64_t* retry_ack = bars + 4;                                       // C > 1: peers have consumed a rejected attempt's partials
+  volatile uint32_t* ctl = reinterpret_cast<volatile uint32_t*>(bars + 5);   // [0] verdict (attempt << 1 | retry), [1] exit
+  uint64_t* full = bars + 6;                                            // [GRU_MAX_KBC]: one per K block of the operand
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -224,6 +275,9 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
     for (int kb = 0; kb < GRU_MAX_KBC; ++kb) mbar_init(full + kb, 1);
     mbar_init(acc_full, MW);
     mbar_init(part_ready, 1);
+    mbar_init(retry_ack, C);
+    ctl[0] = 0u;
+    ctl[1] = 0u;
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -262,53 +316,79 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       const uint32_t a_hi = static_cast<uint32_t>(a_base >> 32), b_hi = static_cast<uint32_t>(b_base >> 32);
       const uint32_t d_tmem = tmem_base + mw * NCOLS;
       const uint32_t hslot16 = static_cast<uint32_t>(p.hslot) >> 4;
-      uint32_t phase = 0;
       const uint32_t a_lo0 = static_cast<uint32_t>(a_base), b_lo0 = static_cast<uint32_t>(b_base);
       const uint32_t blk_bytes = static_cast<uint32_t>(B) * 128u;
-      for (int s = 0; s < rounds; ++s) {
-        if (BWD && s == 0) continue;                 // the last timestep has no recurrent input
+      const bool one_box = p.one_box != 0;
+      const bool strict = (p.flags & 16) != 0;
+      // An ATTEMPT = landing of the operand + the MMAs + one commit.  The epilogue validates every attempt (see
+      // exchange() below) and posts a verdict; a rejected attempt is repeated for the same timestep.  Thread 0 drives:
+      // it knows the round, waits for the grid, issues the loads and reads the verdicts; the other issuing threads just
+      // follow the landing barriers until thread 0 raises the exit flag.
+      uint32_t phase = 0, attempt = 0;
+      int s = BWD ? 1 : 0;                           // backward: the last timestep (round 0) has no recurrent input
+      bool fresh = true;                             // first attempt of round s
+      for (;;) {
         if (mw == 0) {
-          if (s > 0 && !grid_wait_skipped(p.flags)) {
-            grid_wait(p.sync, G * static_cast<uint32_t>(s), (p.flags & 16) != 0);
+          if (fresh && s > 0 && !grid_wait_skipped(p.flags)) {
+            grid_wait(p.sync, G * static_cast<uint32_t>(s), strict);
             GRU_TS(0, s);
           }
           asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy writes -> TMA reads (free: measured)
           const int slot = BWD ? (T - s) : s;        // time slot of the exchange buffer
-          if (p.one_box) {
+          if (one_box) {
             mbar_expect_tx(full, bytes);
             tma_load_4d(hbuf, &tma_x, full, 0, 0, kb0, slot);
           } else {
-            // One box and one barrier per K block, issued back to back by this thread (~80 cycles apart, about the time
-            // the TMA unit needs to turn one 8 KB box into L2 requests), so the blocks LAND in issue order and the MMAs
-            // of block i run while blocks i+1.. are still in flight.
-            for (int kb = 0; kb < KBC; ++kb) {
+            for (int kb = 0; kb < KBC; ++kb) {       // tuning flag 32: one box and one barrier per K block
               mbar_expect_tx(full + kb, blk_bytes);
               tma_load_3d(hbuf + kb * GRU_SLOT, &tma_x, full + kb, (kb0 + kb) * 64, 0, slot);
             }
           }
           GRU_TS(1, s);
-        }
-        // K steps (16 columns = 32 bytes inside a 64-column block) are dealt round-robin inside every K block: issuer mw
-        // takes steps mw, mw + MW, ... of each block.  Only the 14-bit start-address field (low descriptor word) changes.
-        uint32_t first = 0u;
-        for (int kb = 0; kb < KBC; ++kb) {
-          if (kb == 0 || !p.one_box) {
-            mbar_wait(full + (p.one_box ? 0 : kb), phase);
-            tc_fence_after();
-            if (C == 1 && mw == 0 && kb == 0) GRU_TS(7, s);    // first block landed (slot 7 = partials pushed when C > 1)
+          mbar_wait(full, phase);
+        } else {
+          bool leave = false;
+          while (!mbar_try_wait(full, phase)) {
+            if (ctl[1] != 0u) {
+              leave = true;
+              break;
+            }
           }
-#pragma unroll
-          for (int j = mw; j < 4; j += MW) {
-            const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo0 + static_cast<uint32_t>(kb) * hslot16 + j * 2u);
-            const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo0 + static_cast<uint32_t>(kb) * (WBLOCK >> 4) + j * 2u);
-            umma_bf16(d_tmem, ad, bd, IDESC, first);
-            first = 1u;
-          }
+          if (leave) break;
         }
-        phase ^= 1;
-        if (mw == 0) GRU_TS(2, s);                   // last block landed (and its MMAs issued)
+        if (mw == 0) GRU_TS(2, s);
+        tc_fence_after();
+        // K steps (16 columns = 32 bytes inside a 64-column block) are dealt round-robin: issuer mw takes steps
+        // mw, mw + MW, ...  Only the 14-bit start-address field (low descriptor word) changes.  (Keep this loop lean:
+        // one thread issues it, ~5 cycles per dependent SASS instruction - 45 instructions per MMA cost 2.5x the step.)
+#pragma unroll 4
+        for (int ks = mw; ks < KBC * 4; ks += MW) {
+          const uint32_t kb = static_cast<uint32_t>(ks) >> 2, j = static_cast<uint32_t>(ks) & 3u;
+          if (!one_box && kb != 0u && j < static_cast<uint32_t>(MW)) mbar_wait(full + kb, phase);
+          const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo0 + kb * hslot16 + j * 2u);
+          const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo0 + kb * (WBLOCK >> 4) + j * 2u);
+          umma_bf16(d_tmem, ad, bd, IDESC, ks >= MW ? 1u : 0u);
+        }
         umma_commit(acc_full);
-        if (mw == 0) GRU_TS(3, s);
+        phase ^= 1;
+        ++attempt;
+        if (mw == 0) {
+          GRU_TS(3, s);
+          uint32_t v, spins = 0;
+          while (((v = ctl[0]) >> 1) != attempt) {   // the epilogue's verdict on this attempt
+            if (++spins > (1u << 28)) __trap();
+          }
+          tc_fence_after();
+          if (v & 1u) {
+            fresh = false;                           // rejected (the operand was not complete yet): same round again
+            continue;
+          }
+          fresh = true;
+          if (++s == rounds) {
+            ctl[1] = 1u;
+            break;
+          }
+        }
       }
     }
     __syncwarp();
@@ -331,80 +411,112 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
     // WAR safety: a peer pushes step t+1 only after the grid barrier of step t, i.e. after this CTA
     // has consumed step t.
     constexpr uint32_t RECV_BYTES = C * NG * GRU_M * U * 4;
+    uint32_t attempt = 0, ack_phase = 0;
+    // Validation of the exchanged operand.  Producers publish with plain stores followed by a RELAXED counter increment
+    // (no MEMBAR.GPU: it cost ~1 us of every ~4 us step), so the counter may become visible before the data.  The
+    // exchange buffer is pre-filled with bf16 NaN (0xFFFF) by the host wrapper and every element is written exactly once
+    // per launch; an element that has not arrived yet therefore turns ALL accumulators of its batch row into NaN
+    // (tensor cores propagate NaN; checked by scripts/nan_probe.py).  One accumulator per row is tested, the CTA votes,
+    // and a rejected attempt is repeated (reload + MMAs) for the same timestep.  After GRU_MAX_RETRIES rejections the
+    // NaN is accepted as genuine state (diverged training) so the launch always terminates.  With C > 1 all CTAs of
+    // a cluster see the same rows as NaN (each sums the partials of all C K-slices), so they decide alike.
     auto exchange = [&](float (&out)[NG * U], int dbg_step) {
-      if constexpr (C == 1) {                          // no peers: the accumulator columns are the result
-        mbar_wait(acc_full, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
-        static_assert(NCOLS <= 32, "C == 1: one 32-column chunk per partial");
+      uint32_t retries = 0;
+      for (;;) {
+        if constexpr (C == 1) {                          // no peers: the accumulator columns are the result
+          mbar_wait(acc_full, acc_phase);
+          acc_phase ^= 1;
+          tc_fence_after();
+          static_assert(C != 1 || NCOLS <= 32, "C == 1: one 32-column chunk per partial");
 #pragma unroll
-        for (int i = 0; i < NG * U; ++i) out[i] = 0.f;
+          for (int i = 0; i < NG * U; ++i) out[i] = 0.f;
 #pragma unroll
-        for (int pw = 0; pw < MW; pw += 2) {           // two partial tiles in flight per wait
-          if (pw >= KBC * 4) break;                    // fewer K steps than issuers: those partials were never written
-          uint32_t v[2][32];
-          tmem_ld32(t_addr + pw * NCOLS, v[0]);
-          tmem_ld32(t_addr + (pw + 1) * NCOLS, v[1]);
-          tmem_ld_wait();
+          for (int pw = 0; pw < MW; pw += 2) {           // two partial tiles in flight per wait
+            if (pw >= KBC * 4) break;                    // fewer K steps than issuers: those partials were never written
+            uint32_t v[2][32];
+            tmem_ld32(t_addr + pw * NCOLS, v[0]);
+            tmem_ld32(t_addr + (pw + 1) * NCOLS, v[1]);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < NG * U; ++i) out[i] += __uint_as_float(v[0][i]) + __uint_as_float(v[1][i]);
-        }
-        tc_fence_before();
-        return;
-      }
-      if (warp == 2 && lane == 0) mbar_expect_tx(part_ready, RECV_BYTES);
-      mbar_wait(acc_full, acc_phase);
-      acc_phase ^= 1;
-      if (warp == 2 && lane == 0) GRU_TS(4, dbg_step);
-      tc_fence_after();
+            for (int i = 0; i < NG * U; ++i) out[i] += __uint_as_float(v[0][i]) + __uint_as_float(v[1][i]);
+          }
+          tc_fence_before();
+        } else {
+          if (warp == 2 && lane == 0) mbar_expect_tx(part_ready, RECV_BYTES);
+          mbar_wait(acc_full, acc_phase);
+          acc_phase ^= 1;
+          if (warp == 2 && lane == 0) GRU_TS(4, dbg_step);
+          tc_fence_after();
 #pragma unroll
-      for (int bi = 0; bi < NB; ++bi) {                // 32 result columns per batch, ONE wait per batch
-        uint32_t v[MW][32];
+          for (int bi = 0; bi < NB; ++bi) {                // 32 result columns per batch, ONE wait per batch
+            uint32_t v[MW][32];
 #pragma unroll
-        for (int pw = 0; pw < MW; ++pw) tmem_ld32(t_addr + pw * NCOLS + bi * 32, v[pw]);
-        tmem_ld_wait();
-        if (lane_ok) {
+            for (int pw = 0; pw < MW; ++pw) tmem_ld32(t_addr + pw * NCOLS + bi * 32, v[pw]);
+            tmem_ld_wait();
+            if (lane_ok) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {                 // groups of 8 columns = one (gate, dst rank) pair
-            const int col = bi * 32 + e * 8;
-            if (col < NCOLS) {
-              float f[8];
+              for (int e = 0; e < 4; ++e) {                 // groups of 8 columns = one (gate, dst rank) pair
+                const int col = bi * 32 + e * 8;
+                if (col < NCOLS) {
+                  float f[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                f[i] = 0.f;
+                  for (int i = 0; i < 8; ++i) {
+                    f[i] = 0.f;
 #pragma unroll
-                for (int pw = 0; pw < MW; ++pw) f[i] += __uint_as_float(v[pw][e * 8 + i]);
+                    for (int pw = 0; pw < MW; ++pw) f[i] += __uint_as_float(v[pw][e * 8 + i]);
+                  }
+                  const int g = col / UC, dst = (col % UC) / U, sub = (col % U) / 8;
+                  const uint32_t off = static_cast<uint32_t>((((crank * NG + g) * GRU_M + row) * U + sub * 8) * 4);
+                  const uint32_t ra = mapa(part_addr + off, static_cast<uint32_t>(dst));
+                  const uint32_t rb = mapa(ready_addr, static_cast<uint32_t>(dst));
+                  st_async_v4(ra, f[0], f[1], f[2], f[3], rb);
+                  st_async_v4(ra + 16, f[4], f[5], f[6], f[7], rb);
+                }
               }
-              const int g = col / UC, dst = (col % UC) / U, sub = (col % U) / 8;
-              const uint32_t off = static_cast<uint32_t>((((crank * NG + g) * GRU_M + row) * U + sub * 8) * 4);
-              const uint32_t ra = mapa(part_addr + off, static_cast<uint32_t>(dst));
-              const uint32_t rb = mapa(ready_addr, static_cast<uint32_t>(dst));
-              st_async_v4(ra, f[0], f[1], f[2], f[3], rb);
-              st_async_v4(ra + 16, f[4], f[5], f[6], f[7], rb);
             }
+          }
+          tc_fence_before();
+          if (warp == 2 && lane == 0) GRU_TS(7, dbg_step);
+          mbar_wait(part_ready, part_phase);
+          part_phase ^= 1;
+          if (warp == 2 && lane == 0) GRU_TS(5, dbg_step);
+#pragma unroll
+          for (int i = 0; i < NG * U; ++i) out[i] = 0.f;
+          if (lane_ok) {
+#pragma unroll
+            for (int r = 0; r < C; ++r)
+#pragma unroll
+              for (int g = 0; g < NG; ++g) {
+                const float4* rp = reinterpret_cast<const float4*>(part + ((r * NG + g) * GRU_M + row) * U);
+#pragma unroll
+                for (int i4 = 0; i4 < U / 4; ++i4) {
+                  const float4 a = rp[i4];
+                  out[g * U + i4 * 4 + 0] += a.x; out[g * U + i4 * 4 + 1] += a.y;
+                  out[g * U + i4 * 4 + 2] += a.z; out[g * U + i4 * 4 + 3] += a.w;
+                }
+              }
           }
         }
-      }
-      tc_fence_before();
-      if (warp == 2 && lane == 0) GRU_TS(7, dbg_step);
-      mbar_wait(part_ready, part_phase);
-      part_phase ^= 1;
-      if (warp == 2 && lane == 0) GRU_TS(5, dbg_step);
+        ++attempt;
+        const bool bad = row_ok && (out[0] != out[0]);
+        uint32_t reject = bar_red_or<2, 128>(bad);
+        if (reject && retries >= GRU_MAX_RETRIES) reject = 0u;
+        if (warp == 2 && lane == 0) {
+          ctl[0] = (attempt << 1) | reject;
+          if (reject) atomicAdd(p.sync + 32, 1u);        // statistics: rejected attempts of this launch (sync[32])
+        }
+        if (!reject) return;
+        ++retries;
+        if constexpr (C > 1) {
+          // nobody may push the next attempt's partials into a peer that is still summing this attempt's
+          if (warp == 2 && lane == 0) {
+            const uint32_t ack_addr = smem_u32(retry_ack);
 #pragma unroll
-      for (int i = 0; i < NG * U; ++i) out[i] = 0.f;
-      if (lane_ok) {
-#pragma unroll
-        for (int r = 0; r < C; ++r)
-#pragma unroll
-          for (int g = 0; g < NG; ++g) {
-            const float4* rp = reinterpret_cast<const float4*>(part + ((r * NG + g) * GRU_M + row) * U);
-#pragma unroll
-            for (int i4 = 0; i4 < U / 4; ++i4) {
-              const float4 a = rp[i4];
-              out[g * U + i4 * 4 + 0] += a.x; out[g * U + i4 * 4 + 1] += a.y;
-              out[g * U + i4 * 4 + 2] += a.z; out[g * U + i4 * 4 + 3] += a.w;
-            }
+            for (int r = 0; r < C; ++r) mbar_arrive_cluster(mapa(ack_addr, static_cast<uint32_t>(r)));
           }
+          mbar_wait_cluster(retry_ack, ack_phase);
+          ack_phase ^= 1;
+        }
       }
     };
 
@@ -446,7 +558,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         }
         if (io) store_units<U>(p.h_ext + (static_cast<long long>(t + 1) * EB + row) * H + u0, h);
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && lane == 0) red_release_gpu_add(p.sync, 1u);
+        if (warp == 2 && lane == 0) publish(p.sync, p.flags);
         if (p.hall && io) store_units<U>(p.hall + rt * H + u0, h);
         if (p.gates && io) {                           // saved for backward: i, f, g, o, c_t  (5H per row)
           __nv_bfloat16* sp = p.gates + rt * 5 * H + u0;
@@ -527,7 +639,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           store_units<U>(ghp + 3 * H, po);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && lane == 0) red_release_gpu_add(p.sync, 1u);
+        if (warp == 2 && lane == 0) publish(p.sync, p.flags);
         if (io) {                                               // same values, batch-major, for the GEMMs
           __nv_bfloat16* gip = p.dgi + rt * 4 * H + u0;
           store_units<U>(gip, pi);
@@ -594,7 +706,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (warp == 2 && lane == 0) {
           GRU_TS(6, t);
-          red_release_gpu_add(p.sync, 1u);
+          publish(p.sync, p.flags);
         }
         // the batch-major copy of h_t (GEMM operand) and the saved gates are off the critical path
         if (p.hall && io) store_units<U>(p.hall + rt * H + u0, h);
@@ -666,7 +778,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (warp == 2 && lane == 0) {
           GRU_TS(6, s);
-          red_release_gpu_add(p.sync, 1u);
+          publish(p.sync, p.flags);
         }
         if (io) {                                               // dgi is only read after the kernel
           __nv_bfloat16* gip = p.dgi + rt * 3 * H + u0;
@@ -789,9 +901,11 @@ static int launch_gru_mw(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   // number of 64-column blocks and the batch a whole number of 8-row swizzle atoms, the buffer is viewed as
   // [slot][K block][row][64] (strides not monotonic: legal for a tiled map) so that ONE box brings the CTA's
   // whole [batch, K slice] operand, K block by K block, in the layout the MMA reads (8 TMA issues -> 1).
-  // Landing of the per-step operand: by default one TMA box and one barrier per K block (pipelined with the MMAs);
-  // tuning flag 32 selects the older single 4-D box (one issue, everything lands together).
-  const bool one_box = (a->tuning_flags & 32) && K % 64 == 0 && B % 8 == 0 && kbc * B * 128 <= 160 * 1024;
+  // Landing of the per-step operand: ONE 4-D TMA box (one issue, ~240 cycles) when the shape allows it.  Tuning flag 32
+  // lands it as one box + one barrier per K block instead so that the MMAs of block i could start while later blocks
+  // are in flight - measured slower (16 issues cost 1 500 cycles and the FIRST 8 KB box still takes ~1 700 cycles to
+  // land, as long as the whole 128 KB box: the landing is latency-, not bandwidth-bound; profiles/r02_gru_pipelined.txt).
+  const bool one_box = !(a->tuning_flags & 32) && K % 64 == 0 && B % 8 == 0 && kbc * B * 128 <= 160 * 1024;
   {
     const uint64_t slots = BWD ? (uint64_t)T : (uint64_t)T + 1;
     const void* base = BWD ? (const void*)a->dgh : (const void*)a->h_ext;
@@ -834,6 +948,19 @@ static int launch_gru_mw(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
 
   auto kern = gru_kernel<BWD, C, LSTM, U, MW>;
   SRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // Sentinel for the fence-free exchange: every slot the kernel will WRITE and then re-read through the grid handshake
+  // starts as bf16 NaN (0xFFFF), so an element that has not arrived yet cannot be mistaken for data.  Forward: slots
+  // 1..T of h_ext (slot 0 is the caller's h_init); backward: all T slots of dgh.  A single forward timestep never reads
+  // what it wrote, and the strict protocol (flag 16) needs no sentinel.
+  if (!(a->tuning_flags & 16) && (BWD || T > 1)) {
+    const size_t row_bytes = static_cast<size_t>(K) * 2;
+    char* base = BWD ? static_cast<char*>(a->dgh) : static_cast<char*>(a->h_ext) + static_cast<size_t>(a->ext_batch) * row_bytes;
+    if (a->ext_batch == B)
+      SRNN_CUDA(cudaMemsetAsync(base, 0xFF, static_cast<size_t>(T) * B * row_bytes, stream));
+    else
+      SRNN_CUDA(cudaMemset2DAsync(base, static_cast<size_t>(a->ext_batch) * row_bytes, 0xFF, static_cast<size_t>(B) * row_bytes,
+                                  static_cast<size_t>(T), stream));
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ctas);
   cfg.blockDim = dim3(GRU_THREADS);

@@ -14,9 +14,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=64)
 ap.add_argument('--steps', type=int, default=1000)
 ap.add_argument('--hidden', type=int, default=1024)
-ap.add_argument('--flags', default='0,32,16')   # 32 = single-box landing, 16 = acquire fence, bits 8.. force a cluster size
+ap.add_argument('--flags', default='0,16,32')   # 0 = relaxed publish + validated read, 16 = strict protocol, 32 = per-K-block landing, bits 8.. force a cluster size
 ap.add_argument('--reps', type=int, default=3)
-ap.add_argument('--ts-flags', default='0,32')              # timeline(s) of CTA 0 for these flag values
+ap.add_argument('--ts-flags', default='0,16')              # timeline(s) of CTA 0 for these flag values
 ap.add_argument('--units', type=int, default=0)          # units per CTA (0 = default 8)
 a = ap.parse_args()
 b, t, h = a.batch, a.steps, a.hidden
@@ -57,7 +57,7 @@ for flags in [int(f) for f in a.flags.split(',')]:
             e0.record(); run(kind); e1.record()
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
-        print(f'flags={flags} {kind}: {best:8.3f} ms  {1e3 * best / t:6.2f} us/step   (B={b} T={t} H={h})')
+        print(f'flags={flags} {kind}: {best:8.3f} ms  {1e3 * best / t:6.2f} us/step   (B={b} T={t} H={h})  repeated attempts in the last launch: {int(ops.gru_last_sync[32])}')
 # pipeline timestamps of CTA 0 (forward): cycles relative to the end of the grid wait
 names = ['wait_done', 'tma_issued', 'last_landed', 'mma_commit', 'epi_acc_full', 'pushed/1st_land', 'epi_part_rdy', 'epi_publish']
 order = [0, 1, 2, 3, 4, 7, 5, 6]
