@@ -144,14 +144,53 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
 // Watchdog: a protocol bug must end the launch with an error instead of hanging the GPU, but a spin COUNT can fire
 // spuriously when the kernel is time-sliced (debugger, profiler replay, MPS), so the limit is wall-clock: 20 s without
 // progress on one handshake (a timestep takes microseconds).
-__device__ __forceinline__ void grid_wait(const uint32_t* counter, uint32_t target, bool acquire_fence) {
+// `depth` polls are kept in flight (1, 2 or 4), spaced by a quarter of a poll's round trip: with one poll at a time the
+// arrival of the last increment is noticed up to a full L2 round trip (~650 cycles under load) late.
+__device__ __forceinline__ void spin_cycles(uint32_t n) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < static_cast<long long>(n)) {
+  }
+}
+__device__ __forceinline__ void grid_wait(const uint32_t* counter, uint32_t target, bool acquire_fence, int depth,
+                                          uint32_t gap) {
   uint32_t spins = 0;
   unsigned long long t0 = 0;
-  while (ld_relaxed_gpu(counter) < target) {
-    if ((++spins & 0xFFFFu) == 0) {
-      const unsigned long long now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 20000000000ull) __trap();
+  if (depth <= 1) {
+    while (ld_relaxed_gpu(counter) < target) {
+      if ((++spins & 0xFFFFu) == 0) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 20000000000ull) __trap();
+      }
+    }
+  } else {
+    // rotating window of asynchronous loads: a load only blocks when its value is consumed
+    uint32_t v0, v1, v2 = 0, v3 = 0;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v0) : "l"(counter) : "memory");
+    spin_cycles(gap);
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v1) : "l"(counter) : "memory");
+    if (depth >= 4) {
+      spin_cycles(gap);
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v2) : "l"(counter) : "memory");
+      spin_cycles(gap);
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v3) : "l"(counter) : "memory");
+    }
+    for (;;) {
+      if (v0 >= target) break;
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v0) : "l"(counter) : "memory");
+      if (v1 >= target) break;
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v1) : "l"(counter) : "memory");
+      if (depth >= 4) {
+        if (v2 >= target) break;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v2) : "l"(counter) : "memory");
+        if (v3 >= target) break;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v3) : "l"(counter) : "memory");
+      }
+      if ((++spins & 0x3FFFu) == 0) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 20000000000ull) __trap();
+      }
     }
   }
   if (acquire_fence) asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -320,6 +359,15 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       const uint32_t blk_bytes = static_cast<uint32_t>(B) * 128u;
       const bool one_box = p.one_box != 0;
       const bool strict = (p.flags & 16) != 0;
+      // tuning (experiments): bits 12-13 polls in flight (0 -> 1, 1 -> 2, 2 -> 4), bits 14-15 their spacing
+      // ((n + 1) * 64 cycles), bits 16-19 cycles/32 to hold back the TMA read after the wait (fewer rejected attempts)
+      const int poll_depth = 1 << ((p.flags >> 12) & 3);
+      const uint32_t poll_gap = (((p.flags >> 14) & 3) + 1) * 64u;
+      const uint32_t hold = ((p.flags >> 16) & 15) * 32u;
+      // bits 20-23: n*128 cycles before the FIRST poll of a wait.  This thread reaches the wait ~1 000 cycles before the
+      // last CTA can have published (own gate math + publish skew); polling during that time only queues reads on the
+      // counter's L2 line in front of the other CTAs' increments
+      const uint32_t pre_poll = ((p.flags >> 20) & 15) * 128u;
       // An ATTEMPT = landing of the operand + the MMAs + one commit.  The epilogue validates every attempt (see
       // exchange() below) and posts a verdict; a rejected attempt is repeated for the same timestep.  Thread 0 drives:
       // it knows the round, waits for the grid, issues the loads and reads the verdicts; the other issuing threads just
@@ -330,7 +378,9 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       for (;;) {
         if (mw == 0) {
           if (fresh && s > 0 && !grid_wait_skipped(p.flags)) {
-            grid_wait(p.sync, G * static_cast<uint32_t>(s), strict);
+            if (pre_poll) spin_cycles(pre_poll);
+            grid_wait(p.sync, G * static_cast<uint32_t>(s), strict, poll_depth, poll_gap);
+            if (hold) spin_cycles(hold);
             GRU_TS(0, s);
           }
           asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy writes -> TMA reads (free: measured)
@@ -361,13 +411,22 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         // K steps (16 columns = 32 bytes inside a 64-column block) are dealt round-robin: issuer mw takes steps
         // mw, mw + MW, ...  Only the 14-bit start-address field (low descriptor word) changes.  (Keep this loop lean:
         // one thread issues it, ~5 cycles per dependent SASS instruction - 45 instructions per MMA cost 2.5x the step.)
+        if (one_box) {
 #pragma unroll 4
-        for (int ks = mw; ks < KBC * 4; ks += MW) {
-          const uint32_t kb = static_cast<uint32_t>(ks) >> 2, j = static_cast<uint32_t>(ks) & 3u;
-          if (!one_box && kb != 0u && j < static_cast<uint32_t>(MW)) mbar_wait(full + kb, phase);
-          const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo0 + kb * hslot16 + j * 2u);
-          const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo0 + kb * (WBLOCK >> 4) + j * 2u);
-          umma_bf16(d_tmem, ad, bd, IDESC, ks >= MW ? 1u : 0u);
+          for (int ks = mw; ks < KBC * 4; ks += MW) {
+            const uint32_t kb = static_cast<uint32_t>(ks) >> 2, j = static_cast<uint32_t>(ks) & 3u;
+            const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo0 + kb * hslot16 + j * 2u);
+            const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo0 + kb * (WBLOCK >> 4) + j * 2u);
+            umma_bf16(d_tmem, ad, bd, IDESC, ks >= MW ? 1u : 0u);
+          }
+        } else {
+          for (int ks = mw; ks < KBC * 4; ks += MW) {
+            const uint32_t kb = static_cast<uint32_t>(ks) >> 2, j = static_cast<uint32_t>(ks) & 3u;
+            if (kb != 0u && j < static_cast<uint32_t>(MW)) mbar_wait(full + kb, phase);
+            const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo0 + kb * hslot16 + j * 2u);
+            const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo0 + kb * (WBLOCK >> 4) + j * 2u);
+            umma_bf16(d_tmem, ad, bd, IDESC, ks >= MW ? 1u : 0u);
+          }
         }
         umma_commit(acc_full);
         phase ^= 1;
@@ -1069,8 +1128,8 @@ static int dispatch_gru_u(const srnn_gru_args* a, cudaStream_t stream) {
     c = pick_cluster<BWD, LSTM, U>(a->hidden, &kbc);
     cache.put(a->hidden, c, kbc);
   }
-  if (a->tuning_flags >> 8) {                         // experiments: force a cluster size (bits 8..)
-    const int forced = a->tuning_flags >> 8;
+  if ((a->tuning_flags >> 8) & 15) {                  // experiments: force a cluster size (bits 8-11)
+    const int forced = (a->tuning_flags >> 8) & 15;
     const int kb_total = ((BWD ? (LSTM ? 4 : 3) : 1) * a->hidden + 63) / 64;
     if (kb_total % forced == 0 && a->hidden % (U * forced) == 0 && kb_total / forced <= GRU_MAX_KBC) {
       c = forced;

@@ -145,6 +145,9 @@ def adam_case():
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'lf0':          # add one case without rewriting the committed fixtures
+        model_case('gru2_linguistic_lf0', [4, 2], [1, 1], 32, 2, 2, [[1, 1], [0, 1]], kind='linguistic_lf0')
+        sys.exit(0)
     quantizer_case()
     adam_case()
     model_case('gru2_single', [4, 2], [1, 1], 32, 3, 3, [[1, 1, 1]])
@@ -153,3 +156,4 @@ if __name__ == '__main__':
     model_case('gru3_multilayer', [5, 2, 3], [1, 2, 1], 32, 2, 2, [[1, 1], [0, 0]])
     model_case('gru2_linguistic', [4, 2], [1, 1], 32, 2, 2, [[1, 1]], kind='linguistic')
     model_case('gru2_default_ratios', [20, 4], [1, 1], 16, 2, 2, [[1, 1], [0, 0]])
+    model_case('gru2_linguistic_lf0', [4, 2], [1, 1], 32, 2, 2, [[1, 1], [0, 1]], kind='linguistic_lf0')

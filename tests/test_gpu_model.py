@@ -24,7 +24,8 @@ from tests.helpers import Golden, cosine, rel_l2
 
 pytestmark = pytest.mark.gpu
 
-CASES = ['gru2_single', 'gru2_carry', 'gru2_aswritten', 'gru3_multilayer', 'gru2_linguistic', 'gru2_default_ratios']
+CASES = ['gru2_single', 'gru2_carry', 'gru2_aswritten', 'gru3_multilayer', 'gru2_linguistic', 'gru2_default_ratios',
+         'gru2_linguistic_lf0']
 REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out', 'parity_report.txt')
 
 

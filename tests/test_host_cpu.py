@@ -26,7 +26,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_state_dict_keys_and_order_match_reference():
     from samplernn_pase_b200 import SampleRNNModel
-    for case, kind in (('gru2_single', 'acoustic'), ('gru2_linguistic', 'linguistic'), ('gru3_multilayer', 'acoustic')):
+    for case, kind in (('gru2_single', 'acoustic'), ('gru2_linguistic', 'linguistic'), ('gru3_multilayer', 'acoustic'),
+                       ('gru2_linguistic_lf0', 'linguistic_lf0')):
         g = Golden(case)
         s = g.spec_kwargs()
         m = SampleRNNModel('embedding', int(g.meta['n_spk']), 15, kind, [9, 5, 4, 3], 10, 50, s['sequence_length'],
