@@ -420,8 +420,9 @@ def run_gpu(args):
             note='half of the A operand is one-hot (1 non-zero in 256): it draws less power than the dense random operands '
                  'the peaks were measured with, so the sustained-relative fraction can exceed 1; the burst-relative one cannot')
         del trainer, model, resident
-        cpu = cpu_reference(2, 1)
-        eager = gpu_eager_baseline(dev, b) if not args.no_eager else None
+        # host-side and eager baselines: rank 0 at N = 1 only (they describe one GPU / one socket)
+        cpu = cpu_reference(2, 1) if world == 1 and not args.no_cpu else None
+        eager = gpu_eager_baseline(dev, b) if world == 1 and not args.no_eager else None
         line = dict(
             metric=METRIC, value=total / (ms * 1e-3), unit='samples/s', n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=step_ms, higher_is_better=True, scaling=scaling_kind(args), vs_baseline=None,
@@ -440,7 +441,8 @@ def run_gpu(args):
                      final_loss=loss_e2e),
             gpu_launches=launches,
             roofline=roofline, roofline_gemm=roofline_gemm, recurrence=rec,
-            cpu_baseline=dict(value=cpu['value'], unit='samples/s', cores=cpu['cores'], kind='port', sample=cpu['sample']),
+            cpu_baseline=dict(value=cpu['value'], unit='samples/s', cores=cpu['cores'], kind='port',
+                              sample=cpu['sample']) if cpu else None,
             gpu_eager_baseline=eager,
         )
         print(json.dumps(line))
@@ -460,6 +462,7 @@ def main():
                     help='fix the GLOBAL number of slots (strong scaling: slots per GPU = global / N) instead of the '
                          'per-GPU slot count of the workload')
     ap.add_argument('--no-eager', action='store_true', help='skip the informational GPU-eager leg')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg (profiling runs)')
     args = ap.parse_args()
     select_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup

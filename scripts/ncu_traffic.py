@@ -29,7 +29,7 @@ def traffic(path, pick=-1):
 if __name__ == '__main__':
     res, detail = {}, {}
     for arg in sys.argv[1:]:
-        key, path = arg.split('=', 1)
+        key, path = arg.rsplit('=', 1)
         if not os.path.exists(path):
             continue
         launches = traffic(path)
