@@ -451,19 +451,83 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_generation(args):
+    """BASELINE configs[4]: batched autoregressive generation, 256 utterances x 4 s (64 000 samples) with the config-2 model.
+    step = one ``SampleRNNModel.test`` call (model.py:289-351) for all utterances; value = generated samples / s."""
+    from samplernn_pase_b200 import SampleRNNModel, ops
+    if args.gpus != 1:
+        raise SystemExit('config5 is a single-GPU workload (replicas only: utterances are independent)')
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(0)
+    torch.manual_seed(1234)
+    utts, frames = 256, args.gen_frames
+    model = SampleRNNModel(**model_kwargs(frames)).to(dev)
+    fs = int(model.frame_size)
+    host = torch.randn(utts, frames, 43, generator=torch.Generator().manual_seed(4321)).pin_memory()
+    info = [{'speaker': {'index': i % N_SPEAKERS}} for i in range(utts)]
+    resident = host.to(dev)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    def timed(n, e2e):
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(n):
+            y = model.test(host.to(dev, non_blocking=True) if e2e else resident, info, generator=gen)
+            if e2e:
+                y = y.cpu()
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1), y
+
+    timed(warmup, False)
+    sampler = ClockSampler(0)
+    ops.launch_count = 0
+    ms, y = timed(steps, False)
+    launches = ops.launch_count
+    clocks = sampler.stop()
+    ms_e2e, y = timed(steps, True)
+    assert y.shape == (utts, (frames + 1) * fs) and int(y.min()) >= 0 and int(y.max()) <= 255
+    assert len(set(y[0, fs:].tolist())) > 8                                     # it really samples
+    total = steps * utts * frames * fs
+    line = dict(metric='batched autoregressive generation audio samples/sec', value=total / (ms * 1e-3), unit='samples/s',
+                n_gpus=1, steps=steps, warmup=warmup, ms_per_step=ms / steps, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='bf16', data='synthetic',
+                config=dict(workload=f'config5: batched autoregressive generation, {utts} utterances x {frames * fs} samples '
+                                     f'({frames * fs / 16000:.2f} s of 16 kHz audio), config-2 model (ratios [4,4], H=1024), '
+                                     'device-side Philox multinomial draws', utterances=utts, samples_per_utterance=frames * fs),
+                run=dict(us_per_sample_step=1e3 * ms / steps / (frames * fs),
+                         note='one sample step = all utterances advance by one sample; the FS step programs of a frame are '
+                              'one CUDA graph (captured inside every call: set-up + capture are part of the timed step)'),
+                clocks=clocks,
+                e2e=dict(value=total / (ms_e2e * 1e-3), unit='samples/s', ms_per_step=ms_e2e / steps,
+                         h2d_bytes_per_step=host.numel() * 4, d2h_bytes_per_step=utts * (frames + 1) * fs * 8),
+                gpu_launches=launches, roofline=None, cpu_baseline=None)
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='config2', choices=['config1', 'config2', 'config3', 'config4'])
+    ap.add_argument('--workload', default='config2', choices=['config1', 'config2', 'config3', 'config4', 'config5'])
+    ap.add_argument('--gen-frames', type=int, default=4000, help='config5: top-tier frames per utterance (4000 = 4 s)')
     ap.add_argument('--global-batch', type=int, default=0,
                     help='fix the GLOBAL number of slots (strong scaling: slots per GPU = global / N) instead of the '
                          'per-GPU slot count of the workload')
     ap.add_argument('--no-eager', action='store_true', help='skip the informational GPU-eager leg')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg (profiling runs)')
     args = ap.parse_args()
+    if args.workload == 'config5':
+        if args.impl == 'reference':
+            print(json.dumps(dict(impl='reference', unavailable='the reference generates one utterance per call in a Python '
+                                  'per-sample loop (model.py:289-351); no batched CPU generation arm is timed')))
+            return
+        args.steps = min(args.steps, 3)
+        return run_generation(args)
     select_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

@@ -181,7 +181,9 @@ int srnn_gemm_nll(const srnn_nll_args* args, srnn_stream_t stream);
  * One cooperative launch runs all `steps` timesteps; W_hh stays resident in shared memory.
  * ------------------------------------------------------------------------------------------- */
 typedef struct srnn_gru_args {
-  int32_t batch, steps, hidden;   /* batch <= 64 per launch (run larger batches as slot groups), hidden % 8 == 0 */
+  int32_t batch, steps, hidden;   /* batch <= 64 per launch (run larger batches as slot groups); a single forward
+                                     timestep (steps == 1, the per-sample step of generation) takes up to 512 rows in
+                                     one launch; hidden % 8 == 0 */
   int32_t ext_batch;     /* rows per time slot of the TIME-major buffers (>= batch; a launch may cover a
                             sub-range of a larger batch: pass pointers offset to its first row) */
   const void* gi;        /* bf16 [batch*steps, 3H] = W_ih u_t + b_ih, batch-major: row (b,t) = b*steps + t */
@@ -277,12 +279,15 @@ int srnn_embed_sum(const void* table_bf16, const uint8_t* idx, int64_t idx_ld, i
 /* log-softmax + the draw (model.py:203, 346-348).  in[b*ld + :q] holds log-probabilities, or raw logits when
  * normalise != 0 (then the log-softmax is taken here); if logp_out is non-null the log-probabilities are
  * written to logp_out[b*ld_out + :q].  pick[b] is sampled from them by inverse CDF with the uniform u[b] in
- * [0,1) (multinomial of the softmax), or is the arg-max when u is null.  If win is non-null, the utterance's
+ * [0,1) (multinomial of the softmax).  When u is null and rng_state is not, the uniform is drawn ON THE DEVICE:
+ * rng_state is a device array of 3 uint64 {seed, step, 0}; utterance b uses Philox4x32-10(seed; step, b) and the launch
+ * advances `step` by one, so a captured CUDA graph of step programs draws fresh numbers at every replay (the reference
+ * calls torch.multinomial per sample, model.py:346-348).  With both null, pick[b] is the arg-max.  If win is non-null, the utterance's
  * window of its last win_len codes (u8 (batch, win_len)) is shifted left by one and pick[b] appended; if out is
  * non-null, out[b*out_ld] = pick[b]. */
 int srnn_sample_categorical(const float* in, int64_t ld, int32_t batch, int32_t q, int32_t normalise, float* logp_out,
-                            int64_t ld_out, const float* u, uint8_t* win, int32_t win_len, uint8_t* out,
-                            int64_t out_ld, srnn_stream_t stream);
+                            int64_t ld_out, const float* u, uint64_t* rng_state, uint8_t* win, int32_t win_len,
+                            uint8_t* out, int64_t out_ld, srnn_stream_t stream);
 
 #ifdef __cplusplus
 }

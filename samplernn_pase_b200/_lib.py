@@ -79,7 +79,7 @@ SIGNATURES = {
     'srnn_colsum': [P, I64, I32, I64, P, P],
     'srnn_set_pdl': [I32],
     'srnn_embed_sum': [P, P, I64, I32, I32, I32, I32, P, I64, I32, P, I64, P],
-    'srnn_sample_categorical': [P, I64, I32, I32, I32, P, I64, P, P, I32, P, I64, P],
+    'srnn_sample_categorical': [P, I64, I32, I32, I32, P, I64, P, P, P, I32, P, I64, P],
     'srnn_gemm_bf16': [C.POINTER(GemmArgs), P],
     'srnn_gemm_nll': [C.POINTER(NllArgs), P],
     'srnn_gru_forward': [C.POINTER(GruArgs), P],

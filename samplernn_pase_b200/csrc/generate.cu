@@ -52,13 +52,47 @@ __global__ void embed_sum_kernel(const __nv_bfloat16* __restrict__ table, const 
 // the code to the utterance's window of the last `win_len` samples (shift left by one) and store it in out[b].
 constexpr int SAMPLE_PER = 8;                          // classes per lane (q <= 256)
 
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so the draw of utterance b at sample step n is a pure function of
+// (seed, n, b) - reproducible whatever the launch geometry, and it lives inside the captured step program.
+__device__ __forceinline__ uint32_t philox_uniform_bits(unsigned long long seed, unsigned long long step, uint32_t b) {
+  uint32_t c0 = b, c1 = 0u, c2 = static_cast<uint32_t>(step), c3 = static_cast<uint32_t>(step >> 32);
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+
 __global__ void sample_kernel(const float* __restrict__ in, long long ld, int batch, int q, int normalise,
                               float* __restrict__ logp_out, long long ld_out, const float* __restrict__ u,
-                              uint8_t* __restrict__ win, int win_len, uint8_t* __restrict__ out, long long out_ld) {
+                              unsigned long long* __restrict__ rng, uint8_t* __restrict__ win, int win_len,
+                              uint8_t* __restrict__ out, long long out_ld) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  // device-side draws: rng = {seed, step, blocks done}; every block reads the step, the last one to finish advances it
+  unsigned long long rng_seed = 0, rng_step = 0;
+  if (rng) {
+    rng_seed = rng[0];
+    rng_step = *reinterpret_cast<volatile unsigned long long*>(rng + 1);
+    __syncthreads();                                  // all warps of the block have read the step
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(rng + 2, 1ull) == gridDim.x - 1) {
+        rng[2] = 0ull;
+        rng[1] = rng_step + 1ull;
+      }
+    }
+  }
   if (b >= batch) return;
   const float* row = in + b * ld;
   float x[SAMPLE_PER];                                 // log-probabilities of classes lane*8 .. lane*8+7
@@ -88,7 +122,7 @@ __global__ void sample_kernel(const float* __restrict__ in, long long ld, int ba
     }
   }
   int pick;
-  if (u) {
+  if (u || rng) {
     float pr[SAMPLE_PER];
     float local = 0.f;
 #pragma unroll
@@ -102,7 +136,10 @@ __global__ void sample_kernel(const float* __restrict__ in, long long ld, int ba
       if (lane >= o) incl += t;
     }
     const float total = __shfl_sync(0xffffffffu, incl, 31);
-    const float target = u[b] * total;
+    // [0,1) with 24 random bits when drawn on the device (same resolution as torch's float uniform)
+    const float ub = u ? u[b] : static_cast<float>(philox_uniform_bits(rng_seed, rng_step, static_cast<uint32_t>(b)) >> 8) *
+                                    (1.0f / 16777216.0f);
+    const float target = ub * total;
     // first lane whose inclusive sum exceeds the target (the last lane with mass if rounding leaves none)
     const unsigned ahead = __ballot_sync(0xffffffffu, incl > target);
     const unsigned mass = __ballot_sync(0xffffffffu, local > 0.f);
@@ -195,7 +232,7 @@ extern "C" int srnn_embed_sum(const void* table, const uint8_t* idx, int64_t idx
 }
 
 extern "C" int srnn_sample_categorical(const float* in, int64_t ld, int32_t batch, int32_t q, int32_t normalise,
-                                       float* logp_out, int64_t ld_out, const float* u, uint8_t* win,
+                                       float* logp_out, int64_t ld_out, const float* u, uint64_t* rng_state, uint8_t* win,
                                        int32_t win_len, uint8_t* out, int64_t out_ld, srnn_stream_t s) {
   SRNN_CHECK_ARG(in && batch > 0 && q > 0 && q <= 32 * SAMPLE_PER && (win || out || logp_out),
                  "sample_categorical: bad arguments");
@@ -203,6 +240,6 @@ extern "C" int srnn_sample_categorical(const float* in, int64_t ld, int32_t batc
   const int warps = 4;
   SRNN_CUDA(launch_pdl(sample_kernel, dim3((batch + warps - 1) / warps), dim3(warps * 32), static_cast<cudaStream_t>(s),
                        in, static_cast<long long>(ld), batch, q, normalise, logp_out, static_cast<long long>(ld_out), u,
-                       win, win_len, out, static_cast<long long>(out_ld)));
+                       reinterpret_cast<unsigned long long*>(rng_state), win, win_len, out, static_cast<long long>(out_ld)));
   return SRNN_OK;
 }

@@ -48,6 +48,8 @@ struct GruParams {
   int kbc;                         // K blocks (of 64) per CTA
   int hslot;                       // bytes between K blocks of the staged [batch, K slice] operand
   int one_box;                     // the whole slice arrives as ONE 4-D TMA box (else one box per K block)
+  int groups;                      // > 1: single-timestep forward over `groups` blocks of 64 rows in ONE launch (generation)
+  int box_rows;                    // rows of one TMA box of the exchanged operand (min(batch, 64))
   const __nv_bfloat16* gi;
   const float* b_hh;
   __nv_bfloat16* h_ext;
@@ -305,7 +307,11 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
   const int u0 = blockIdx.x * U;                     // first unit finalised by this CTA
   const int kb0 = static_cast<int>(crank) * KBC;     // first K block of this CTA's slice
   const uint32_t G = gridDim.x;
-  const int rounds = BWD ? T + 1 : T;
+  // Multi-group mode (forward, T == 1, batch > 64: the per-sample recurrent step of batched generation): the rounds walk
+  // over blocks of 64 batch rows instead of timesteps.  Nothing is exchanged between CTAs (every block reads slot 0,
+  // written before the launch), so there is no grid handshake; the weight slice is fetched once for all blocks.
+  const bool multi = !BWD && p.groups > 1;
+  const int rounds = BWD ? T + 1 : (multi ? p.groups : T);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_w);
@@ -348,7 +354,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
     // own partial accumulator (summed by the epilogue).
     if (lane == 0) {
       const int mw = warp < 2 ? warp : warp - 4;
-      const uint32_t bytes = static_cast<uint32_t>(KBC) * static_cast<uint32_t>(B) * 128u;
+      const uint32_t bytes = static_cast<uint32_t>(KBC) * static_cast<uint32_t>(p.box_rows) * 128u;
       mbar_wait(wfull, 0);
       const uint64_t a_base = smem_desc_sw128(smem_u32(hbuf), 16, 1024);
       const uint64_t b_base = smem_desc_sw128(smem_u32(sw), 16, 1024);
@@ -356,7 +362,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       const uint32_t d_tmem = tmem_base + mw * NCOLS;
       const uint32_t hslot16 = static_cast<uint32_t>(p.hslot) >> 4;
       const uint32_t a_lo0 = static_cast<uint32_t>(a_base), b_lo0 = static_cast<uint32_t>(b_base);
-      const uint32_t blk_bytes = static_cast<uint32_t>(B) * 128u;
+      const uint32_t blk_bytes = static_cast<uint32_t>(p.box_rows) * 128u;
       const bool one_box = p.one_box != 0;
       const bool strict = (p.flags & 16) != 0;
       // tuning (experiments): bits 12-13 polls in flight (0 -> 1, 1 -> 2, 2 -> 4), bits 14-15 their spacing
@@ -379,21 +385,22 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       bool fresh = true;                             // first attempt of round s
       for (;;) {
         if (mw == 0) {
-          if (fresh && s > 0 && !grid_wait_skipped(p.flags)) {
+          if (fresh && s > 0 && !multi && !grid_wait_skipped(p.flags)) {
             if (pre_poll) spin_cycles(pre_poll);
             grid_wait(p.sync, G * static_cast<uint32_t>(s), strict, poll_depth, poll_gap);
             if (hold) spin_cycles(hold);
             GRU_TS(0, s);
           }
           asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy writes -> TMA reads (free: measured)
-          const int slot = BWD ? (T - s) : s;        // time slot of the exchange buffer
+          const int slot = BWD ? (T - s) : (multi ? 0 : s);      // time slot of the exchange buffer
+          const int row0 = multi ? s * GRU_M : 0;                 // first batch row of this round
           if (one_box) {
             mbar_expect_tx(full, bytes);
-            tma_load_4d(hbuf, &tma_x, full, 0, 0, kb0, slot);
+            tma_load_4d(hbuf, &tma_x, full, 0, row0, kb0, slot);
           } else {
             for (int kb = 0; kb < KBC; ++kb) {       // tuning flag 32: one box and one barrier per K block
               mbar_expect_tx(full + kb, blk_bytes);
-              tma_load_3d(hbuf + kb * GRU_SLOT, &tma_x, full + kb, (kb0 + kb) * 64, 0, slot);
+              tma_load_3d(hbuf + kb * GRU_SLOT, &tma_x, full + kb, (kb0 + kb) * 64, row0, slot);
             }
           }
           GRU_TS(1, s);
@@ -458,8 +465,11 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
     const int q = warp & 3;                          // TMEM lane quadrant of this warp
     const int row = q * 16 + lane;                   // M=64: rows 16q..16q+15 live in lanes 32q..32q+15
     const bool lane_ok = lane < 16;
-    const bool row_ok = lane_ok && row < B;
-    const bool io = row_ok && !epilogue_io_skipped(p.flags);
+    // `row` is the row inside the 64-row MMA tile, `grow` the batch row it stands for (they differ in multi-group mode)
+    int grow = row;
+    bool row_ok = lane_ok && grow < B;
+    bool io = row_ok && !epilogue_io_skipped(p.flags);
+    const int n_groups = multi ? p.groups : 1;
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t part_addr = smem_u32(part);
     const uint32_t ready_addr = smem_u32(part_ready);
@@ -586,15 +596,22 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       float h[U], c[U], bi[U], bf[U], bg[U], bo[U];
 #pragma unroll
       for (int i = 0; i < U; ++i) {
-        h[i] = row_ok ? p.h_state[static_cast<long long>(row) * H + u0 + i] : 0.f;
-        c[i] = row_ok ? p.c_state[static_cast<long long>(row) * H + u0 + i] : 0.f;
         bi[i] = p.b_hh[u0 + i];
         bf[i] = p.b_hh[H + u0 + i];
         bg[i] = p.b_hh[2 * H + u0 + i];
         bo[i] = p.b_hh[3 * H + u0 + i];
       }
+      for (int grp = 0; grp < n_groups; ++grp) {
+      grow = grp * GRU_M + row;
+      row_ok = lane_ok && grow < B;
+      io = row_ok && !epilogue_io_skipped(p.flags);
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        h[i] = row_ok ? p.h_state[static_cast<long long>(grow) * H + u0 + i] : 0.f;
+        c[i] = row_ok ? p.c_state[static_cast<long long>(grow) * H + u0 + i] : 0.f;
+      }
       for (int t = 0; t < T; ++t) {
-        const long long rt = static_cast<long long>(row) * T + t;
+        const long long rt = static_cast<long long>(grow) * T + t;
         float xi[U], xf[U], xg[U], xo[U];
 #pragma unroll
         for (int i = 0; i < U; ++i) xi[i] = xf[i] = xg[i] = xo[i] = 0.f;
@@ -606,7 +623,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           load_units<U>(gp + 3 * H, xo);
         }
         float acc[4 * U];
-        exchange(acc, t);
+        exchange(acc, multi ? grp : t);
         float gi_[U], gf_[U], gg_[U], go_[U];
 #pragma unroll
         for (int i = 0; i < U; ++i) {
@@ -617,7 +634,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           c[i] = gf_[i] * c[i] + gi_[i] * gg_[i];
           h[i] = go_[i] * tanh_fast(c[i]);
         }
-        if (io) store_units<U>(p.h_ext + (static_cast<long long>(t + 1) * EB + row) * H + u0, h);
+        if (io) store_units<U>(p.h_ext + (static_cast<long long>(t + 1) * EB + grow) * H + u0, h);
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (warp == 2 && lane == 0) publish(p.sync, p.flags);
         if (p.hall && io) store_units<U>(p.hall + rt * H + u0, h);
@@ -633,10 +650,11 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       if (row_ok) {
 #pragma unroll
         for (int i = 0; i < U; ++i) {
-          p.h_state[static_cast<long long>(row) * H + u0 + i] = h[i];
-          p.c_state[static_cast<long long>(row) * H + u0 + i] = c[i];
+          p.h_state[static_cast<long long>(grow) * H + u0 + i] = h[i];
+          p.c_state[static_cast<long long>(grow) * H + u0 + i] = c[i];
         }
       }
+      }  // groups
     } else if constexpr (BWD && LSTM) {
       // ---------------- LSTM backward ----------------
       float carry_c[U];
@@ -735,13 +753,18 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       float h[U], bhr[U], bhz[U], bhn[U];
 #pragma unroll
       for (int i = 0; i < U; ++i) {
-        h[i] = row_ok ? p.h_state[static_cast<long long>(row) * H + u0 + i] : 0.f;
         bhr[i] = p.b_hh[u0 + i];
         bhz[i] = p.b_hh[H + u0 + i];
         bhn[i] = p.b_hh[2 * H + u0 + i];
       }
+      for (int grp = 0; grp < n_groups; ++grp) {
+      grow = grp * GRU_M + row;
+      row_ok = lane_ok && grow < B;
+      io = row_ok && !epilogue_io_skipped(p.flags);
+#pragma unroll
+      for (int i = 0; i < U; ++i) h[i] = row_ok ? p.h_state[static_cast<long long>(grow) * H + u0 + i] : 0.f;
       for (int t = 0; t < T; ++t) {
-        const long long rt = static_cast<long long>(row) * T + t;
+        const long long rt = static_cast<long long>(grow) * T + t;
         float gr[U], gz[U], gn[U];
 #pragma unroll
         for (int i = 0; i < U; ++i) gr[i] = gz[i] = gn[i] = 0.f;
@@ -752,7 +775,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           load_units<U>(gp + 2 * H, gn);
         }
         float acc[3 * U];
-        exchange(acc, t);
+        exchange(acc, multi ? grp : t);
         float r[U], z[U], n[U], hn[U];
 #pragma unroll
         for (int i = 0; i < U; ++i) {
@@ -762,7 +785,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           n[i] = tanh_fast(gn[i] + r[i] * hn[i]);
           h[i] = (1.f - z[i]) * n[i] + z[i] * h[i];
         }
-        if (io) store_units<U>(p.h_ext + (static_cast<long long>(t + 1) * EB + row) * H + u0, h);
+        if (io) store_units<U>(p.h_ext + (static_cast<long long>(t + 1) * EB + grow) * H + u0, h);
         // publish h_t: all epilogue threads' stores -> one release arrival per CTA
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (warp == 2 && lane == 0) {
@@ -781,8 +804,9 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       }
       if (row_ok) {
 #pragma unroll
-        for (int i = 0; i < U; ++i) p.h_state[static_cast<long long>(row) * H + u0 + i] = h[i];
+        for (int i = 0; i < U; ++i) p.h_state[static_cast<long long>(grow) * H + u0 + i] = h[i];
       }
+      }  // groups
     } else {
       float carry[U];
       float sb[4 * U];                                 // bias gradients: running sums of gr, gz, gn, ghn of this row
@@ -966,7 +990,9 @@ static int launch_gru_mw(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   // lands it as one box + one barrier per K block instead so that the MMAs of block i could start while later blocks
   // are in flight - measured slower (16 issues cost 1 500 cycles and the FIRST 8 KB box still takes ~1 700 cycles to
   // land, as long as the whole 128 KB box: the landing is latency-, not bandwidth-bound; profiles/r02_gru_pipelined.txt).
-  const bool one_box = !(a->tuning_flags & 32) && K % 64 == 0 && B % 8 == 0 && kbc * B * 128 <= 160 * 1024;
+  const int rows = B < GRU_M ? B : GRU_M;              // rows of one MMA tile / TMA box (B > 64: multi-group mode)
+  const int groups = (B + GRU_M - 1) / GRU_M;
+  const bool one_box = !(a->tuning_flags & 32) && K % 64 == 0 && B % 8 == 0 && kbc * rows * 128 <= 160 * 1024;
   {
     const uint64_t slots = BWD ? (uint64_t)T : (uint64_t)T + 1;
     const void* base = BWD ? (const void*)a->dgh : (const void*)a->h_ext;
@@ -974,12 +1000,12 @@ static int launch_gru_mw(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
     if (one_box) {
       const uint64_t dims[4] = {64, (uint64_t)B, (uint64_t)(K / 64), slots};
       const uint64_t strides[3] = {(uint64_t)K * 2, 128, (uint64_t)K * 2 * (uint64_t)a->ext_batch};
-      const uint32_t box[4] = {64, (uint32_t)B, (uint32_t)kbc, 1};
+      const uint32_t box[4] = {64, (uint32_t)rows, (uint32_t)kbc, 1};
       rc = make_tmap_bf16(&tx, base, 4, dims, strides, box, true);
     } else {
       const uint64_t dims[3] = {(uint64_t)K, (uint64_t)B, slots};
       const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)K * 2 * (uint64_t)a->ext_batch};
-      const uint32_t box[3] = {64, (uint32_t)B, 1};
+      const uint32_t box[3] = {64, (uint32_t)rows, 1};
       rc = make_tmap_bf16(&tx, base, 3, dims, strides, box, true);
     }
     if (rc) return rc;
@@ -987,7 +1013,9 @@ static int launch_gru_mw(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   GruParams p{};
   p.batch = B; p.steps = T; p.hidden = H; p.ext_batch = a->ext_batch; p.kbc = kbc;
   p.one_box = one_box ? 1 : 0;
-  p.hslot = one_box ? B * 128 : GRU_SLOT;
+  p.groups = groups;
+  p.box_rows = rows;
+  p.hslot = one_box ? rows * 128 : GRU_SLOT;
   p.gi = static_cast<const __nv_bfloat16*>(a->gi);
   p.b_hh = a->b_hh;
   p.h_ext = static_cast<__nv_bfloat16*>(a->h_ext);
@@ -1182,8 +1210,7 @@ using namespace srnn;
 
 static int check_common(const srnn_gru_args* a) {
   SRNN_CHECK_ARG(a != nullptr, "gru: null args");
-  SRNN_CHECK_ARG(a->batch > 0 && a->batch <= GRU_M, "gru: batch must be in 1..64 (got %d); split larger batches",
-                 a->batch);
+  SRNN_CHECK_ARG(a->batch > 0 && a->batch <= 8 * GRU_M, "gru: batch must be in 1..512 (got %d)", a->batch);
   SRNN_CHECK_ARG(a->steps > 0 && a->hidden > 0 && a->hidden % 8 == 0, "gru: bad steps/hidden (%d, %d)", a->steps,
                  a->hidden);
   SRNN_CHECK_ARG(a->w_hh && a->h_ext && a->gates && a->sync, "gru: null buffer");
@@ -1201,6 +1228,9 @@ static int check_common(const srnn_gru_args* a) {
 extern "C" int srnn_gru_forward(const srnn_gru_args* a, srnn_stream_t stream) {
   int rc = check_common(a);
   if (rc) return rc;
+  SRNN_CHECK_ARG(a->batch <= GRU_M || a->steps == 1,
+                 "gru_forward: more than 64 rows per launch only for steps == 1 (got batch %d, steps %d): run longer "
+                 "sequences as slot groups of <= 64 rows", a->batch, a->steps);
   SRNN_CHECK_ARG(a->gi && a->b_hh && a->h_state, "gru_forward: null buffer");
   if (a->cell == 1) {
     SRNN_CHECK_ARG(a->c_state, "lstm forward: c_state required");
@@ -1212,6 +1242,7 @@ extern "C" int srnn_gru_forward(const srnn_gru_args* a, srnn_stream_t stream) {
 extern "C" int srnn_gru_backward(const srnn_gru_args* a, srnn_stream_t stream) {
   int rc = check_common(a);
   if (rc) return rc;
+  SRNN_CHECK_ARG(a->batch <= GRU_M, "gru_backward: batch must be <= 64 per launch (got %d)", a->batch);
   SRNN_CHECK_ARG(a->dh_out && a->dgi && a->dgh && a->dh0, "gru_backward: null buffer");
   if (a->cell == 1) {
     SRNN_CHECK_ARG(a->c_init && a->dc0, "lstm backward: c_init and dc0 required");

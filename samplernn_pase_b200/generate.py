@@ -168,7 +168,7 @@ class _GenState:
         self.frame_out = torch.empty(b, fs_top, dtype=torch.uint8, device=dev)
         self.logp_frame = torch.empty(b, fs_top, sw.q, dtype=F32, device=dev) if return_logp else None
         self.logits = torch.empty(b, sw.q, dtype=F32, device=dev)
-        self.u_frame = torch.empty(fs_top, b, dtype=F32, device=dev)
+        self.rng_state = torch.zeros(3, dtype=torch.int64, device=dev)      # {seed, step, 0} of the device-side draws
 
 
 def _frame_phase(p, tiers, sw, lut, st, states, cstates):
@@ -191,8 +191,9 @@ def _frame_phase(p, tiers, sw, lut, st, states, cstates):
     j = p % sw.r0                                                            # model.py:343
     sample_step(sw, win, st.pre[:, j], sw.r0 * sw.h, st.logits)
     # model.py:203,346-348: log-softmax, draw from it, append to the window of the last FS samples
-    ops.sample_categorical(st.logits, b, sw.q, None if _GREEDY else st.u_frame[p], win, fs_top, st.frame_out[:, p],
-                           fs_top, normalise=True, logp_out=st.logp_frame[:, p] if st.logp_frame is not None else None)
+    ops.sample_categorical(st.logits, b, sw.q, None, win, fs_top, st.frame_out[:, p], fs_top, normalise=True,
+                           logp_out=st.logp_frame[:, p] if st.logp_frame is not None else None,
+                           rng_state=None if _GREEDY else st.rng_state)
 
 
 @torch.no_grad()
@@ -204,8 +205,9 @@ def generate(model, utt_conds, info, return_logp=False, generator=None, use_grap
     The FS sample steps of one top-tier frame always run the same kernels on the same buffers (which tier
     fires and which upsampled vector is read depends only on ``xi % FS``), so after an eager first frame the
     FS step programs are captured once as ONE CUDA graph and replayed for every later frame (one replay per FS
-    samples keeps the host out of the way: a replay per sample was host-bound at ~40 us per step).  The uniforms of
-    the draws are produced once per frame outside the graphs, so any ``generator`` works with them."""
+    samples keeps the host out of the way: a replay per sample was host-bound at ~40 us per step).  The draws are
+    Philox numbers generated inside the sampling kernel (seeded once per call from ``generator``), so the captured
+    step programs contain the whole sample step, RNG included."""
     dev = utt_conds.device
     b, t, _ = utt_conds.shape
     infos = info if isinstance(info, (list, tuple)) else [info] * b
@@ -223,6 +225,11 @@ def generate(model, utt_conds, info, return_logp=False, generator=None, use_grap
     cstates = [w.c0[:, None, :].expand(-1, b, -1).clone() if w.lstm else None for w in tiers]   # LSTM extension
     st = _GenState(b, fs_top, tiers, sw, c, return_logp, dev)
     st.win = y[:, :fs_top].clone()                                           # the FS samples before the frame
+    # seed of the device-side Philox draws, taken once from ``generator`` (or torch's default CUDA generator)
+    if generator is not None and generator.device.type == 'cpu':
+        st.rng_state[0:1].copy_(torch.empty(1, dtype=torch.int64).random_(0, 2 ** 62, generator=generator))
+    else:
+        st.rng_state[0:1].random_(0, 2 ** 62, generator=generator)
     graphed = use_graphs and t > 2
     ops.set_pdl(_PDL)
     try:
@@ -243,16 +250,18 @@ def _generate_frames(model, st, states, cstates, tiers, sw, lut, conds, y, t, b,
         st.conds_cur.copy_(conds[:, f: f + 1])                               # model.py:308-309: conds index xi//FS - 1
         ops.pad_cast_bf16(st.conds_cur.view(b, c), b, c, c, st.conds_b, sw.cp, sw.cp)
         frame_terms(sw, st.conds_b, st.c_term, st.cc)
-        if not _GREEDY:
-            st.u_frame.uniform_(generator=generator)                         # the frame's FS x B uniforms (outside the graphs)
         if graphed and f == 1:                                               # frame 0 ran eagerly (lazy init done)
             torch.cuda.synchronize()
             graphs = torch.cuda.CUDAGraph()                                  # ONE graph = the FS step programs of a frame
+            before = ops.launch_count
             with torch.cuda.graph(graphs):
                 for p in range(fs_top):
                     _frame_phase(p, tiers, sw, lut, st, states, cstates)
+            per_frame = ops.launch_count - before                            # kernels inside the captured graph
+            ops.launch_count = before
         if graphs is not None:
             graphs.replay()
+            ops.launch_count += per_frame
         else:
             for p in range(fs_top):
                 _frame_phase(p, tiers, sw, lut, st, states, cstates)

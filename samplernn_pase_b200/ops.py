@@ -125,13 +125,14 @@ def embed_sum(table, idx_u8, idx_ld, batch, r0, q, hidden, pre, pre_ld, relu, ou
     return out
 
 
-def sample_categorical(x, batch, q, u, win, win_len, out, out_ld, normalise=False, logp_out=None):
+def sample_categorical(x, batch, q, u, win, win_len, out, out_ld, normalise=False, logp_out=None, rng_state=None):
     """Draw one code per row from exp(log-probabilities) (inverse CDF with the uniforms ``u``; arg-max when ``u`` is
     None), append it to the row's window ``win`` (shifted left by one) and store it at ``out[b*out_ld]``.  With
     ``normalise`` the rows of ``x`` are raw logits and the log-softmax is taken first (written to ``logp_out``)."""
     _need(x, F32, 'sample input')
     call('srnn_sample_categorical', ptr(x), x.stride(0), batch, q, int(normalise), ptr(logp_out),
-         logp_out.stride(0) if logp_out is not None else 0, ptr(u), ptr(win), win_len, ptr(out), out_ld, stream())
+         logp_out.stride(0) if logp_out is not None else 0, ptr(u), ptr(rng_state), ptr(win), win_len, ptr(out), out_ld,
+         stream())
     _count()
 
 
@@ -312,6 +313,7 @@ def gemm_nll(mode, a, w, bias, target, m, k, lda, ldw, lse=None, logp_target=Non
 # recurrence
 # ----------------------------------------------------------------------------------------------
 GRU_MAX_BATCH = 64
+GRU_MAX_STEP_BATCH = 512
 gru_tuning_flags = 0     # srnn_gru_args.tuning_flags (scripts/gru_microbench.py sweeps them)
 gru_debug_ts = None      # int64 [256, 8] tensor receiving CTA 0's pipeline timestamps
 gru_units_per_cta = 8    # 16 halves the recurrent kernels' CTA count (SMs left free for concurrent GEMMs)
@@ -324,8 +326,10 @@ gru_last_sync = None
 def _gru_call(name, batch, steps, hidden, cell=0, **bufs):
     """Runs the persistent kernel over slot groups of <= 64 rows (independent sequences).
     ``bufs``: field -> (tensor, elements per batch row); time-major buffers advance by one row."""
-    for b0 in range(0, batch, GRU_MAX_BATCH):
-        nb = min(GRU_MAX_BATCH, batch - b0)
+    # a single forward timestep (generation) takes all rows in one launch: the kernel walks the 64-row blocks itself
+    group = GRU_MAX_STEP_BATCH if (steps == 1 and name == 'srnn_gru_forward') else GRU_MAX_BATCH
+    for b0 in range(0, batch, group):
+        nb = min(group, batch - b0)
         a = GruArgs()
         a.batch, a.steps, a.hidden, a.ext_batch, a.cell = nb, steps, hidden, batch, cell
         for key, (t, per_row) in bufs.items():

@@ -79,5 +79,5 @@ timed('embed_sum 256 x (4 rows of 1024)', lambda: ops.embed_sum(table, win[:, 12
 logits = torch.randn(bg, q, device=dev)
 u = torch.rand(bg, device=dev)
 picks = torch.empty(bg, dtype=torch.uint8, device=dev)
-timed('log-softmax + draw 256 x 256', lambda: ops.sample_categorical(logits, bg, q, u, win, 16, picks, 1, normalise=True),
+timed("log-softmax + draw 256 x 256", lambda: ops.sample_categorical(logits, bg, q, u, win, 16, picks, 1, normalise=True),
       nbytes=bg * q * 4)

@@ -628,3 +628,80 @@ def test_sample_categorical_inverse_cdf_argmax_and_window(ops):
     freq = torch.bincount(draws.long().cpu(), minlength=q).double() / n
     p = torch.exp(row[0].double())
     assert float((freq - p).abs().max()) <= 5 * float(torch.sqrt(p.max() / n)) + 1e-4
+
+
+def test_sample_categorical_device_side_philox_draws(ops):
+    """Device-side draws (rng_state = {seed, step, 0}): the empirical distribution matches, the same seed reproduces the
+    same picks, every launch advances the step (so replays of a captured graph draw fresh numbers), different
+    utterances at one step and one utterance at different steps draw different uniforms."""
+    q, n = 256, 200_000
+    g = torch.Generator().manual_seed(11)
+    row = torch.log_softmax(torch.randn(1, q, generator=g) * 2, dim=1)
+    rows = row.expand(n, q).contiguous().cuda()
+    state = torch.tensor([1234567, 0, 0], dtype=torch.int64, device='cuda')
+    d1 = torch.empty(n, dtype=torch.uint8, device='cuda')
+    ops.sample_categorical(rows, n, q, None, None, 0, d1, 1, rng_state=state)
+    assert state.tolist() == [1234567, 1, 0]                                   # step advanced, done-counter reset
+    freq = torch.bincount(d1.long().cpu(), minlength=q).double() / n
+    p = torch.exp(row[0].double())
+    assert float((freq - p).abs().max()) <= 5 * float(torch.sqrt(p.max() / n)) + 1e-4
+    d2 = torch.empty_like(d1)
+    ops.sample_categorical(rows, n, q, None, None, 0, d2, 1, rng_state=state)  # next step: different draws
+    assert state.tolist() == [1234567, 2, 0]
+    assert 0.5 < float((d1 != d2).float().mean()) < 1.0
+    state2 = torch.tensor([1234567, 0, 0], dtype=torch.int64, device='cuda')
+    d3 = torch.empty_like(d1)
+    ops.sample_categorical(rows, n, q, None, None, 0, d3, 1, rng_state=state2)  # same seed and step: same picks
+    assert torch.equal(d1, d3)
+    state3 = torch.tensor([7654321, 0, 0], dtype=torch.int64, device='cuda')
+    ops.sample_categorical(rows, n, q, None, None, 0, d3, 1, rng_state=state3)
+    assert 0.5 < float((d1 != d3).float().mean()) < 1.0
+    # inside a CUDA graph: every replay advances the step
+    small = rows[:300].contiguous()
+    out = torch.zeros(300, dtype=torch.uint8, device='cuda')
+    st = torch.tensor([99, 0, 0], dtype=torch.int64, device='cuda')
+    ops.sample_categorical(small, 300, q, None, None, 0, out, 1, rng_state=st)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ops.sample_categorical(small, 300, q, None, None, 0, out, 1, rng_state=st)
+    seen = []
+    for _ in range(3):
+        graph.replay()
+        torch.cuda.synchronize()
+        seen.append(out.clone())
+    assert int(st[1]) == 4 and not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])
+
+
+def test_gru_single_step_many_rows_in_one_launch(ops):
+    """Generation's recurrent step: steps == 1 with more than 64 rows runs as ONE launch that walks the 64-row blocks
+    (weights fetched once) and must equal the per-block launches bit for bit (GRU and LSTM, ragged last block)."""
+    h = 256
+    for cell, ng in ((0, 3), (1, 4)):
+        for bsz in (130, 256):
+            gi = rnd(bsz, ng * h, seed=cell).to(BF16)
+            w_hh = rnd(ng * h, h, scale=1 / math.sqrt(h), seed=1).to(BF16)
+            b_hh = rnd(ng * h, scale=0.1, seed=2)
+            h0 = rnd(bsz, h, scale=0.5, seed=3)
+            c0 = rnd(bsz, h, scale=0.5, seed=4)
+
+            def run(max_rows):
+                old = ops.GRU_MAX_STEP_BATCH
+                ops.GRU_MAX_STEP_BATCH = max_rows
+                try:
+                    h_ext = torch.zeros(2, bsz, h, dtype=BF16, device='cuda')
+                    h_ext[0] = h0.to(BF16)
+                    hall = torch.zeros(bsz, h, dtype=BF16, device='cuda')
+                    hs, cs = h0.clone(), c0.clone()
+                    gates = torch.zeros(bsz, (ng + 1) * h, dtype=BF16, device='cuda')
+                    if cell:
+                        ops.lstm_forward(gi, w_hh, b_hh, h_ext, hall, hs, cs, gates, bsz, 1, h)
+                    else:
+                        ops.gru_forward(gi, w_hh, b_hh, h_ext, hall, hs, gates, bsz, 1, h)
+                    return hall, hs, cs, gates, h_ext
+                finally:
+                    ops.GRU_MAX_STEP_BATCH = old
+
+            ref = run(64)
+            got = run(512)
+            assert all(torch.equal(a, b) for a, b in zip(got, ref)), (cell, bsz)
