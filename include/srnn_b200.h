@@ -200,15 +200,17 @@ typedef struct srnn_gru_args {
   void* dgi;             /* bf16 [batch*steps, 3H] batch-major, out */
   void* dgh;             /* bf16 [steps, ext_batch, 3H] TIME-major, out (also the per-step exchange buffer) */
   float* dh0;            /* fp32 [batch, H] out: dL/dh_init */
-  uint32_t* sync;        /* >= 1 KB, zeroed by the caller before every launch: [0] grid-wide arrival counter; on return
-                            [32] holds the number of exchange attempts the kernel rejected and repeated (see below) */
+  uint32_t* sync;        /* >= 32 KB (8192 uint32), zeroed by the caller before every launch: [0] grid-wide arrival
+                            counter, [64 + 32 j] release flag of CTA j; on return [32] holds the number of exchange
+                            attempts the kernel rejected and repeated (see below) */
   int32_t tuning_flags;  /* 0 = defaults.  Every documented bit leaves the results unchanged:
                             2 = force a cooperative launch for steps == 1, 16 = strict exchange protocol (release
                             increment + acquire fence instead of relaxed increment + validated read), 32 = land the
                             per-step operand as one TMA box per K block instead of ONE box, 64 = two MMA-issuing warps, bits 12-13 = polls of the arrival
                             counter kept in flight (0: 1, 1: 2, 2: 4), bits 14-15 = their spacing ((n+1)*64 cycles),
                             bits 16-19 = n*32 cycles to hold the TMA read back after the wait, bits 20-23 = cycles before the first
-                            poll of a wait (0: 256, n: (n-1)*128), 128 = debug_ts receives the global
+                            poll of a wait (0: 256, n: (n-1)*128), 1 << 24 = every CTA polls the arrival counter itself
+                            (default: the last arriver releases the others through per-CTA flag lines), 128 = debug_ts receives the global
                             timer of every CTA at timestep 24, bits 8-11 = force a cluster size.  Bits 1 and 4 exist only
                             in instrumented (-DSRNN_DEBUG) builds and are rejected with SRNN_ERR_ARG otherwise. */
   uint64_t* debug_ts;    /* NULL, or [256][8] clock64 stamps of CTA 0's pipeline events (profiling aid) */

@@ -202,11 +202,33 @@ __device__ __forceinline__ void grid_wait(const uint32_t* counter, uint32_t targ
 // stores.  Default: RELAXED - the data stores and the increment travel to L2 concurrently and consumers validate what
 // they read (see exchange()).  Tuning flag 16 = strict protocol: release increment (MEMBAR.ALL.GPU + RED) here and an
 // acquire fence after the consumer's wait.
-__device__ __forceinline__ void publish(uint32_t* counter, int flags) {
-  if (flags & 16) {
-    red_release_gpu_add(counter, 1u);
-  } else {
-    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+//
+// Release fan-out (default): the increment is an ATOM whose return value tells the CTA whether it was the LAST arriver
+// of the round; that CTA alone then writes the round number into one flag line per CTA (sync[64 + 32 j], 128 B apart;
+// 4 store instructions of one warp for 128 CTAs), and every CTA polls only its own line.  Nobody polls the counter, so
+// the increments do not queue behind 128 readers of the same L2 line, and a poll is an uncontended round trip.
+// Tuning flag 1 << 24 restores the older scheme (every CTA polls the counter itself).
+// Called by the whole of epilogue warp 2 (converged); `round` = publishes of this CTA so far, this one included.
+constexpr int GRU_FLAG_BASE = 64, GRU_FLAG_STRIDE = 32;            // in uint32 words of the sync buffer
+__device__ __forceinline__ void publish(uint32_t* sync, int flags, uint32_t round, uint32_t n_ctas, int lane) {
+  const bool strict = (flags & 16) != 0;
+  if (flags & (1 << 24)) {                                       // legacy: plain counter, polled by everyone
+    if (lane == 0) {
+      if (strict) red_release_gpu_add(sync, 1u);
+      else asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(sync), "r"(1u) : "memory");
+    }
+    return;
+  }
+  uint32_t old = 0;
+  if (lane == 0) {
+    if (strict) asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(sync), "r"(1u) : "memory");
+    else asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(sync), "r"(1u) : "memory");
+  }
+  old = __shfl_sync(0xffffffffu, old, 0);
+  if (old + 1u == n_ctas * round) {                              // last arriver of this round: release everyone
+    if (strict) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    for (uint32_t j = static_cast<uint32_t>(lane); j < n_ctas; j += 32u)
+      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(sync + GRU_FLAG_BASE + GRU_FLAG_STRIDE * j), "r"(round) : "memory");
   }
 }
 constexpr uint32_t GRU_MAX_RETRIES = 256;
@@ -387,7 +409,11 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         if (mw == 0) {
           if (fresh && s > 0 && !multi && !grid_wait_skipped(p.flags)) {
             if (pre_poll) spin_cycles(pre_poll);
-            grid_wait(p.sync, G * static_cast<uint32_t>(s), strict, poll_depth, poll_gap);
+            if (p.flags & (1 << 24))
+              grid_wait(p.sync, G * static_cast<uint32_t>(s), strict, poll_depth, poll_gap);
+            else                                     // own flag line, written by the last arriver of round s
+              grid_wait(p.sync + GRU_FLAG_BASE + GRU_FLAG_STRIDE * blockIdx.x, static_cast<uint32_t>(s), strict, poll_depth,
+                        poll_gap);
             if (hold) spin_cycles(hold);
             GRU_TS(0, s);
           }
@@ -636,7 +662,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         }
         if (io) store_units<U>(p.h_ext + (static_cast<long long>(t + 1) * EB + grow) * H + u0, h);
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && lane == 0) publish(p.sync, p.flags);
+        if (warp == 2 && T > 1) publish(p.sync, p.flags, static_cast<uint32_t>(t + 1), G, lane);   // T == 1: nobody waits
         if (p.hall && io) store_units<U>(p.hall + rt * H + u0, h);
         if (p.gates && io) {                           // saved for backward: i, f, g, o, c_t  (5H per row)
           __nv_bfloat16* sp = p.gates + rt * 5 * H + u0;
@@ -718,7 +744,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           store_units<U>(ghp + 3 * H, po);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && lane == 0) publish(p.sync, p.flags);
+        if (warp == 2) publish(p.sync, p.flags, static_cast<uint32_t>(s + 1), G, lane);
         if (io) {                                               // same values, batch-major, for the GEMMs
           __nv_bfloat16* gip = p.dgi + rt * 4 * H + u0;
           store_units<U>(gip, pi);
@@ -788,9 +814,9 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         if (io) store_units<U>(p.h_ext + (static_cast<long long>(t + 1) * EB + grow) * H + u0, h);
         // publish h_t: all epilogue threads' stores -> one release arrival per CTA
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && lane == 0) {
-          GRU_TS(6, t);
-          publish(p.sync, p.flags);
+        if (warp == 2) {
+          if (lane == 0) GRU_TS(6, t);
+          if (T > 1) publish(p.sync, p.flags, static_cast<uint32_t>(t + 1), G, lane);   // T == 1: nobody waits
         }
         // the batch-major copy of h_t (GEMM operand) and the saved gates are off the critical path
         if (p.hall && io) store_units<U>(p.hall + rt * H + u0, h);
@@ -861,9 +887,9 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           store_units<U>(ghp + 2 * H, ghn);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && lane == 0) {
-          GRU_TS(6, s);
-          publish(p.sync, p.flags);
+        if (warp == 2) {
+          if (lane == 0) GRU_TS(6, s);
+          publish(p.sync, p.flags, static_cast<uint32_t>(s + 1), G, lane);
         }
         if (io) {                                               // dgi is only read after the kernel
           __nv_bfloat16* gip = p.dgi + rt * 3 * H + u0;

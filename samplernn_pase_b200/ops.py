@@ -314,6 +314,7 @@ def gemm_nll(mode, a, w, bias, target, m, k, lda, ldw, lse=None, logp_target=Non
 # ----------------------------------------------------------------------------------------------
 GRU_MAX_BATCH = 64
 GRU_MAX_STEP_BATCH = 512
+GRU_SYNC_WORDS = 8192       # srnn_gru_args.sync: arrival counter, statistics and one release-flag line per CTA
 gru_tuning_flags = 0     # srnn_gru_args.tuning_flags (scripts/gru_microbench.py sweeps them)
 gru_debug_ts = None      # int64 [256, 8] tensor receiving CTA 0's pipeline timestamps
 gru_units_per_cta = 8    # 16 halves the recurrent kernels' CTA count (SMs left free for concurrent GEMMs)
@@ -343,9 +344,9 @@ def _gru_call(name, batch, steps, hidden, cell=0, **bufs):
             # runs steps + 1 rounds and does wait at round 1, so it always gets a freshly zeroed counter.)
             sync = _gru_scratch.get(dev)
             if sync is None:
-                sync = _gru_scratch[dev] = torch.zeros(256, dtype=torch.int32, device=dev)
+                sync = _gru_scratch[dev] = torch.zeros(GRU_SYNC_WORDS, dtype=torch.int32, device=dev)
         else:
-            sync = torch.zeros(256, dtype=torch.int32, device=dev)
+            sync = torch.zeros(GRU_SYNC_WORDS, dtype=torch.int32, device=dev)
         a.sync = sync.data_ptr()
         global gru_last_sync
         gru_last_sync = sync               # [32] = exchange attempts the launch rejected and repeated (tests read it)
