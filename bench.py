@@ -392,6 +392,9 @@ def run_gpu(args):
             ncu = json.load(open(os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')))
         except (OSError, ValueError):
             pass
+        if args.workload == 'config2' and not args.global_batch:
+            for r in rec:                                 # measured DRAM bytes per launch where a capture exists
+                r['traffic'] = ncu.get(r['kernel'])
         top = rec[0] if rec else None
         roofline = None
         if top:

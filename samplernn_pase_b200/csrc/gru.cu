@@ -203,16 +203,17 @@ __device__ __forceinline__ void grid_wait(const uint32_t* counter, uint32_t targ
 // they read (see exchange()).  Tuning flag 16 = strict protocol: release increment (MEMBAR.ALL.GPU + RED) here and an
 // acquire fence after the consumer's wait.
 //
-// Release fan-out (default): the increment is an ATOM whose return value tells the CTA whether it was the LAST arriver
-// of the round; that CTA alone then writes the round number into one flag line per CTA (sync[64 + 32 j], 128 B apart;
-// 4 store instructions of one warp for 128 CTAs), and every CTA polls only its own line.  Nobody polls the counter, so
-// the increments do not queue behind 128 readers of the same L2 line, and a poll is an uncontended round trip.
-// Tuning flag 1 << 24 restores the older scheme (every CTA polls the counter itself).
+// Release fan-out (tuning flag 1 << 24, an experiment that LOST): the increment is an ATOM whose return value tells the
+// CTA whether it was the LAST arriver of the round; that CTA alone then writes the round number into one flag line per
+// CTA (sync[64 + 32 j], 128 B apart; 4 store instructions of one warp for 128 CTAs), and every CTA polls only its own
+// line, so nobody reads the counter's L2 line.  Measured on one box, B=64 H=1024, us per timestep fwd / bwd: every CTA
+// polling the counter 3.64 / 4.49, fan-out 4.29 / 5.00 - the 128 returning atomics serialise on the counter and the last
+// arriver's return + flag stores + a second poll round trip cost more than the reader queue they remove.
 // Called by the whole of epilogue warp 2 (converged); `round` = publishes of this CTA so far, this one included.
 constexpr int GRU_FLAG_BASE = 64, GRU_FLAG_STRIDE = 32;            // in uint32 words of the sync buffer
 __device__ __forceinline__ void publish(uint32_t* sync, int flags, uint32_t round, uint32_t n_ctas, int lane) {
   const bool strict = (flags & 16) != 0;
-  if (flags & (1 << 24)) {                                       // legacy: plain counter, polled by everyone
+  if (!(flags & (1 << 24))) {                                    // default: plain counter, polled by everyone
     if (lane == 0) {
       if (strict) red_release_gpu_add(sync, 1u);
       else asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(sync), "r"(1u) : "memory");
@@ -409,9 +410,9 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         if (mw == 0) {
           if (fresh && s > 0 && !multi && !grid_wait_skipped(p.flags)) {
             if (pre_poll) spin_cycles(pre_poll);
-            if (p.flags & (1 << 24))
+            if (!(p.flags & (1 << 24)))
               grid_wait(p.sync, G * static_cast<uint32_t>(s), strict, poll_depth, poll_gap);
-            else                                     // own flag line, written by the last arriver of round s
+            else                                     // experiment: own flag line, written by the last arriver of round s
               grid_wait(p.sync + GRU_FLAG_BASE + GRU_FLAG_STRIDE * blockIdx.x, static_cast<uint32_t>(s), strict, poll_depth,
                         poll_gap);
             if (hold) spin_cycles(hold);
