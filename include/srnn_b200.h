@@ -167,7 +167,9 @@ typedef struct srnn_nll_args {
   const void* w; int64_t ldw;   /* bf16 [256,k] */
   const float* bias;            /* [256] */
   const uint8_t* target;        /* [m] */
-  float* lse; float* logp_target;        /* [m] (modes 0,1) */
+  float* lse; float* logp_target;        /* [m]: written by modes 0,1.  Modes 2,3: if lse is non-null it must hold the
+                                            forward's values and the backward makes one pass over the row instead of
+                                            three (max, sum of exp, gradient) */
   float* logp; int64_t ldlogp;           /* mode 1 */
   const float* row_grad;                 /* [m] mode 2 */
   const float* g; int64_t ldg;           /* [m,256] mode 3 */

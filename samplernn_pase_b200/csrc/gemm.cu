@@ -456,28 +456,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       } else {
         // log-softmax + NLL family; BN == 256 == N, one thread owns one full row of logits in TMEM
         const long long row = static_cast<long long>(wk.b) * p.m + j;
-        float mx = -INFINITY;
-        for (int c = 0; c < 8; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_addr + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]) + sbias[c * 32 + i]);
-        }
         const int tgt = row_ok ? static_cast<int>(p.target[row]) : 0;
-        float sum = 0.f, xt = 0.f;
-        for (int c = 0; c < 8; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_addr + c * 32, v);
-          tmem_ld_wait();
+        float lse, xt = 0.f;
+        if (p.nll_mode >= 2 && p.lse != nullptr) {
+          // backward with the forward's log-sum-exp at hand: ONE pass over the row instead of three (the logits are
+          // recomputed by the same GEMM, so exp(x - lse) is the forward's softmax up to the accumulation order)
+          lse = row_ok ? p.lse[row] : 0.f;
+        } else {
+          float mx = -INFINITY;
+          for (int c = 0; c < 8; ++c) {
+            uint32_t v[32];
+            tmem_ld32(t_addr + c * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = __uint_as_float(v[i]) + sbias[c * 32 + i];
-            sum += expf(x - mx);
-            if (c * 32 + i == tgt) xt = x;
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]) + sbias[c * 32 + i]);
           }
+          float sum = 0.f;
+          for (int c = 0; c < 8; ++c) {
+            uint32_t v[32];
+            tmem_ld32(t_addr + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float x = __uint_as_float(v[i]) + sbias[c * 32 + i];
+              sum += expf(x - mx);
+              if (c * 32 + i == tgt) xt = x;
+            }
+          }
+          lse = mx + logf(sum);
         }
-        const float lse = mx + logf(sum);
         if (p.nll_mode <= 1) {
           if (row_ok) {
             p.lse[row] = lse;

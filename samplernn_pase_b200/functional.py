@@ -357,21 +357,21 @@ class SampleLevelFn(torch.autograd.Function):
             out = logp.view(b, rf, q)
         ctx.dims = (b, w, l, c, h, q, r0, rf, m, fsz, cp, fused)
         ctx.save_for_backward(onehot, e_b, we_t, inv_e, conds_b, wcs_t, c_frame, upper_c, tt, wcomb_t, h1, w2, w2_t, inv_2,
-                              h2, w3, w3_t, inv_3, target_u8, b3c, eg, ev, w2g, w2v, w3g, w3v)
+                              h2, w3, w3_t, inv_3, target_u8, b3c, eg, ev, w2g, w2v, w3g, w3v, lse)
         return out
 
     @staticmethod
     def backward(ctx, gout):
         (onehot, e_b, we_t, inv_e, conds_b, wcs_t, c_frame, upper_c, tt, wcomb_t, h1, w2, w2_t, inv_2, h2, w3, w3_t, inv_3,
-         target_u8, b3c, eg, ev, w2g, w2v, w3g, w3v) = ctx.saved_tensors
+         target_u8, b3c, eg, ev, w2g, w2v, w3g, w3v, lse) = ctx.saved_tensors
         b, w, l, c, h, q, r0, rf, m, fsz, cp, fused = ctx.dims
         dev = gout.device
         gout = gout.contiguous().float()
         dlog = _empty(m, q, device=dev)
         if fused:
-            ops.gemm_nll(2, h2, w3, b3c, target_u8, m, h, h, h, row_grad=gout, dlogits=dlog)
+            ops.gemm_nll(2, h2, w3, b3c, target_u8, m, h, h, h, row_grad=gout, dlogits=dlog, lse=lse)
         else:
-            ops.gemm_nll(3, h2, w3, b3c, target_u8, m, h, h, h, g=gout, dlogits=dlog)
+            ops.gemm_nll(3, h2, w3, b3c, target_u8, m, h, h, h, g=gout, dlogits=dlog, lse=lse)
         # adapt
         d_b3 = ops.colsum(dlog, m, q, q)
         dw3 = _zeros(q, h, device=dev)

@@ -264,10 +264,15 @@ def test_gemm_nll_all_modes(ops, m, k):
     ops.gemm_nll(2, a, w, bias, tgt, m, k, k, k, row_grad=rg, dlogits=dl)
     ref = rg[:, None] * (torch.nn.functional.one_hot(tgt.long(), 256).float() - logp_ref.exp())
     assert rel_l2(dl, ref) < 4e-3
+    dl1 = torch.empty_like(dl)                                   # single pass with the forward's lse: same result
+    ops.gemm_nll(2, a, w, bias, tgt, m, k, k, k, row_grad=rg, dlogits=dl1, lse=lse)
+    assert rel_l2(dl1, ref) < 4e-3 and rel_l2(dl1, dl) < 1e-3
     g = rnd(m, 256, seed=4)
     ops.gemm_nll(3, a, w, bias, tgt, m, k, k, k, g=g, dlogits=dl)
     ref = g - logp_ref.exp() * g.sum(1, keepdim=True)
     assert rel_l2(dl, ref) < 4e-3
+    ops.gemm_nll(3, a, w, bias, tgt, m, k, k, k, g=g, dlogits=dl1, lse=lse)
+    assert rel_l2(dl1, ref) < 4e-3 and rel_l2(dl1, dl) < 1e-3
 
 
 # ------------------------------------------------------------------------------------------------
