@@ -80,3 +80,31 @@ def test_product_does_not_import_the_oracle():
         for f in files:
             if f.endswith(('.py', '.cu', '.cuh')):
                 assert not pat.search(open(os.path.join(root, f)).read()), f
+
+
+def test_carry_state_dict_round_trip_keeps_reference_keys():
+    """The carried hidden state is persisted NEXT TO state_dict() (opt-in): the parameter state_dict keeps exactly the
+    reference's keys, and a model restored from (state_dict, carry_state_dict) continues from the same state."""
+    from samplernn_pase_b200 import SampleRNNModel
+    g = Golden('gru3_multilayer')
+    s = g.spec_kwargs()
+
+    def make():
+        m = SampleRNNModel('embedding', int(g.meta['n_spk']), 15, 'acoustic', [9, 5, 4, 3], 10, 50, s['sequence_length'],
+                           s['ratios'], s['rnn_layers'], s['rnn_hidden_size'], True, 256)
+        m.load_state_dict(g.state_dict())
+        return m
+
+    a = make()
+    keys = list(a.state_dict().keys())
+    a._init_rnn_states(3)
+    for n, layer in enumerate(a.frames_layers):
+        a._state[n] = torch.randn(layer.rnn_layers, 3, layer.rnn_hidden_size)
+        a._state_valid[n] = [True, False, True]
+    carry = a.carry_state_dict()
+    assert list(a.state_dict().keys()) == keys == list(g.state_dict().keys())
+    b = make()
+    b.load_carry_state_dict(carry)
+    for n in range(len(a.frames_layers)):
+        assert torch.equal(b._state[n], a._state[n]) and b._state_valid[n] == [True, False, True]
+    assert [st is None for st in b.rnn_states[b.frames_layers[0]]] == [False, True, False]
