@@ -107,11 +107,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin with a watchdog: a protocol bug traps (launch error) instead of hanging the GPU box.
+// Spin with a watchdog: a protocol bug traps (launch error) instead of hanging the GPU box.  The limit is wall-clock
+// (20 s without progress), not a spin count, so time-slicing under a debugger, profiler replay or MPS cannot fire it.
+__device__ __forceinline__ unsigned long long watchdog_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if ((++spins & 0xFFFFFu) == 0) {
+      const unsigned long long now = watchdog_now_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) __trap();
+    }
   }
 }
 

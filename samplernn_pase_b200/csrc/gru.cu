@@ -266,7 +266,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
-    if (++spins > (1u << 26)) __trap();
+    if ((++spins & 0xFFFFFu) == 0 && spins > (1u << 30)) __trap();
   }
 }
 
@@ -470,8 +470,13 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         if (mw == 0) {
           GRU_TS(3, s);
           uint32_t v, spins = 0;
+          unsigned long long w0 = 0;
           while (((v = ctl[0]) >> 1) != attempt) {   // the epilogue's verdict on this attempt
-            if (++spins > (1u << 28)) __trap();
+            if ((++spins & 0xFFFFFu) == 0) {
+              const unsigned long long now = globaltimer_ns();
+              if (w0 == 0) w0 = now;
+              else if (now - w0 > 20000000000ull) __trap();
+            }
           }
           tc_fence_after();
           if (v & 1u) {

@@ -444,3 +444,46 @@ def test_full_size_config2_step_properties():
         model.reset_states()
         b = model(x.cuda(), y.cuda(), c.cuda(), info, reset)[0]
     assert torch.equal(a, b)
+
+
+def test_single_frame_sequences_forward_backward_vs_cpu_oracle():
+    """sequence_length == 1: the top tier runs ONE timestep per chunk (forward launches without a grid handshake,
+    backward with steps + 1 = 2 rounds on a freshly zeroed arrival counter - a reused counter made the second round
+    read an exchange slot before it was written).  Three chunks with carry; loss, every gradient (incl. rnn_h0) and
+    the carried state against the CPU oracle."""
+    from samplernn_pase_b200 import SampleRNNModel
+    spec = O.ModelSpec([4, 2], [1, 2], [64, 64], 1)
+    params = O.init_params(spec, conds_speaker_n=5, perturb=0.1)
+    model = SampleRNNModel('embedding', 5, 15, 'acoustic', [9, 5, 4, 3], 10, 50, 1, [4, 2], [1, 2], [64, 64], True,
+                           256).cuda()
+    model.load_state_dict(params)
+    bsz = 6
+    wav, conds, spk = O.synthetic_utterances(spec, bsz, 3, n_speakers=5)
+    info = [{'speaker': {'index': int(s)}} for s in spk]
+    p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    state = None
+    for k in range(3):
+        x, y, c = O.chunk_of(spec, wav, conds, k)
+        reset = [1] * bsz if k == 0 else [0, 0, 1, 0, 0, 0]
+        model.zero_grad()
+        for v in p_ref.values():
+            v.grad = None
+        y_hat, yq = model(x.cuda(), y.cuda(), c.cuda(), info, torch.tensor(reset))
+        loss = torch.nn.functional.nll_loss(y_hat.view(-1, 256), yq.view(-1))
+        loss.backward()
+        logp, tgt, state, _ = O.forward(p_ref, spec, x, y, c, spk, reset, state)
+        ref = O.nll(logp, tgt)
+        ref.backward()
+        assert torch.equal(yq.cpu(), tgt)
+        assert abs(float(loss) - float(ref)) <= 5e-4 * float(ref)
+        names = [n for n, _ in model.named_parameters()]
+        got = torch.cat([dict(model.named_parameters())[n].grad.flatten().cpu() for n in names])
+        want = torch.cat([(p_ref[n].grad if p_ref[n].grad is not None else torch.zeros_like(p_ref[n])).flatten() for n in names])
+        r, cs = rel_l2(got, want), cosine(got, want)
+        report(f'single-frame chunks (L=1) chunk {k}: loss {float(loss):.6f} ref {float(ref):.6f} ALL GRADS rel_l2 {r:.3e} cos {cs:.6f}')
+        assert r <= 0.15 and cs >= 0.99, (k, r, cs)
+        for n in (0, 1):
+            h0g = dict(model.named_parameters())[f'frames_layers.{n}.rnn_h0'].grad.cpu()
+            h0r = p_ref[f'frames_layers.{n}.rnn_h0'].grad
+            assert rel_l2(h0g, h0r) <= 0.2, (k, n, rel_l2(h0g, h0r))
+            assert float((model._state[n].cpu() - state.h[n]).abs().max()) <= 3e-2
