@@ -148,3 +148,86 @@ def test_device_resident_loader_matches_host_loader():
         assert xd.is_cuda and yd.is_cuda and cd.is_cuda and not rd.is_cuda
         assert torch.equal(xd.cpu(), x) and torch.equal(yd.cpu(), y) and torch.equal(cd.cpu(), c)
         assert torch.equal(rd, r) and info == infod
+
+
+def test_full_width_config3_lstm_pase_and_fused_loss_vs_cpu_oracle():
+    """BASELINE config 3 shape at full width (LSTM tiers, H=1024, 100-d PASE speaker vector; definitions are the oracle's
+    O-C / O-D - parity unpinned by the reference) through the FUSED-loss path: loss, all gradients and the carried
+    (h, c) against the CPU oracle, two chunks."""
+    if not torch.cuda.is_available():
+        pytest.skip('needs a GPU')
+    from samplernn_pase_b200 import SampleRNNModel
+    torch.set_num_threads(os.cpu_count() or 1)
+    s_dim, seq, bsz = 100, 8, 8
+    spec = O.ModelSpec([4, 4], [1, 1], [1024, 1024], seq, cell='lstm')
+    params = O.init_params(spec, conds_speaker_n=3, conds_speaker_size=s_dim, perturb=0.1)
+    model = SampleRNNModel('pase', 3, s_dim, 'acoustic', [9, 5, 4, 3], 10, 50, seq, [4, 4], [1, 1], [1024, 1024], True, 256,
+                           rnn_cell='lstm', fused_loss=True).cuda()
+    model.load_state_dict(params)
+    wav, conds, _ = O.synthetic_utterances(spec, bsz, 2)
+    vecs = torch.randn(bsz, s_dim, generator=torch.Generator().manual_seed(9))
+    info = [{'speaker': {'pase': vecs[i]}} for i in range(bsz)]
+    p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    names = [n for n, _ in model.named_parameters() if n != 'conds_mixer.speaker_embedding.weight']
+    state = None
+    for k in range(2):
+        x, y, c = O.chunk_of(spec, wav, conds, k)
+        reset = [1] * bsz if k == 0 else [0, 0, 1, 0, 0, 0, 0, 0]
+        model.zero_grad()
+        for v in p_ref.values():
+            v.grad = None
+        y_hat, tgt0 = model(x.cuda(), y.cuda(), c.cuda(), info, torch.tensor(reset))
+        assert y_hat.shape[2] == 1                                                 # fused: log p(target) only
+        loss = torch.nn.functional.nll_loss(y_hat.view(-1, 1), tgt0.view(-1))     # runner.py:52 verbatim
+        loss.backward()
+        logp, tgt, state, _ = O.forward(p_ref, spec, x, y, c, None, reset, state, speaker_vectors=vecs)
+        ref = O.nll(logp, tgt)
+        ref.backward()
+        rel = abs(float(loss) - float(ref)) / abs(float(ref))
+        bad, worst = [], 0.0
+        for n in names:
+            want = p_ref[n].grad if p_ref[n].grad is not None else torch.zeros_like(p_ref[n])
+            got = dict(model.named_parameters())[n].grad.detach().cpu()
+            if float(want.norm()) < 1e-7:
+                continue
+            r, cs = rel_l2(got, want), cosine(got, want)
+            worst = max(worst, r)
+            if not (r <= 0.1 and cs >= 0.995):
+                bad.append((n, r, cs))
+        report(f'config3 LSTM+PASE H=1024 fused-loss chunk {k}: loss {float(loss):.6f} oracle {float(ref):.6f} rel {rel:.2e} '
+               f'worst per-tensor grad rel_l2 {worst:.3e}')
+        assert rel <= 1e-3 and not bad, (k, rel, bad)
+        for n in range(2):
+            assert float((model._state[n].cpu() - state.h[n]).abs().max()) <= 3e-2
+            assert float((model._state_c[n].cpu() - state.c[n]).abs().max()) <= 6e-2
+
+
+def test_full_width_generation_consistent_with_teacher_forcing():
+    """SURVEY probe P8 at the config-5 shape in width: H=1024, ratios [4,4], 130 utterances (three 64-row blocks in the
+    single recurrent launch) x 3 frames, CUDA-graph path with device-side Philox draws: the log-probabilities every
+    sample was drawn from must equal the CPU oracle's teacher-forced log-probabilities of the generated sequence."""
+    if not torch.cuda.is_available():
+        pytest.skip('needs a GPU')
+    from samplernn_pase_b200 import SampleRNNModel
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = O.ModelSpec([4, 4], [1, 1], [1024, 1024], 3)
+    params = O.init_params(spec, conds_speaker_n=126, perturb=0.1)
+    model = SampleRNNModel('embedding', 126, 15, 'acoustic', [9, 5, 4, 3], 10, 50, 3, [4, 4], [1, 1], [1024, 1024], True,
+                           256).cuda()
+    model.load_state_dict(params)
+    bsz, t, fs = 130, 3, 16
+    utt = torch.randn(bsz, t, 43, generator=torch.Generator().manual_seed(3))
+    info = [{'speaker': {'index': i % 126}} for i in range(bsz)]
+    gen = torch.Generator(device='cuda').manual_seed(5)
+    y, logp = model.test(utt.cuda(), info, return_logp=True, generator=gen)
+    y = y.cpu()
+    rf = t * fs
+    ref = O.forward_indices(params, spec, y[:, :rf + fs - 1], y[:, fs:fs + rf], utt, torch.arange(bsz) % 126, [1] * bsz,
+                            fast=True)[0]
+    d = float((logp.cpu() - ref).abs().max())
+    report(f'generation H=1024, 130 utterances x {rf} samples vs teacher forcing: max|dlogp| {d:.3e}')
+    assert d <= 0.06, d
+    y2 = model.test(utt.cuda(), info, generator=torch.Generator(device='cuda').manual_seed(5)).cpu()
+    assert torch.equal(y, y2)                                                   # same seed -> same audio
+    y3 = model.test(utt.cuda(), info, generator=torch.Generator(device='cuda').manual_seed(6)).cpu()
+    assert not torch.equal(y, y3)
