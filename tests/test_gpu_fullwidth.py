@@ -199,7 +199,10 @@ def test_full_width_config3_lstm_pase_and_fused_loss_vs_cpu_oracle():
         assert rel <= 1e-3 and not bad, (k, rel, bad)
         for n in range(2):
             assert float((model._state[n].cpu() - state.h[n]).abs().max()) <= 3e-2
-            assert float((model._state_c[n].cpu() - state.c[n]).abs().max()) <= 6e-2
+            # the cell state is an unbounded accumulator (|c| reaches several units): bound the error relative to it
+            dc = model._state_c[n].cpu() - state.c[n]
+            assert rel_l2(model._state_c[n].cpu(), state.c[n]) <= 1e-2, (k, n, rel_l2(model._state_c[n].cpu(), state.c[n]))
+            assert float(dc.abs().max()) <= 3e-2 * max(1.0, float(state.c[n].abs().max())), (k, n, float(dc.abs().max()))
 
 
 def test_full_width_generation_consistent_with_teacher_forcing():
