@@ -39,6 +39,10 @@ int srnn_abi_version(void);
  * attributes, occupancy answers) is cached per CUDA device and may be used from several host threads. */
 int srnn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* how many clusters of `cluster_size` CTAs (dynamic shared memory and threads per CTA given) can be co-resident on the
+ * current device (decides which decompositions the generation kernels may use) */
+int srnn_probe_clusters(int32_t cluster_size, int32_t smem_bytes, int32_t threads, int32_t* max_clusters);
+
 /* ---------------------------------------------------------------------------------------------
  * Quantiser - replaces SampleRNNQuantizer (utils.py:25-73)
  * ------------------------------------------------------------------------------------------- */
@@ -292,6 +296,15 @@ int srnn_embed_sum(const void* table_bf16, const uint8_t* idx, int64_t idx_ld, i
 int srnn_sample_categorical(const float* in, int64_t ld, int32_t batch, int32_t q, int32_t normalise, float* logp_out,
                             int64_t ld_out, const float* u, uint64_t* rng_state, uint8_t* win, int32_t win_len,
                             uint8_t* out, int64_t out_ld, srnn_stream_t stream);
+
+/* srnn_sample_categorical followed, in the same launch, by srnn_embed_sum for the NEXT sample step: after the draw has
+ * been appended to the window, h1_next[b, :] = relu(sum_k table[k*q + win[b, win_len - r0 + k], :] + pre_next[b, :]).
+ * Usable whenever the frame-constant term of the next step is already known (every step that is not followed by a
+ * frame-tier step); saves one launch of the per-sample latency chain. */
+int srnn_sample_embed(const float* in, int64_t ld, int32_t batch, int32_t q, int32_t normalise, float* logp_out,
+                      int64_t ld_out, const float* u, uint64_t* rng_state, uint8_t* win, int32_t win_len, uint8_t* out,
+                      int64_t out_ld, const void* table_bf16, int32_t r0, int32_t hidden, const void* pre_next_bf16,
+                      int64_t pre_ld, void* h1_next_bf16, int64_t h1_ld, srnn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,7 @@ P, I32, I64, F64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 SIGNATURES = {
     'srnn_abi_version': [],
     'srnn_device_info': [P, P, P],
+    'srnn_probe_clusters': [I32, I32, I32, P],
     'srnn_quantize_ulaw': [P, I64, P, P, P, P],
     'srnn_quantize_linear': [P, I64, I64, I32, P, P, P],
     'srnn_dequantize_lut': [P, P, I64, P, P, P, P],
@@ -80,6 +81,7 @@ SIGNATURES = {
     'srnn_set_pdl': [I32],
     'srnn_embed_sum': [P, P, I64, I32, I32, I32, I32, P, I64, I32, P, I64, P],
     'srnn_sample_categorical': [P, I64, I32, I32, I32, P, I64, P, P, P, I32, P, I64, P],
+    'srnn_sample_embed': [P, I64, I32, I32, I32, P, I64, P, P, P, I32, P, I64, P, I32, I32, P, I64, P, I64, P],
     'srnn_gemm_bf16': [C.POINTER(GemmArgs), P],
     'srnn_gemm_nll': [C.POINTER(NllArgs), P],
     'srnn_gru_forward': [C.POINTER(GruArgs), P],

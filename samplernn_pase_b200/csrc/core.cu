@@ -126,3 +126,38 @@ extern "C" int srnn_device_info(int* sms, int* major, int* minor) {
   if (minor) SRNN_CUDA(cudaDeviceGetAttribute(minor, cudaDevAttrComputeCapabilityMinor, dev));
   return SRNN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Device probe: how many thread-block clusters of `cluster_size` CTAs (each with `smem_bytes` of dynamic shared memory
+// and `threads` threads) can be co-resident?  Used by scripts/cluster_probe.py to choose decompositions (clusters of 16
+// need the non-portable attribute and one whole GPC each).
+// ---------------------------------------------------------------------------------------------
+namespace srnn {
+__global__ void probe_kernel(int* out) {
+  extern __shared__ uint8_t probe_smem[];
+  if (out && threadIdx.x == 0 && blockIdx.x == 0) out[0] = static_cast<int>(probe_smem[0]);
+}
+}  // namespace srnn
+
+extern "C" int srnn_probe_clusters(int32_t cluster_size, int32_t smem_bytes, int32_t threads, int32_t* max_clusters) {
+  SRNN_CHECK_ARG(cluster_size >= 1 && cluster_size <= 16 && smem_bytes >= 0 && threads > 0 && max_clusters,
+                 "probe_clusters: bad arguments");
+  auto kern = srnn::probe_kernel;
+  SRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  if (cluster_size > 8) SRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cluster_size * 64);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_size;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  SRNN_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+  *max_clusters = n;
+  return SRNN_OK;
+}

@@ -74,7 +74,9 @@ __device__ __forceinline__ uint32_t philox_uniform_bits(unsigned long long seed,
 __global__ void sample_kernel(const float* __restrict__ in, long long ld, int batch, int q, int normalise,
                               float* __restrict__ logp_out, long long ld_out, const float* __restrict__ u,
                               unsigned long long* __restrict__ rng, uint8_t* __restrict__ win, int win_len,
-                              uint8_t* __restrict__ out, long long out_ld) {
+                              uint8_t* __restrict__ out, long long out_ld, const __nv_bfloat16* __restrict__ table,
+                              int r0, int hidden, const __nv_bfloat16* __restrict__ pre_next, long long pre_ld,
+                              __nv_bfloat16* __restrict__ h1_next, long long h1_ld) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -193,6 +195,32 @@ __global__ void sample_kernel(const float* __restrict__ in, long long ld, int ba
     }
   }
   if (out && lane == 0) out[b * out_ld] = static_cast<uint8_t>(pick);
+  // Fused head of the NEXT sample step (when its frame-constant term is already known): the embedding side of
+  // comb_layer for the window that now ends with the code just drawn - srnn_embed_sum without a launch of its own.
+  if (h1_next) {
+    __syncwarp();
+    const uint8_t* w = win + static_cast<long long>(b) * win_len + (win_len - r0);
+    for (int c8 = lane; c8 * 8 < hidden; c8 += 32) {
+      float acc[8];
+      {
+        const uint4 u4 = __ldg(reinterpret_cast<const uint4*>(pre_next + b * pre_ld) + c8);
+        acc[0] = bf16_lo(u4.x); acc[1] = bf16_hi(u4.x); acc[2] = bf16_lo(u4.y); acc[3] = bf16_hi(u4.y);
+        acc[4] = bf16_lo(u4.z); acc[5] = bf16_hi(u4.z); acc[6] = bf16_lo(u4.w); acc[7] = bf16_hi(u4.w);
+      }
+      for (int k = 0; k < r0; ++k) {
+        const int code = (k == r0 - 1) ? pick : static_cast<int>(w[k]);
+        const uint4 u4 = __ldg(reinterpret_cast<const uint4*>(table + (static_cast<long long>(k) * q + code) * hidden) + c8);
+        acc[0] += bf16_lo(u4.x); acc[1] += bf16_hi(u4.x); acc[2] += bf16_lo(u4.y); acc[3] += bf16_hi(u4.y);
+        acc[4] += bf16_lo(u4.z); acc[5] += bf16_hi(u4.z); acc[6] += bf16_lo(u4.w); acc[7] += bf16_hi(u4.w);
+      }
+      uint4 o;
+      o.x = pack_bf16x2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
+      o.y = pack_bf16x2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+      o.z = pack_bf16x2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
+      o.w = pack_bf16x2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+      reinterpret_cast<uint4*>(h1_next + b * h1_ld)[c8] = o;
+    }
+  }
 }
 
 // <<<>>> with the programmatic-stream-serialization attribute when srnn_set_pdl(1) is in effect
@@ -231,15 +259,37 @@ extern "C" int srnn_embed_sum(const void* table, const uint8_t* idx, int64_t idx
   return SRNN_OK;
 }
 
-extern "C" int srnn_sample_categorical(const float* in, int64_t ld, int32_t batch, int32_t q, int32_t normalise,
-                                       float* logp_out, int64_t ld_out, const float* u, uint64_t* rng_state, uint8_t* win,
-                                       int32_t win_len, uint8_t* out, int64_t out_ld, srnn_stream_t s) {
+static int sample_launch(const float* in, int64_t ld, int32_t batch, int32_t q, int32_t normalise, float* logp_out,
+                         int64_t ld_out, const float* u, uint64_t* rng_state, uint8_t* win, int32_t win_len, uint8_t* out,
+                         int64_t out_ld, const void* table, int32_t r0, int32_t hidden, const void* pre_next, int64_t pre_ld,
+                         void* h1_next, int64_t h1_ld, srnn_stream_t s) {
   SRNN_CHECK_ARG(in && batch > 0 && q > 0 && q <= 32 * SAMPLE_PER && (win || out || logp_out),
                  "sample_categorical: bad arguments");
   SRNN_CHECK_ARG(!win || win_len > 0, "sample_categorical: win_len must be positive");
   const int warps = 4;
   SRNN_CUDA(launch_pdl(sample_kernel, dim3((batch + warps - 1) / warps), dim3(warps * 32), static_cast<cudaStream_t>(s),
                        in, static_cast<long long>(ld), batch, q, normalise, logp_out, static_cast<long long>(ld_out), u,
-                       reinterpret_cast<unsigned long long*>(rng_state), win, win_len, out, static_cast<long long>(out_ld)));
+                       reinterpret_cast<unsigned long long*>(rng_state), win, win_len, out, static_cast<long long>(out_ld),
+                       static_cast<const __nv_bfloat16*>(table), r0, hidden, static_cast<const __nv_bfloat16*>(pre_next),
+                       static_cast<long long>(pre_ld), static_cast<__nv_bfloat16*>(h1_next), static_cast<long long>(h1_ld)));
   return SRNN_OK;
+}
+
+extern "C" int srnn_sample_categorical(const float* in, int64_t ld, int32_t batch, int32_t q, int32_t normalise,
+                                       float* logp_out, int64_t ld_out, const float* u, uint64_t* rng_state, uint8_t* win,
+                                       int32_t win_len, uint8_t* out, int64_t out_ld, srnn_stream_t s) {
+  return sample_launch(in, ld, batch, q, normalise, logp_out, ld_out, u, rng_state, win, win_len, out, out_ld, nullptr, 0, 0,
+                       nullptr, 0, nullptr, 0, s);
+}
+
+extern "C" int srnn_sample_embed(const float* in, int64_t ld, int32_t batch, int32_t q, int32_t normalise, float* logp_out,
+                                 int64_t ld_out, const float* u, uint64_t* rng_state, uint8_t* win, int32_t win_len,
+                                 uint8_t* out, int64_t out_ld, const void* table, int32_t r0, int32_t hidden,
+                                 const void* pre_next, int64_t pre_ld, void* h1_next, int64_t h1_ld, srnn_stream_t s) {
+  SRNN_CHECK_ARG(table && pre_next && h1_next && win && r0 > 0 && r0 <= win_len && hidden > 0 && hidden % 8 == 0 &&
+                 pre_ld % 8 == 0 && h1_ld % 8 == 0, "sample_embed: bad arguments");
+  SRNN_CHECK_ARG(((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(pre_next) |
+                   reinterpret_cast<uintptr_t>(h1_next)) & 15) == 0, "sample_embed: pointers must be 16-byte aligned");
+  return sample_launch(in, ld, batch, q, normalise, logp_out, ld_out, u, rng_state, win, win_len, out, out_ld, table, r0, hidden,
+                       pre_next, pre_ld, h1_next, h1_ld, s);
 }

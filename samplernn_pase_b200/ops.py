@@ -136,6 +136,16 @@ def sample_categorical(x, batch, q, u, win, win_len, out, out_ld, normalise=Fals
     _count()
 
 
+def sample_embed(x, batch, q, win, win_len, out, out_ld, table, r0, hidden, pre_next, pre_ld, h1_next, h1_ld,
+                 normalise=False, logp_out=None, rng_state=None, u=None):
+    """``sample_categorical`` + the embedding head of the NEXT sample step in one launch (see srnn_sample_embed)."""
+    _need(x, F32, 'sample input')
+    call('srnn_sample_embed', ptr(x), x.stride(0), batch, q, int(normalise), ptr(logp_out),
+         logp_out.stride(0) if logp_out is not None else 0, ptr(u), ptr(rng_state), ptr(win), win_len, ptr(out), out_ld,
+         ptr(table), r0, hidden, ptr(pre_next), pre_ld, ptr(h1_next), h1_ld, stream())
+    _count()
+
+
 # ----------------------------------------------------------------------------------------------
 # parameter preparation
 # ----------------------------------------------------------------------------------------------
