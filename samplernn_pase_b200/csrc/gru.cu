@@ -4,28 +4,30 @@
 // One cooperative launch runs all T timesteps of a tier; the recurrent weights never leave shared
 // memory.  Work decomposition (H hidden units, batch rows M <= 64, K = H forward / 3H backward):
 //
-//   * the grid is H/U CTAs (U = 8 units per CTA, optionally 16) in thread-block clusters of C CTAs;
+//   * the grid is H/U CTAs (U = 8 units per CTA, optionally 16) in thread-block clusters of C CTAs
+//     (forward at H = 1024: C = 1, every CTA holds its 24 gate rows of W_hh for the whole K; backward: C = 4);
 //   * a cluster owns U*C hidden units: forward its 3*U*C gate rows of W_hh, backward its U*C rows of
 //     W_hh^T.  Inside the cluster the reduction dimension is SPLIT: CTA rank c keeps only the K/C
 //     slice [c*K/C, (c+1)*K/C) of those rows resident (48 KB at H=1024, 128-byte-swizzled K-major);
 //   * per timestep each CTA
 //       1. polls a grid-wide arrival counter in L2 (relaxed loads) until every CTA has published its
-//          part of h_{t-1} (backward: of the gate gradients of step t+1), then a generic->async proxy
-//          fence,
-//       2. TMA-loads only its K slice of that [batch, K] matrix (one mbarrier, K/(64 C) boxes),
-//       3. multiplies it with tcgen05.mma (M=64, N=U*C*{3,1}), issued by two threads into two partial
+//          part of h_{t-1} (backward: of the gate gradients of step t+1), then a generic->async proxy fence,
+//       2. TMA-loads only its K slice of that [batch, K] matrix (ONE 4-D box, one mbarrier),
+//       3. multiplies it with tcgen05.mma (M=64, N=U*C*{3,1}), issued by four threads into four partial
 //          accumulators in TMEM,
-//       4. reads the partial tile from TMEM and PUSHES, for every peer rank, the columns of that rank's
+//       4. (C > 1) reads the partial tile from TMEM and PUSHES, for every peer rank, the columns of that rank's
 //          units into the peer's shared memory with st.async; the bytes complete on the peer's mbarrier,
-//       5. sums the C partial tiles that landed in its own shared memory, finishes the gate math in fp32
-//          registers (MUFU tanh), stores its U columns of h_t (bf16, time-major exchange buffer) and
-//          arrives on the counter (release); the batch-major copy of h_t and the saved gates are written
+//       5. sums the partials, VALIDATES the operand it read (a bf16 NaN sentinel in any element that had not
+//          arrived yet makes the row's accumulators NaN: the attempt is then repeated), finishes the gate math in
+//          fp32 registers (MUFU tanh), stores its U columns of h_t (bf16, time-major exchange buffer) and arrives
+//          on the counter with a RELAXED increment; the batch-major copy of h_t and the saved gates are written
 //          after the arrival, off the critical path.
 //
-// How it got here (B=64, H=1024, us per step fwd/bwd; profiles/r01_gru_*): one CTA per 8 units doing the
+// How it got here (B=64, H=1024, us per step fwd/bwd; profiles/r01_gru_*, r02_gru_*): one CTA per 8 units doing the
 // whole K loop 9.5/18.0 (tensor pipe 5 % busy, L2 5 % busy: single-thread issue + handshake latency) ->
-// cluster split-K with smem staging + DSMEM loads 6.8/7.5 -> st.async push exchange 5.4/6.0 -> two MMA
-// issuers + running descriptors 5.0/5.35 -> no gpu-scope acquire fence on the consumer 4.5/4.8.
+// cluster split-K with smem staging + DSMEM loads 6.8/7.5 -> st.async push exchange 5.4/6.0 -> MMA issuers with
+// separate partial accumulators + running descriptors 5.0/5.35 -> forward without clusters 3.97/4.6 -> release /
+// acquire fences replaced by the validated read (same box: 4.77/5.57 strict -> 3.54/4.26).
 //
 // The fp32 recurrent state of a unit never leaves the registers of its owner thread.
 #include <mutex>

@@ -15,8 +15,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=256)
 ap.add_argument('--frames', type=int, default=16)
 ap.add_argument('--eager', action='store_true')
+ap.add_argument('--no-pdl', action='store_true')   # exclusive kernel durations (with PDL a kernel's time includes waiting for its predecessor)
 a = ap.parse_args()
 torch.manual_seed(0)
+if a.no_pdl:
+    from samplernn_pase_b200 import generate as _g
+    _g._PDL = False
 model = SampleRNNModel(**bench.model_kwargs(a.frames)).cuda()
 utt = torch.randn(a.batch, a.frames, 43).cuda()
 info = [{'speaker': {'index': i % 126}} for i in range(a.batch)]
