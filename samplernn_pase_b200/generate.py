@@ -204,18 +204,24 @@ class _GenState:
         self.h1 = _e(b, sw.h, device=dev)                                  # embedding-side activation of the next step
         # chains of bf16 hidden states per tier and layer: a tier runs FS / fs_n steps per top-tier frame
         self.hx = [[_e(fs_top // w.fs + 1, b, w.h, device=dev) for _ in range(w.layers)] for w in tiers]
-        self.frame_out = torch.empty(b, fs_top, dtype=torch.uint8, device=dev)
-        self.logp_frame = torch.empty(b, fs_top, sw.q, dtype=F32, device=dev) if return_logp else None
+        # staging for GRAPH_FRAMES top-tier frames: one CUDA graph covers that many frames, the host refills / drains
+        # the stages once per replay (a replay per frame left the host as busy as the GPU: ~0.5 ms of enqueue work per
+        # 0.54 ms frame, so every host hiccup showed up in the throughput)
+        self.conds_stage = torch.empty(b, GRAPH_FRAMES, c, dtype=F32, device=dev)
+        self.out_stage = torch.empty(b, GRAPH_FRAMES * fs_top, dtype=torch.uint8, device=dev)
+        self.logp_stage = torch.empty(b, GRAPH_FRAMES * fs_top, sw.q, dtype=F32, device=dev) if return_logp else None
         self.logits = torch.empty(b, sw.q, dtype=F32, device=dev)
         self.rng_state = torch.zeros(3, dtype=torch.int64, device=dev)      # {seed, step, 0} of the device-side draws
 
 
-def _frame_phase(p, tiers, sw, lut, st, states, cstates):
+def _frame_phase(p, tiers, sw, lut, st, states, cstates, slot):
     """One sample step at phase ``p = xi % FS`` of a top-tier frame, written against the static buffers of ``st`` so
     that it can be captured in a CUDA graph: ``st.win`` (B,FS) holds the last FS generated samples, ``st.outs`` the
-    tiers' current composed outputs, ``st.frame_out[:, p]`` receives the new sample."""
+    tiers' current composed outputs, ``st.out_stage[:, slot*FS + p]`` receives the new sample."""
     win = st.win
     b, fs_top = win.shape
+    col = slot * fs_top + p
+    out_ld = st.out_stage.shape[1]
     r0, h = sw.r0, sw.h
     fired = False
     for n in reversed(range(len(tiers))):                                    # model.py:312-337
@@ -238,14 +244,14 @@ def _frame_phase(p, tiers, sw, lut, st, states, cstates):
     sample_step(sw, st.h1, st.logits)
     # model.py:203,346-348: log-softmax, draw from it, append to the window of the last FS samples; unless a tier step
     # comes first, the same launch also gathers the embedding side of the NEXT step
-    logp_out = st.logp_frame[:, p] if st.logp_frame is not None else None
+    logp_out = st.logp_stage[:, col] if st.logp_stage is not None else None
     rng = None if _GREEDY else st.rng_state
     nxt = p + 1
     if nxt < fs_top and nxt % tiers[0].fs != 0:
-        ops.sample_embed(st.logits, b, sw.q, win, fs_top, st.frame_out[:, p], fs_top, sw.table_t, r0, h,
+        ops.sample_embed(st.logits, b, sw.q, win, fs_top, st.out_stage[:, col], out_ld, sw.table_t, r0, h,
                          st.outs[0][:, (nxt % r0) * h:], r0 * h, st.h1, h, normalise=True, logp_out=logp_out, rng_state=rng)
     else:
-        ops.sample_categorical(st.logits, b, sw.q, None, win, fs_top, st.frame_out[:, p], fs_top, normalise=True,
+        ops.sample_categorical(st.logits, b, sw.q, None, win, fs_top, st.out_stage[:, col], out_ld, normalise=True,
                                logp_out=logp_out, rng_state=rng)
 
 
@@ -305,35 +311,62 @@ def generate(model, utt_conds, info, return_logp=False, generator=None, use_grap
 _PDL = True
 
 
+#: top-tier frames per CUDA graph
+GRAPH_FRAMES = 8
+
+
+def _run_frame(slot, first, tiers, sw, lut, st, states, cstates):
+    """All FS sample steps of one top-tier frame against stage slot ``slot`` (graph-capturable)."""
+    b, c = st.conds_cur.shape[0], st.conds_cur.shape[2]
+    fs_top = st.win.shape[1]
+    st.conds_cur.copy_(st.conds_stage[:, slot: slot + 1])                    # model.py:308-309: conds index xi//FS - 1
+    ops.pad_cast_bf16(st.conds_cur.view(b, c), b, c, c, st.conds_b, sw.cp, sw.cp)
+    frame_terms(sw, st.conds_b, st.c_term, st.cc, st.cc_rep)
+    if not first:                                                            # the chains wrap: slot 0 <- last slot
+        for chain in st.hx:
+            for hx in chain:
+                hx[0].copy_(hx[-1])
+    for p in range(fs_top):
+        _frame_phase(p, tiers, sw, lut, st, states, cstates, slot)
+
+
 def _generate_frames(model, st, states, cstates, tiers, sw, lut, conds, y, t, b, c, fs_top, graphed, generator, return_logp):
     logps = [] if return_logp else None
-    graphs = None
-    for f in range(t):                                                       # top-tier frames; xi = (f+1)*FS + p
-        st.conds_cur.copy_(conds[:, f: f + 1])                               # model.py:308-309: conds index xi//FS - 1
-        ops.pad_cast_bf16(st.conds_cur.view(b, c), b, c, c, st.conds_b, sw.cp, sw.cp)
-        frame_terms(sw, st.conds_b, st.c_term, st.cc, st.cc_rep)
-        if f > 0:                                                            # the chains wrap: slot 0 <- last slot
-            for chain in st.hx:
-                for hx in chain:
-                    hx[0].copy_(hx[-1])
-        if graphed and f == 1:                                               # frame 0 ran eagerly (lazy init done)
-            torch.cuda.synchronize()
-            graphs = torch.cuda.CUDAGraph()                                  # ONE graph = the FS step programs of a frame
-            before = ops.launch_count
-            with torch.cuda.graph(graphs):
-                for p in range(fs_top):
-                    _frame_phase(p, tiers, sw, lut, st, states, cstates)
-            per_frame = ops.launch_count - before                            # kernels inside the captured graph
-            ops.launch_count = before
-        if graphs is not None:
-            graphs.replay()
-            ops.launch_count += per_frame
-        else:
-            for p in range(fs_top):
-                _frame_phase(p, tiers, sw, lut, st, states, cstates)
-        y[:, (f + 1) * fs_top: (f + 2) * fs_top] = st.frame_out
+
+    def drain(f0, n):
+        y[:, (f0 + 1) * fs_top: (f0 + 1 + n) * fs_top] = st.out_stage[:, :n * fs_top]
         if return_logp:
-            logps.append(st.logp_frame.clone())
+            logps.append(st.logp_stage[:, :n * fs_top].clone())
+
+    def eager(f0, n):
+        st.conds_stage[:, :n].copy_(conds[:, f0: f0 + n])
+        for i in range(n):
+            _run_frame(i, f0 + i == 0, tiers, sw, lut, st, states, cstates)
+        drain(f0, n)
+
+    eager(0, 1)                                                              # frame 0 runs eagerly (lazy initialisation)
+    f = 1
+    graph, per_graph = None, 0
+    while f < t:
+        n = min(GRAPH_FRAMES, t - f)
+        if not graphed or n < GRAPH_FRAMES:
+            eager(f, n)                                                      # tail shorter than one graph
+            f += n
+            continue
+        st.conds_stage.copy_(conds[:, f: f + n])
+        if graph is None:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()                                   # ONE graph = GRAPH_FRAMES x FS step programs
+            before = ops.launch_count
+            with torch.cuda.graph(graph):
+                for i in range(n):
+                    _run_frame(i, False, tiers, sw, lut, st, states, cstates)
+            per_graph = ops.launch_count - before                            # kernels inside the captured graph
+            ops.launch_count = before
+        graph.replay()
+        ops.launch_count += per_graph
+        drain(f, n)
+        f += n
     out = y.to(torch.int64)
     if return_logp:
         return out, torch.cat(logps, dim=1)

@@ -218,6 +218,8 @@ def test_full_width_generation_consistent_with_teacher_forcing():
     model = SampleRNNModel('embedding', 126, 15, 'acoustic', [9, 5, 4, 3], 10, 50, 3, [4, 4], [1, 1], [1024, 1024], True,
                            256).cuda()
     model.load_state_dict(params)
+    from samplernn_pase_b200 import generate as G
+    G.GRAPH_FRAMES = 2                                                          # frame 0 eager, frames 1-2 one captured graph
     bsz, t, fs = 130, 3, 16
     utt = torch.randn(bsz, t, 43, generator=torch.Generator().manual_seed(3))
     info = [{'speaker': {'index': i % 126}} for i in range(bsz)]
@@ -234,3 +236,4 @@ def test_full_width_generation_consistent_with_teacher_forcing():
     assert torch.equal(y, y2)                                                   # same seed -> same audio
     y3 = model.test(utt.cuda(), info, generator=torch.Generator(device='cuda').manual_seed(6)).cpu()
     assert not torch.equal(y, y3)
+    G.GRAPH_FRAMES = 8

@@ -274,8 +274,12 @@ def test_generation_is_consistent_with_teacher_forcing():
     single = model.test(utt[:1].cuda(), info[0])                               # the reference's calling convention
     assert single.shape == (1, (t + 1) * fs)
     assert all(torch.equal(v.cpu(), params[k]) for k, v in model.state_dict().items())   # generation is read-only
-    # CUDA-graph path (default generator, frames >= 3): same consistency check on a longer utterance
-    t2 = 5
+    # CUDA-graph path (default generator): same consistency check on a longer utterance; 2 frames per graph here so that
+    # frame 0 runs eagerly, frames 1-2 are captured + replayed, frames 3-4 replayed and frame 5 runs as the eager tail
+    from samplernn_pase_b200 import generate as G
+    monkey_frames = G.GRAPH_FRAMES
+    G.GRAPH_FRAMES = 2
+    t2 = 6
     utt2 = torch.randn(bsz, t2, 43, generator=torch.Generator().manual_seed(4))
     torch.cuda.manual_seed(11)
     y2, logp2 = model.test(utt2.cuda(), info, return_logp=True)
@@ -287,6 +291,7 @@ def test_generation_is_consistent_with_teacher_forcing():
     report(f'generation (CUDA-graph path) vs teacher forcing ({rf2} samples): max|dlogp| {d2:.3e}')
     assert d2 <= 0.05, d2
     assert len(set(y2[0, fs:].tolist())) > 3                                   # it really samples
+    G.GRAPH_FRAMES = monkey_frames
     # more utterances than one recurrent launch or one GEMM M tile holds (3 slot groups: 64 + 64 + 2 rows)
     bsz3, t3 = 130, 3
     utt3 = torch.randn(bsz3, t3, 43, generator=torch.Generator().manual_seed(6))
