@@ -29,7 +29,7 @@ extern "C" {
 #define SRNN_ERR_ARG (-1)     /* bad argument (shape, alignment, null pointer) */
 #define SRNN_ERR_DEVICE (-2)  /* not an sm_100 device / driver entry point missing */
 
-#define SRNN_ABI_VERSION 4
+#define SRNN_ABI_VERSION 5
 
 typedef void* srnn_stream_t; /* cudaStream_t */
 
@@ -153,6 +153,11 @@ typedef struct srnn_gemm_args {
   /* NT only, optional second A operand: A_i = [ A_i[m, k1] | A2_i[m, k - k1] ] concatenated along K without being
    * materialised (comb_layer's input [one-hot windows | upper conditioning], model.py:196-199).  k1 % 64 == 0. */
   const void* a2; int64_t lda2; int64_t a2_batch_stride; int32_t k1;
+  /* NT only, ReLU as a bit mask: with relu != 0 and relu_mask non-null the epilogue also writes bit (row, col) = result > 0
+   * (one uint32 per row and 32 columns, row = batch * m + row in batch, ldmask words per row); a later GEMM given the same
+   * words as gate_mask multiplies its result by that bit - the ReLU gradient (model.py:195,201 backward) from 4 bytes
+   * per row and 32 columns instead of re-reading the 64 bytes of the saved activation (aux_mode 2). */
+  uint32_t* relu_mask; const uint32_t* gate_mask; int64_t ldmask;
 } srnn_gemm_args;
 
 int srnn_gemm_bf16(const srnn_gemm_args* args, srnn_stream_t stream);

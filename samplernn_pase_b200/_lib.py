@@ -26,6 +26,7 @@ class GemmArgs(C.Structure):
         ('aux_mode', C.c_int32), ('relu', C.c_int32), ('aux_row_div', C.c_int32), ('max_ctas', C.c_int32),
         ('colsum', C.c_void_p),
         ('a2', C.c_void_p), ('lda2', C.c_int64), ('a2_batch_stride', C.c_int64), ('k1', C.c_int32),
+        ('relu_mask', C.c_void_p), ('gate_mask', C.c_void_p), ('ldmask', C.c_int64),
     ]
 
 
@@ -112,7 +113,7 @@ def load(path=None):
         fn.restype = C.c_int
     lib.srnn_last_error.argtypes = []
     lib.srnn_last_error.restype = C.c_char_p
-    if lib.srnn_abi_version() != 4:
+    if lib.srnn_abi_version() != 5:
         raise RuntimeError('libsrnn_b200.so ABI version mismatch')
     _lib = lib
     return lib

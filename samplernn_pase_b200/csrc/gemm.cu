@@ -43,6 +43,9 @@ struct GemmParams {
   int kb_a1;                       // NT: K blocks taken from the first A operand (the rest from tma_a2); total if single
   int tn_4d;                       // TN: operands described as [batch][MN/64][k][64] - one TMA box per operand and K block
   float* colsum;                   // NT: column sums of the fp32 epilogue result, accumulated with atomics (nullable)
+  uint32_t* relu_mask;             // NT + relu (nullable): bit (row, col) = result > 0, one word per row and 32 columns
+  const uint32_t* gate_mask;       // NT (nullable): C = acc where the bit is set, else 0 (ReLU gradient gate)
+  long long ldmask;                // words per row of either mask
   // schedule
   int tiles_m, tiles_n, kb_per_batch, splits, kb_per_split, total_kb, total_work;
   // NLL epilogue
@@ -277,6 +280,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       uint4 ax[4];
       bool ax_ok = false;
       const __nv_bfloat16* aux_row = nullptr;
+      // ReLU-gradient gate as a bit mask written by the forward GEMM: 4 bytes per row and chunk instead of the 64 bytes of
+      // the saved activation (32 different rows per warp instruction either way, but 16x fewer bytes and sectors)
+      uint32_t gmask[CHUNKS_PER_WARP];
+      const long long mrow = static_cast<long long>(wk.b) * p.m + j;
+      if constexpr (STORE) {
+#pragma unroll
+        for (int c = 0; c < CHUNKS_PER_WARP; ++c) {
+          const int n0c = wk.nt * BN + (c_begin + c) * 32;
+          gmask[c] = (p.gate_mask && row_ok && n0c < p.n) ? __ldg(p.gate_mask + mrow * p.ldmask + (n0c >> 5)) : 0xFFFFFFFFu;
+        }
+      }
       auto aux_prefetch = [&](int c) {
         const int n0c = wk.nt * BN + c * 32;
         ax_ok = false;
@@ -354,9 +368,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               for (int i = 0; i < 32; ++i) f[i] = a[i] > 0.f ? f[i] : 0.f;
             }
           }
+          if (p.gate_mask) {
+            const uint32_t mk = gmask[ci];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = ((mk >> i) & 1u) ? f[i] : 0.f;
+          }
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+            if (p.relu_mask && row_ok) {
+              uint32_t mk = 0u;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mk |= (f[i] > 0.f ? 1u : 0u) << i;
+              p.relu_mask[mrow * p.ldmask + (n0 >> 5)] = mk;
+            }
           }
           if constexpr (CSUM) {
             // transposing reduction over the warp's 32 rows: at every step a lane keeps the half of its values whose
@@ -376,6 +401,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               }
             }
             csum[ci] += r[0];
+          }
+          if (p.c_tma == 2) {
+            // Wide variant: the warp's chunks leave in PAIRS as one 32-row x 128-byte tile (128-byte swizzle, lane = row)
+            // and ONE TMA store per 64 columns - half the store requests of the 64-byte rows below, which bound every
+            // GEMM whose K is small against its output (m x 1024 x 256: 345 TFLOP/s = store-engine-bound).  The tile is
+            // single-buffered (the staging area is as large as shared memory allows): the previous store of this warp
+            // must have READ the tile before the first half of the next pair overwrites it; that wait sits behind this
+            // chunk's TMEM read and arithmetic.
+            uint8_t* sb = smem + Cfg::STG_OFF + (warp - 4) * 4096;
+            const int half = ci & 1;
+            if (half == 0) {
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              u.x = pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1]);
+              u.y = pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3]);
+              u.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]);
+              u.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
+              *reinterpret_cast<uint4*>(sb + lane * 128 + (((half * 4 + i) ^ (lane & 7)) << 4)) = u;
+            }
+            // the pair is complete after its second half, or after the first if the second lies beyond N (clipped)
+            if (half == 1 || n0 + 32 >= p.n) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                const int nf = p.n_fold > 0 ? p.n_fold : p.n;
+                const int np = n0 - half * 32;         // first column of the pair
+                tma_store_4d(&tma_c, sb, np % nf, np / nf, wk.mt * BM + q * 32, wk.b);
+                tma_store_commit();
+              }
+            }
+            continue;
           }
           if (p.c_tma) {
             // bf16 tile chunk -> 64-byte-swizzled staging tile (lane = row) -> one TMA store.  Per-lane global stores
@@ -899,10 +959,19 @@ static int run_nt(const srnn_gemm_args* a, GemmParams& p, bool nll, cudaStream_t
     const uint64_t bs = a->batch > 1 ? (uint64_t)a->c_batch_stride * 2 : row_bytes * fold_rows * (uint64_t)a->m;
     const uint64_t dims[4] = {nf, fold_rows, (uint64_t)a->m, (uint64_t)a->batch};
     const uint64_t strides[3] = {row_bytes, row_bytes * fold_rows, bs};
-    const uint32_t box[4] = {32, 1, 32, 1};
-    int rc = make_tmap_bf16_sw64(&tc, a->c, 4, dims, strides, box);
+    // 64-column (128-byte) store tiles unless a fold boundary could fall inside one
+    static const bool narrow_only = getenv("SRNN_GEMM_STORE64") != nullptr;      // A/B switch for measurements
+    const bool wide = !narrow_only && (a->n_fold == 0 || a->n_fold % 64 == 0);
+    int rc;
+    if (wide) {
+      const uint32_t box[4] = {64, 1, 32, 1};
+      rc = make_tmap_bf16(&tc, a->c, 4, dims, strides, box, true);
+    } else {
+      const uint32_t box[4] = {32, 1, 32, 1};
+      rc = make_tmap_bf16_sw64(&tc, a->c, 4, dims, strides, box);
+    }
     if (rc) return rc;
-    p.c_tma = 1;
+    p.c_tma = wide ? 2 : 1;
   }
   if (p.colsum) {
     if (bn == 256) return launch<256, false, 3>(ta, tb, tc, ta2, p, stream);
@@ -1081,10 +1150,17 @@ extern "C" int srnn_gemm_bf16(const srnn_gemm_args* a, srnn_stream_t stream_) {
   p.aux_row_div = a->aux_row_div > 0 ? a->aux_row_div : 1;
   p.max_ctas = a->max_ctas;
   p.colsum = a->op == 0 ? a->colsum : nullptr;
+  p.relu_mask = a->op == 0 ? a->relu_mask : nullptr;
+  p.gate_mask = a->op == 0 ? a->gate_mask : nullptr;
+  p.ldmask = a->ldmask;
+  SRNN_CHECK_ARG((!a->relu_mask && !a->gate_mask) || (a->op == 0 && a->ldmask * 32 >= a->n && a->n_fold == 0),
+                 "gemm: relu_mask / gate_mask need op NT, no n_fold and ldmask >= ceil(n / 32)");
+  SRNN_CHECK_ARG(!a->relu_mask || a->relu, "gemm: relu_mask is an output of the ReLU epilogue");
   if (a->op == 0) {
     SRNN_CHECK_ARG(a->n_fold == 0 || (a->n % a->n_fold == 0 && a->n_fold % 32 == 0 && !a->aux),
                    "gemm NT: n_fold must divide n, be a multiple of 32, and exclude aux");
-    if (a->m <= 512 && a->batch == 1 && a->n_fold == 0 && p.aux_mode != 2 && a->max_ctas == 0 && !a->colsum && !a->a2)
+    if (a->m <= 512 && a->batch == 1 && a->n_fold == 0 && p.aux_mode != 2 && a->max_ctas == 0 && !a->colsum && !a->a2 &&
+        !a->relu_mask && !a->gate_mask)
       return run_nt_small(a, p, stream);
     return run_nt(a, p, false, stream);
   }

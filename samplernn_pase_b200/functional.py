@@ -327,16 +327,20 @@ class SampleLevelFn(torch.autograd.Function):
         ops.gemm_nt(c_frame, w_c, cterm, b * l, h, h, h, h, h, bias=cbias.contiguous())
 
         h1 = _empty(m, h, device=dev)
+        # ReLU bit masks of h1 / h2 for the backward gates (4 bytes per row and 32 columns; see srnn_gemm_args.relu_mask)
+        mk1 = torch.empty(m, (h + 31) // 32, dtype=torch.int32, device=dev)
+        mk2 = torch.empty(m, (h + 31) // 32, dtype=torch.int32, device=dev)
         with ops.timed('comb_layer_fwd'):
             # A = [overlapping one-hot windows (row stride Q, row length r0*Q) | upper], batched per slot
             ops.gemm_nt(onehot, w_cat, h1, rf, h, kc, q, kc, h, batch=b, a_bs=w * q, c_bs=rf * h, aux=cterm, ldaux=h,
-                        aux_bs=l * h, aux_mode=1, aux_row_div=fsz, relu=True, a2=upper_c, lda2=h, a2_bs=rf * h, k1=r0 * q)
+                        aux_bs=l * h, aux_mode=1, aux_row_div=fsz, relu=True, a2=upper_c, lda2=h, a2_bs=rf * h, k1=r0 * q,
+                        relu_mask=mk1)
         w2 = _empty(h, h, device=dev)
         w2_t = _empty(h, h, device=dev)
         inv_2 = _empty(h, dtype=F32, device=dev)
         ops.weight_prep(w2v, w2g, (h, h, 1), w2, (h, 1, 0), w2_t, (1, h, 0), inv_norm=inv_2)
         h2 = _empty(m, h, device=dev)
-        ops.gemm_nt(h1, w2, h2, m, h, h, h, h, h, bias=b2.contiguous(), relu=True)
+        ops.gemm_nt(h1, w2, h2, m, h, h, h, h, h, bias=b2.contiguous(), relu=True, relu_mask=mk2)
         w3 = _empty(q, h, device=dev)
         w3_t = _empty(h, q, device=dev)
         inv_3 = _empty(q, dtype=F32, device=dev)
@@ -357,13 +361,13 @@ class SampleLevelFn(torch.autograd.Function):
             out = logp.view(b, rf, q)
         ctx.dims = (b, w, l, c, h, q, r0, rf, m, fsz, cp, fused)
         ctx.save_for_backward(onehot, e_b, we_t, inv_e, conds_b, wcs_t, c_frame, upper_c, tt, wcomb_t, h1, w2, w2_t, inv_2,
-                              h2, w3, w3_t, inv_3, target_u8, b3c, eg, ev, w2g, w2v, w3g, w3v, lse)
+                              h2, w3, w3_t, inv_3, target_u8, b3c, eg, ev, w2g, w2v, w3g, w3v, lse, mk1, mk2)
         return out
 
     @staticmethod
     def backward(ctx, gout):
         (onehot, e_b, we_t, inv_e, conds_b, wcs_t, c_frame, upper_c, tt, wcomb_t, h1, w2, w2_t, inv_2, h2, w3, w3_t, inv_3,
-         target_u8, b3c, eg, ev, w2g, w2v, w3g, w3v, lse) = ctx.saved_tensors
+         target_u8, b3c, eg, ev, w2g, w2v, w3g, w3v, lse, mk1, mk2) = ctx.saved_tensors
         b, w, l, c, h, q, r0, rf, m, fsz, cp, fused = ctx.dims
         dev = gout.device
         gout = gout.contiguous().float()
@@ -379,14 +383,14 @@ class SampleLevelFn(torch.autograd.Function):
         d_w3v, d_w3g = ops.weight_prep_bwd(dw3, (h, 1, 0), w3v, w3g, inv_3, (q, h, 1))
         dh2 = _empty(m, h, device=dev)
         d_b2 = _zeros(h, dtype=F32, device=dev)                 # bias gradient = column sums, fused into the GEMM epilogue
-        ops.gemm_nt(dlog, w3_t, dh2, m, h, q, q, q, h, aux=h2, ldaux=h, aux_mode=2, colsum=d_b2)
+        ops.gemm_nt(dlog, w3_t, dh2, m, h, q, q, q, h, gate_mask=mk2, colsum=d_b2)
         # comb_layer_expand
         dw2 = _zeros(h, h, device=dev)
         ops.gemm_tn(dh2, h1, dw2, h, h, m, h, h, h)
         d_w2v, d_w2g = ops.weight_prep_bwd(dw2, (h, 1, 0), w2v, w2g, inv_2, (h, h, 1))
         dh1 = _empty(m, h, device=dev)
         d_cbias = _zeros(h, dtype=F32, device=dev)
-        ops.gemm_nt(dh2, w2_t, dh1, m, h, h, h, h, h, aux=h1, ldaux=h, aux_mode=2, colsum=d_cbias)
+        ops.gemm_nt(dh2, w2_t, dh1, m, h, h, h, h, h, gate_mask=mk1, colsum=d_cbias)
         # comb_layer: [e | upper] blocks at sample rate, conditioning block at frame rate
         d_cw = _zeros(h, 3 * h, device=dev)
         ops.gemm_tn(dh1, upper_c, d_cw[:, 2 * h:], h, h, m, h, h, 3 * h)                   # d W_u

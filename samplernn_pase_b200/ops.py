@@ -256,7 +256,8 @@ def repeat_rows_bwd(dout, rows, cols, ld_dout, rep, din, ld_din):
 # GEMMs
 # ----------------------------------------------------------------------------------------------
 def gemm_nt(a, b, c, m, n, k, lda, ldb, ldc, batch=1, a_bs=0, c_bs=0, bias=None, aux=None, ldaux=0, aux_bs=0,
-            aux_mode=0, relu=False, n_fold=0, aux_row_div=1, colsum=None, a2=None, lda2=0, a2_bs=0, k1=0):
+            aux_mode=0, relu=False, n_fold=0, aux_row_div=1, colsum=None, a2=None, lda2=0, a2_bs=0, k1=0, relu_mask=None,
+            gate_mask=None):
     """C_i[m,n] = epi(A_i[m,k] . B[n,k]^T); c.dtype selects bf16 / fp32 output."""
     _need(a, BF16, 'gemm A')
     _need(b, BF16, 'gemm B')
@@ -274,6 +275,11 @@ def gemm_nt(a, b, c, m, n, k, lda, ldb, ldc, batch=1, a_bs=0, c_bs=0, bias=None,
     g.aux_row_div = aux_row_div
     g.max_ctas = gemm_max_ctas
     g.colsum = colsum.data_ptr() if colsum is not None else None
+    for mk, field in ((relu_mask, 'relu_mask'), (gate_mask, 'gate_mask')):
+        if mk is not None:
+            _need(mk, torch.int32, 'gemm ' + field)
+            setattr(g, field, mk.data_ptr())
+            g.ldmask = mk.shape[-1]
     if a2 is not None:
         _need(a2, BF16, 'gemm A2')
         g.a2, g.lda2, g.a2_batch_stride, g.k1 = a2.data_ptr(), lda2, a2_bs, k1

@@ -710,3 +710,27 @@ def test_gru_single_step_many_rows_in_one_launch(ops):
             ref = run(64)
             got = run(512)
             assert all(torch.equal(a, b) for a, b in zip(got, ref)), (cell, bsz)
+
+
+@pytest.mark.parametrize('m,n,k,batch', [(1000, 256, 192, 1), (300, 1024, 64, 3), (129, 96, 72, 1)])
+def test_gemm_relu_mask_and_gate_mask(ops, m, n, k, batch):
+    """ReLU as a bit mask: the forward GEMM writes bit (row, col) = result > 0 next to the activation; a backward GEMM
+    gated by those words equals one gated by the saved activation (aux_mode 2) bit for bit."""
+    a = rnd(batch * m, k).to(BF16)
+    w = rnd(n, k, scale=0.2, seed=1).to(BF16)
+    bias = rnd(n, seed=2)
+    h = torch.empty(batch * m, n, dtype=BF16, device='cuda')
+    words = (n + 31) // 32
+    mask = torch.zeros(batch * m, words, dtype=torch.int32, device='cuda')
+    ops.gemm_nt(a, w, h, m, n, k, k, k, n, batch=batch, a_bs=m * k, c_bs=m * n, bias=bias, relu=True, relu_mask=mask)
+    bits = ((mask.view(batch * m, words, 1) >> torch.arange(32, device='cuda').view(1, 1, 32)) & 1).reshape(batch * m, -1)[:, :n]
+    assert torch.equal(bits.bool(), h > 0)
+    g = rnd(batch * m, k, seed=3).to(BF16)                                  # any other GEMM with an (m, n) result
+    d_act = torch.empty(batch * m, n, dtype=BF16, device='cuda')
+    d_msk = torch.empty(batch * m, n, dtype=BF16, device='cuda')
+    cs_a = torch.zeros(n, device='cuda'); cs_m = torch.zeros(n, device='cuda')
+    ops.gemm_nt(g, w, d_act, m, n, k, k, k, n, batch=batch, a_bs=m * k, c_bs=m * n, aux=h, ldaux=n, aux_bs=m * n, aux_mode=2,
+                colsum=cs_a)
+    ops.gemm_nt(g, w, d_msk, m, n, k, k, k, n, batch=batch, a_bs=m * k, c_bs=m * n, gate_mask=mask, colsum=cs_m)
+    assert torch.equal(d_act, d_msk)
+    assert rel_l2(cs_m, cs_a) < 1e-5
