@@ -1,5 +1,6 @@
 #!/bin/bash
-# final-build verification (driver-equivalent) + the profiles that quote it
+# What the driver runs at round end (whole GPU suite in one process, smoke, both bench arms) plus the secondary bench lines
+# and microbenchmarks the profiles quote:  gpurun -- bash scripts/gpu_verify.sh
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_report.txt gpurun_out/parity_fullwidth.txt
 ( time timeout 1500 python -m pytest tests/ -x -q -m gpu -p no:cacheprovider ) > gpurun_out/pytest_gpu_all.log 2>&1; echo "pytest -m gpu exit $?"; tail -4 gpurun_out/pytest_gpu_all.log
