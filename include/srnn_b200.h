@@ -192,9 +192,10 @@ int srnn_gemm_nll(const srnn_nll_args* args, srnn_stream_t stream);
  * One cooperative launch runs all `steps` timesteps; W_hh stays resident in shared memory.
  * ------------------------------------------------------------------------------------------- */
 typedef struct srnn_gru_args {
-  int32_t batch, steps, hidden;   /* batch <= 64 per launch (run larger batches as slot groups); a single forward
-                                     timestep (steps == 1, the per-sample step of generation) takes up to 512 rows in
-                                     one launch; hidden % 8 == 0 */
+  int32_t batch, steps, hidden;   /* batch <= 512 per launch: rows are processed in groups of 64 (one MMA tile) inside
+                                     every timestep with one grid handshake per timestep; with more than one group the
+                                     fp32 state of a row is kept in h_state / c_state (backward: dh0 / dc0) between
+                                     timesteps instead of in registers; hidden % 8 == 0 */
   int32_t ext_batch;     /* rows per time slot of the TIME-major buffers (>= batch; a launch may cover a
                             sub-range of a larger batch: pass pointers offset to its first row) */
   const void* gi;        /* bf16 [batch*steps, 3H] = W_ih u_t + b_ih, batch-major: row (b,t) = b*steps + t */

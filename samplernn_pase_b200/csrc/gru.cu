@@ -332,11 +332,12 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
   const int u0 = blockIdx.x * U;                     // first unit finalised by this CTA
   const int kb0 = static_cast<int>(crank) * KBC;     // first K block of this CTA's slice
   const uint32_t G = gridDim.x;
-  // Multi-group mode (forward, T == 1, batch > 64: the per-sample recurrent step of batched generation): the rounds walk
-  // over blocks of 64 batch rows instead of timesteps.  Nothing is exchanged between CTAs (every block reads slot 0,
-  // written before the launch), so there is no grid handshake; the weight slice is fetched once for all blocks.
-  const bool multi = !BWD && p.groups > 1;
-  const int rounds = BWD ? T + 1 : (multi ? p.groups : T);
+  // More than 64 batch rows per launch: the rows are walked in GROUPS of 64 inside every timestep (one MMA tile, one
+  // landing of the operand per group) with ONE grid handshake per timestep; the weight slice stays resident for all
+  // of them.  With several groups the fp32 recurrent state of a row lives in its global buffer between timesteps
+  // (h_state / c_state forward, dh0 / dc0 as the running carries backward) instead of in registers.
+  const int n_groups = p.groups;
+  const int steps_end = BWD ? T + 1 : T;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_w);
@@ -407,10 +408,11 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       // follow the landing barriers until thread 0 raises the exit flag.
       uint32_t phase = 0, attempt = 0;
       int s = BWD ? 1 : 0;                           // backward: the last timestep (round 0) has no recurrent input
-      bool fresh = true;                             // first attempt of round s
+      int grp = 0;                                   // group of 64 batch rows inside timestep s
+      bool fresh = true;                             // first attempt of (s, grp)
       for (;;) {
         if (mw == 0) {
-          if (fresh && s > 0 && !multi && !grid_wait_skipped(p.flags)) {
+          if (fresh && grp == 0 && s > 0 && !grid_wait_skipped(p.flags)) {
             if (pre_poll) spin_cycles(pre_poll);
             if (!(p.flags & (1 << 24)))
               grid_wait(p.sync, G * static_cast<uint32_t>(s), strict, poll_depth, poll_gap);
@@ -421,8 +423,8 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
             GRU_TS(0, s);
           }
           asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy writes -> TMA reads (free: measured)
-          const int slot = BWD ? (T - s) : (multi ? 0 : s);      // time slot of the exchange buffer
-          const int row0 = multi ? s * GRU_M : 0;                 // first batch row of this round
+          const int slot = BWD ? (T - s) : s;                     // time slot of the exchange buffer
+          const int row0 = grp * GRU_M;                           // first batch row of this group
           if (one_box) {
             mbar_expect_tx(full, bytes);
             tma_load_4d(hbuf, &tma_x, full, 0, row0, kb0, slot);
@@ -486,9 +488,12 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
             continue;
           }
           fresh = true;
-          if (++s == rounds) {
-            ctl[1] = 1u;
-            break;
+          if (++grp == n_groups) {
+            grp = 0;
+            if (++s == steps_end) {
+              ctl[1] = 1u;
+              break;
+            }
           }
         }
       }
@@ -503,7 +508,12 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
     int grow = row;
     bool row_ok = lane_ok && grow < B;
     bool io = row_ok && !epilogue_io_skipped(p.flags);
-    const int n_groups = multi ? p.groups : 1;
+    const bool regs = n_groups == 1;                 // the recurrent state stays in registers across timesteps
+    auto set_group = [&](int g) {
+      grow = g * GRU_M + row;
+      row_ok = lane_ok && grow < B;
+      io = row_ok && !epilogue_io_skipped(p.flags);
+    };
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t part_addr = smem_u32(part);
     const uint32_t ready_addr = smem_u32(part_ready);
@@ -630,140 +640,165 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       float h[U], c[U], bi[U], bf[U], bg[U], bo[U];
 #pragma unroll
       for (int i = 0; i < U; ++i) {
+        h[i] = (regs && row_ok) ? p.h_state[static_cast<long long>(grow) * H + u0 + i] : 0.f;
+        c[i] = (regs && row_ok) ? p.c_state[static_cast<long long>(grow) * H + u0 + i] : 0.f;
         bi[i] = p.b_hh[u0 + i];
         bf[i] = p.b_hh[H + u0 + i];
         bg[i] = p.b_hh[2 * H + u0 + i];
         bo[i] = p.b_hh[3 * H + u0 + i];
       }
-      for (int grp = 0; grp < n_groups; ++grp) {
-      grow = grp * GRU_M + row;
-      row_ok = lane_ok && grow < B;
-      io = row_ok && !epilogue_io_skipped(p.flags);
-#pragma unroll
-      for (int i = 0; i < U; ++i) {
-        h[i] = row_ok ? p.h_state[static_cast<long long>(grow) * H + u0 + i] : 0.f;
-        c[i] = row_ok ? p.c_state[static_cast<long long>(grow) * H + u0 + i] : 0.f;
-      }
       for (int t = 0; t < T; ++t) {
-        const long long rt = static_cast<long long>(grow) * T + t;
-        float xi[U], xf[U], xg[U], xo[U];
+        for (int grp = 0; grp < n_groups; ++grp) {
+          if (!regs) set_group(grp);
+          const long long rt = static_cast<long long>(grow) * T + t;
+          float xi[U], xf[U], xg[U], xo[U];
 #pragma unroll
-        for (int i = 0; i < U; ++i) xi[i] = xf[i] = xg[i] = xo[i] = 0.f;
-        if (io) {
-          const __nv_bfloat16* gp = p.gi + rt * 4 * H + u0;
-          load_units<U>(gp, xi);
-          load_units<U>(gp + H, xf);
-          load_units<U>(gp + 2 * H, xg);
-          load_units<U>(gp + 3 * H, xo);
-        }
-        float acc[4 * U];
-        exchange(acc, multi ? grp : t);
-        float gi_[U], gf_[U], gg_[U], go_[U];
+          for (int i = 0; i < U; ++i) xi[i] = xf[i] = xg[i] = xo[i] = 0.f;
+          if (io) {
+            const __nv_bfloat16* gp = p.gi + rt * 4 * H + u0;
+            load_units<U>(gp, xi);
+            load_units<U>(gp + H, xf);
+            load_units<U>(gp + 2 * H, xg);
+            load_units<U>(gp + 3 * H, xo);
+          }
+          if (!regs) {
 #pragma unroll
-        for (int i = 0; i < U; ++i) {
-          gi_[i] = sigmoid_fast(xi[i] + acc[i] + bi[i]);
-          gf_[i] = sigmoid_fast(xf[i] + acc[U + i] + bf[i]);
-          gg_[i] = tanh_fast(xg[i] + acc[2 * U + i] + bg[i]);
-          go_[i] = sigmoid_fast(xo[i] + acc[3 * U + i] + bo[i]);
-          c[i] = gf_[i] * c[i] + gi_[i] * gg_[i];
-          h[i] = go_[i] * tanh_fast(c[i]);
-        }
-        if (io) store_units<U>(p.h_ext + (static_cast<long long>(t + 1) * EB + grow) * H + u0, h);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && T > 1) publish(p.sync, p.flags, static_cast<uint32_t>(t + 1), G, lane);   // T == 1: nobody waits
-        if (p.hall && io) store_units<U>(p.hall + rt * H + u0, h);
-        if (p.gates && io) {                           // saved for backward: i, f, g, o, c_t  (5H per row)
-          __nv_bfloat16* sp = p.gates + rt * 5 * H + u0;
-          store_units<U>(sp, gi_);
-          store_units<U>(sp + H, gf_);
-          store_units<U>(sp + 2 * H, gg_);
-          store_units<U>(sp + 3 * H, go_);
-          store_units<U>(sp + 4 * H, c);
+            for (int i = 0; i < U; ++i) {
+              h[i] = row_ok ? p.h_state[static_cast<long long>(grow) * H + u0 + i] : 0.f;
+              c[i] = row_ok ? p.c_state[static_cast<long long>(grow) * H + u0 + i] : 0.f;
+            }
+          }
+          float acc[4 * U];
+          exchange(acc, t);
+          float gi_[U], gf_[U], gg_[U], go_[U];
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            gi_[i] = sigmoid_fast(xi[i] + acc[i] + bi[i]);
+            gf_[i] = sigmoid_fast(xf[i] + acc[U + i] + bf[i]);
+            gg_[i] = tanh_fast(xg[i] + acc[2 * U + i] + bg[i]);
+            go_[i] = sigmoid_fast(xo[i] + acc[3 * U + i] + bo[i]);
+            c[i] = gf_[i] * c[i] + gi_[i] * gg_[i];
+            h[i] = go_[i] * tanh_fast(c[i]);
+          }
+          if (io) store_units<U>(p.h_ext + (static_cast<long long>(t + 1) * EB + grow) * H + u0, h);
+          if (!regs && row_ok) {
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+              p.h_state[static_cast<long long>(grow) * H + u0 + i] = h[i];
+              p.c_state[static_cast<long long>(grow) * H + u0 + i] = c[i];
+            }
+          }
+          if (grp == n_groups - 1) {                   // every group's h_t is stored: one arrival per CTA and timestep
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 2 && T > 1) publish(p.sync, p.flags, static_cast<uint32_t>(t + 1), G, lane);   // T == 1: nobody waits
+          }
+          if (p.hall && io) store_units<U>(p.hall + rt * H + u0, h);
+          if (p.gates && io) {                           // saved for backward: i, f, g, o, c_t  (5H per row)
+            __nv_bfloat16* sp = p.gates + rt * 5 * H + u0;
+            store_units<U>(sp, gi_);
+            store_units<U>(sp + H, gf_);
+            store_units<U>(sp + 2 * H, gg_);
+            store_units<U>(sp + 3 * H, go_);
+            store_units<U>(sp + 4 * H, c);
+          }
         }
       }
-      if (row_ok) {
+      if (regs && row_ok) {
 #pragma unroll
         for (int i = 0; i < U; ++i) {
           p.h_state[static_cast<long long>(grow) * H + u0 + i] = h[i];
           p.c_state[static_cast<long long>(grow) * H + u0 + i] = c[i];
         }
       }
-      }  // groups
     } else if constexpr (BWD && LSTM) {
       // ---------------- LSTM backward ----------------
       float carry_c[U];
-      float sb[4 * U];                                 // bias gradients: running sums of the 4 gate gradients of this row
+      float sb[4 * U];                                 // bias gradients: running sums of the 4 gate gradients of this thread's rows
 #pragma unroll
       for (int i = 0; i < U; ++i) carry_c[i] = 0.f;
 #pragma unroll
       for (int i = 0; i < 4 * U; ++i) sb[i] = 0.f;
       for (int s = 0; s <= T; ++s) {
         const int t = T - 1 - s;
-        const long long rt = static_cast<long long>(row) * T + t;
-        float dh[U], gi_[U], gf_[U], gg_[U], go_[U], ct[U], cp[U];
+        for (int grp = 0; grp < n_groups; ++grp) {
+          if (!regs) set_group(grp);
+          const long long rt = static_cast<long long>(grow) * T + t;
+          float dh[U], gi_[U], gf_[U], gg_[U], go_[U], ct[U], cp[U];
 #pragma unroll
-        for (int i = 0; i < U; ++i) dh[i] = gi_[i] = gf_[i] = gg_[i] = go_[i] = ct[i] = cp[i] = 0.f;
-        if (io && t >= 0) {
-          load_units<U>(p.dh_out + rt * H + u0, dh);
-          const __nv_bfloat16* sp = p.gates + rt * 5 * H + u0;
-          load_units<U>(sp, gi_);
-          load_units<U>(sp + H, gf_);
-          load_units<U>(sp + 2 * H, gg_);
-          load_units<U>(sp + 3 * H, go_);
-          load_units<U>(sp + 4 * H, ct);
-          if (t > 0) {
-            load_units<U>(p.gates + (rt - 1) * 5 * H + 4 * H + u0, cp);
-          } else {
+          for (int i = 0; i < U; ++i) dh[i] = gi_[i] = gf_[i] = gg_[i] = go_[i] = ct[i] = cp[i] = 0.f;
+          if (io && t >= 0) {
+            load_units<U>(p.dh_out + rt * H + u0, dh);
+            const __nv_bfloat16* sp = p.gates + rt * 5 * H + u0;
+            load_units<U>(sp, gi_);
+            load_units<U>(sp + H, gf_);
+            load_units<U>(sp + 2 * H, gg_);
+            load_units<U>(sp + 3 * H, go_);
+            load_units<U>(sp + 4 * H, ct);
+            if (t > 0) {
+              load_units<U>(p.gates + (rt - 1) * 5 * H + 4 * H + u0, cp);
+            } else {
 #pragma unroll
-            for (int i = 0; i < U; ++i) cp[i] = p.c_init[static_cast<long long>(row) * H + u0 + i];
+              for (int i = 0; i < U; ++i) cp[i] = p.c_init[static_cast<long long>(grow) * H + u0 + i];
+            }
           }
-        }
-        float d[U];
+          if (!regs) {                                   // the running cell-state carry of this row lives in dc0
 #pragma unroll
-        for (int i = 0; i < U; ++i) d[i] = 0.f;
-        if (s > 0) exchange(d, s);
-        if (t < 0) {
+            for (int i = 0; i < U; ++i)
+              carry_c[i] = (s > 0 && row_ok) ? p.dc0[static_cast<long long>(grow) * H + u0 + i] : 0.f;
+          }
+          float d[U];
+#pragma unroll
+          for (int i = 0; i < U; ++i) d[i] = 0.f;
+          if (s > 0) exchange(d, s);
+          if (t < 0) {
+            if (row_ok) {
+#pragma unroll
+              for (int i = 0; i < U; ++i) {
+                p.dh0[static_cast<long long>(grow) * H + u0 + i] = d[i];
+                p.dc0[static_cast<long long>(grow) * H + u0 + i] = carry_c[i];
+              }
+            }
+            continue;
+          }
+          float pi[U], pf[U], pg[U], po[U];
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            const float dht = dh[i] + d[i];
+            const float tc = tanh_fast(ct[i]);
+            const float dc = dht * go_[i] * (1.f - tc * tc) + carry_c[i];
+            carry_c[i] = dc * gf_[i];
+            pi[i] = dc * gg_[i] * gi_[i] * (1.f - gi_[i]);
+            pf[i] = dc * cp[i] * gf_[i] * (1.f - gf_[i]);
+            pg[i] = dc * gi_[i] * (1.f - gg_[i] * gg_[i]);
+            po[i] = dht * tc * go_[i] * (1.f - go_[i]);
+          }
+          if (io) {
+            __nv_bfloat16* ghp = p.dgh + (static_cast<long long>(t) * EB + grow) * 4 * H + u0;   // exchanged
+            store_units<U>(ghp, pi);
+            store_units<U>(ghp + H, pf);
+            store_units<U>(ghp + 2 * H, pg);
+            store_units<U>(ghp + 3 * H, po);
+          }
+          if (!regs && row_ok) {
+#pragma unroll
+            for (int i = 0; i < U; ++i) p.dc0[static_cast<long long>(grow) * H + u0 + i] = carry_c[i];
+          }
+          if (grp == n_groups - 1) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 2) publish(p.sync, p.flags, static_cast<uint32_t>(s + 1), G, lane);
+          }
+          if (io) {                                               // same values, batch-major, for the GEMMs
+            __nv_bfloat16* gip = p.dgi + rt * 4 * H + u0;
+            store_units<U>(gip, pi);
+            store_units<U>(gip + H, pf);
+            store_units<U>(gip + 2 * H, pg);
+            store_units<U>(gip + 3 * H, po);
+          }
           if (row_ok) {
 #pragma unroll
             for (int i = 0; i < U; ++i) {
-              p.dh0[static_cast<long long>(row) * H + u0 + i] = d[i];
-              p.dc0[static_cast<long long>(row) * H + u0 + i] = carry_c[i];
+              sb[i] += pi[i]; sb[U + i] += pf[i]; sb[2 * U + i] += pg[i]; sb[3 * U + i] += po[i];
             }
-          }
-          break;
-        }
-        float pi[U], pf[U], pg[U], po[U];
-#pragma unroll
-        for (int i = 0; i < U; ++i) {
-          const float dht = dh[i] + d[i];
-          const float tc = tanh_fast(ct[i]);
-          const float dc = dht * go_[i] * (1.f - tc * tc) + carry_c[i];
-          carry_c[i] = dc * gf_[i];
-          pi[i] = dc * gg_[i] * gi_[i] * (1.f - gi_[i]);
-          pf[i] = dc * cp[i] * gf_[i] * (1.f - gf_[i]);
-          pg[i] = dc * gi_[i] * (1.f - gg_[i] * gg_[i]);
-          po[i] = dht * tc * go_[i] * (1.f - go_[i]);
-        }
-        if (io) {
-          __nv_bfloat16* ghp = p.dgh + (static_cast<long long>(t) * EB + row) * 4 * H + u0;   // exchanged
-          store_units<U>(ghp, pi);
-          store_units<U>(ghp + H, pf);
-          store_units<U>(ghp + 2 * H, pg);
-          store_units<U>(ghp + 3 * H, po);
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2) publish(p.sync, p.flags, static_cast<uint32_t>(s + 1), G, lane);
-        if (io) {                                               // same values, batch-major, for the GEMMs
-          __nv_bfloat16* gip = p.dgi + rt * 4 * H + u0;
-          store_units<U>(gip, pi);
-          store_units<U>(gip + H, pf);
-          store_units<U>(gip + 2 * H, pg);
-          store_units<U>(gip + 3 * H, po);
-        }
-        if (row_ok) {
-#pragma unroll
-          for (int i = 0; i < U; ++i) {
-            sb[i] += pi[i]; sb[U + i] += pf[i]; sb[2 * U + i] += pg[i]; sb[3 * U + i] += po[i];
           }
         }
       }
@@ -771,7 +806,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         float* sred = reinterpret_cast<float*>(hbuf);
         if (lane_ok) {
 #pragma unroll
-          for (int i = 0; i < 4 * U; ++i) sred[i * GRU_M + row] = row_ok ? sb[i] : 0.f;
+          for (int i = 0; i < 4 * U; ++i) sred[i * GRU_M + row] = sb[i];     // (0 for rows that never held a slot)
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int v = threadIdx.x - 64;
@@ -787,128 +822,149 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       float h[U], bhr[U], bhz[U], bhn[U];
 #pragma unroll
       for (int i = 0; i < U; ++i) {
+        h[i] = (regs && row_ok) ? p.h_state[static_cast<long long>(grow) * H + u0 + i] : 0.f;
         bhr[i] = p.b_hh[u0 + i];
         bhz[i] = p.b_hh[H + u0 + i];
         bhn[i] = p.b_hh[2 * H + u0 + i];
       }
-      for (int grp = 0; grp < n_groups; ++grp) {
-      grow = grp * GRU_M + row;
-      row_ok = lane_ok && grow < B;
-      io = row_ok && !epilogue_io_skipped(p.flags);
-#pragma unroll
-      for (int i = 0; i < U; ++i) h[i] = row_ok ? p.h_state[static_cast<long long>(grow) * H + u0 + i] : 0.f;
       for (int t = 0; t < T; ++t) {
-        const long long rt = static_cast<long long>(grow) * T + t;
-        float gr[U], gz[U], gn[U];
+        for (int grp = 0; grp < n_groups; ++grp) {
+          if (!regs) set_group(grp);
+          const long long rt = static_cast<long long>(grow) * T + t;
+          float gr[U], gz[U], gn[U];
 #pragma unroll
-        for (int i = 0; i < U; ++i) gr[i] = gz[i] = gn[i] = 0.f;
-        if (io) {
-          const __nv_bfloat16* gp = p.gi + rt * 3 * H + u0;
-          load_units<U>(gp, gr);
-          load_units<U>(gp + H, gz);
-          load_units<U>(gp + 2 * H, gn);
-        }
-        float acc[3 * U];
-        exchange(acc, multi ? grp : t);
-        float r[U], z[U], n[U], hn[U];
+          for (int i = 0; i < U; ++i) gr[i] = gz[i] = gn[i] = 0.f;
+          if (io) {
+            const __nv_bfloat16* gp = p.gi + rt * 3 * H + u0;
+            load_units<U>(gp, gr);
+            load_units<U>(gp + H, gz);
+            load_units<U>(gp + 2 * H, gn);
+          }
+          if (!regs) {
 #pragma unroll
-        for (int i = 0; i < U; ++i) {
-          r[i] = sigmoid_fast(gr[i] + acc[i] + bhr[i]);
-          z[i] = sigmoid_fast(gz[i] + acc[U + i] + bhz[i]);
-          hn[i] = acc[2 * U + i] + bhn[i];
-          n[i] = tanh_fast(gn[i] + r[i] * hn[i]);
-          h[i] = (1.f - z[i]) * n[i] + z[i] * h[i];
-        }
-        if (io) store_units<U>(p.h_ext + (static_cast<long long>(t + 1) * EB + grow) * H + u0, h);
-        // publish h_t: all epilogue threads' stores -> one release arrival per CTA
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2) {
-          if (lane == 0) GRU_TS(6, t);
-          if (T > 1) publish(p.sync, p.flags, static_cast<uint32_t>(t + 1), G, lane);   // T == 1: nobody waits
-        }
-        // the batch-major copy of h_t (GEMM operand) and the saved gates are off the critical path
-        if (p.hall && io) store_units<U>(p.hall + rt * H + u0, h);
-        if (p.gates && io) {
-          __nv_bfloat16* sp = p.gates + rt * 4 * H + u0;
-          store_units<U>(sp, r);
-          store_units<U>(sp + H, z);
-          store_units<U>(sp + 2 * H, n);
-          store_units<U>(sp + 3 * H, hn);
+            for (int i = 0; i < U; ++i) h[i] = row_ok ? p.h_state[static_cast<long long>(grow) * H + u0 + i] : 0.f;
+          }
+          float acc[3 * U];
+          exchange(acc, t);
+          float r[U], z[U], n[U], hn[U];
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            r[i] = sigmoid_fast(gr[i] + acc[i] + bhr[i]);
+            z[i] = sigmoid_fast(gz[i] + acc[U + i] + bhz[i]);
+            hn[i] = acc[2 * U + i] + bhn[i];
+            n[i] = tanh_fast(gn[i] + r[i] * hn[i]);
+            h[i] = (1.f - z[i]) * n[i] + z[i] * h[i];
+          }
+          if (io) store_units<U>(p.h_ext + (static_cast<long long>(t + 1) * EB + grow) * H + u0, h);
+          if (!regs && row_ok) {
+#pragma unroll
+            for (int i = 0; i < U; ++i) p.h_state[static_cast<long long>(grow) * H + u0 + i] = h[i];
+          }
+          if (grp == n_groups - 1) {
+            // publish h_t: all epilogue threads' stores (of every group) -> one arrival per CTA
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 2) {
+              if (lane == 0) GRU_TS(6, t);
+              if (T > 1) publish(p.sync, p.flags, static_cast<uint32_t>(t + 1), G, lane);   // T == 1: nobody waits
+            }
+          }
+          // the batch-major copy of h_t (GEMM operand) and the saved gates are off the critical path
+          if (p.hall && io) store_units<U>(p.hall + rt * H + u0, h);
+          if (p.gates && io) {
+            __nv_bfloat16* sp = p.gates + rt * 4 * H + u0;
+            store_units<U>(sp, r);
+            store_units<U>(sp + H, z);
+            store_units<U>(sp + 2 * H, n);
+            store_units<U>(sp + 3 * H, hn);
+          }
         }
       }
-      if (row_ok) {
+      if (regs && row_ok) {
 #pragma unroll
         for (int i = 0; i < U; ++i) p.h_state[static_cast<long long>(grow) * H + u0 + i] = h[i];
       }
-      }  // groups
     } else {
       float carry[U];
-      float sb[4 * U];                                 // bias gradients: running sums of gr, gz, gn, ghn of this row
+      float sb[4 * U];                                 // bias gradients: running sums of gr, gz, gn, ghn of this thread's rows
 #pragma unroll
       for (int i = 0; i < U; ++i) carry[i] = 0.f;
 #pragma unroll
       for (int i = 0; i < 4 * U; ++i) sb[i] = 0.f;
       for (int s = 0; s <= T; ++s) {
         const int t = T - 1 - s;
-        const long long rt = static_cast<long long>(row) * T + t;
-        float dh[U], r[U], z[U], n[U], hn[U], hp[U];
+        for (int grp = 0; grp < n_groups; ++grp) {
+          if (!regs) set_group(grp);
+          const long long rt = static_cast<long long>(grow) * T + t;
+          float dh[U], r[U], z[U], n[U], hn[U], hp[U];
 #pragma unroll
-        for (int i = 0; i < U; ++i) dh[i] = r[i] = z[i] = n[i] = hn[i] = hp[i] = 0.f;
-        if (io && t >= 0) {
-          load_units<U>(p.dh_out + rt * H + u0, dh);
-          const __nv_bfloat16* sp = p.gates + rt * 4 * H + u0;
-          load_units<U>(sp, r);
-          load_units<U>(sp + H, z);
-          load_units<U>(sp + 2 * H, n);
-          load_units<U>(sp + 3 * H, hn);
-          load_units<U>(p.h_ext + (static_cast<long long>(t) * EB + row) * H + u0, hp);
-        }
-        float d[U];
-#pragma unroll
-        for (int i = 0; i < U; ++i) d[i] = 0.f;
-        if (s > 0) exchange(d, s);
-        if (t < 0) {
-          if (row_ok) {
-#pragma unroll
-            for (int i = 0; i < U; ++i) p.dh0[static_cast<long long>(row) * H + u0 + i] = carry[i] + d[i];
+          for (int i = 0; i < U; ++i) dh[i] = r[i] = z[i] = n[i] = hn[i] = hp[i] = 0.f;
+          if (io && t >= 0) {
+            load_units<U>(p.dh_out + rt * H + u0, dh);
+            const __nv_bfloat16* sp = p.gates + rt * 4 * H + u0;
+            load_units<U>(sp, r);
+            load_units<U>(sp + H, z);
+            load_units<U>(sp + 2 * H, n);
+            load_units<U>(sp + 3 * H, hn);
+            load_units<U>(p.h_ext + (static_cast<long long>(t) * EB + grow) * H + u0, hp);
           }
-          break;
-        }
-        float gr[U], gz[U], gn[U], ghn[U];
+          if (!regs) {                                   // the running carry z * dL/dh of this row lives in dh0
 #pragma unroll
-        for (int i = 0; i < U; ++i) {
-          const float dht = dh[i] + carry[i] + d[i];
-          const float dn_ = dht * (1.f - z[i]);
-          const float dz_ = dht * (hp[i] - n[i]);
-          carry[i] = dht * z[i];
-          const float dn_pre = dn_ * (1.f - n[i] * n[i]);
-          const float dr_ = dn_pre * hn[i];
-          gr[i] = dr_ * r[i] * (1.f - r[i]);
-          gz[i] = dz_ * z[i] * (1.f - z[i]);
-          gn[i] = dn_pre;
-          ghn[i] = dn_pre * r[i];
-        }
-        if (io) {
-          __nv_bfloat16* ghp = p.dgh + (static_cast<long long>(t) * EB + row) * 3 * H + u0;   // exchanged
-          store_units<U>(ghp, gr);
-          store_units<U>(ghp + H, gz);
-          store_units<U>(ghp + 2 * H, ghn);
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2) {
-          if (lane == 0) GRU_TS(6, s);
-          publish(p.sync, p.flags, static_cast<uint32_t>(s + 1), G, lane);
-        }
-        if (io) {                                               // dgi is only read after the kernel
-          __nv_bfloat16* gip = p.dgi + rt * 3 * H + u0;
-          store_units<U>(gip, gr);
-          store_units<U>(gip + H, gz);
-          store_units<U>(gip + 2 * H, gn);
-        }
-        if (row_ok) {                                           // (rows beyond the batch hold garbage)
+            for (int i = 0; i < U; ++i)
+              carry[i] = (s > 0 && row_ok) ? p.dh0[static_cast<long long>(grow) * H + u0 + i] : 0.f;
+          }
+          float d[U];
+#pragma unroll
+          for (int i = 0; i < U; ++i) d[i] = 0.f;
+          if (s > 0) exchange(d, s);
+          if (t < 0) {
+            if (row_ok) {
+#pragma unroll
+              for (int i = 0; i < U; ++i) p.dh0[static_cast<long long>(grow) * H + u0 + i] = carry[i] + d[i];
+            }
+            continue;
+          }
+          float gr[U], gz[U], gn[U], ghn[U];
 #pragma unroll
           for (int i = 0; i < U; ++i) {
-            sb[i] += gr[i]; sb[U + i] += gz[i]; sb[2 * U + i] += gn[i]; sb[3 * U + i] += ghn[i];
+            const float dht = dh[i] + carry[i] + d[i];
+            const float dn_ = dht * (1.f - z[i]);
+            const float dz_ = dht * (hp[i] - n[i]);
+            carry[i] = dht * z[i];
+            const float dn_pre = dn_ * (1.f - n[i] * n[i]);
+            const float dr_ = dn_pre * hn[i];
+            gr[i] = dr_ * r[i] * (1.f - r[i]);
+            gz[i] = dz_ * z[i] * (1.f - z[i]);
+            gn[i] = dn_pre;
+            ghn[i] = dn_pre * r[i];
+          }
+          if (io) {
+            __nv_bfloat16* ghp = p.dgh + (static_cast<long long>(t) * EB + grow) * 3 * H + u0;   // exchanged
+            store_units<U>(ghp, gr);
+            store_units<U>(ghp + H, gz);
+            store_units<U>(ghp + 2 * H, ghn);
+          }
+          if (!regs && row_ok) {
+#pragma unroll
+            for (int i = 0; i < U; ++i) p.dh0[static_cast<long long>(grow) * H + u0 + i] = carry[i];
+          }
+          if (grp == n_groups - 1) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 2) {
+              if (lane == 0) GRU_TS(6, s);
+              publish(p.sync, p.flags, static_cast<uint32_t>(s + 1), G, lane);
+            }
+          }
+          if (io) {                                               // dgi is only read after the kernel
+            __nv_bfloat16* gip = p.dgi + rt * 3 * H + u0;
+            store_units<U>(gip, gr);
+            store_units<U>(gip + H, gz);
+            store_units<U>(gip + 2 * H, gn);
+          }
+          if (row_ok) {                                           // (rows beyond the batch hold garbage)
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+              sb[i] += gr[i]; sb[U + i] += gz[i]; sb[2 * U + i] += gn[i]; sb[3 * U + i] += ghn[i];
+            }
           }
         }
       }
@@ -917,7 +973,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
         float* sred = reinterpret_cast<float*>(hbuf);            // [4U][64 rows]
         if (lane_ok) {
 #pragma unroll
-          for (int i = 0; i < 4 * U; ++i) sred[i * GRU_M + row] = row_ok ? sb[i] : 0.f;
+          for (int i = 0; i < 4 * U; ++i) sred[i * GRU_M + row] = sb[i];     // (0 for rows that never held a slot)
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int v = threadIdx.x - 64;                          // epilogue threads 0..127
@@ -1262,9 +1318,7 @@ static int check_common(const srnn_gru_args* a) {
 extern "C" int srnn_gru_forward(const srnn_gru_args* a, srnn_stream_t stream) {
   int rc = check_common(a);
   if (rc) return rc;
-  SRNN_CHECK_ARG(a->batch <= GRU_M || a->steps == 1,
-                 "gru_forward: more than 64 rows per launch only for steps == 1 (got batch %d, steps %d): run longer "
-                 "sequences as slot groups of <= 64 rows", a->batch, a->steps);
+
   SRNN_CHECK_ARG(a->gi && a->b_hh && a->h_state, "gru_forward: null buffer");
   if (a->cell == 1) {
     SRNN_CHECK_ARG(a->c_state, "lstm forward: c_state required");
@@ -1276,7 +1330,7 @@ extern "C" int srnn_gru_forward(const srnn_gru_args* a, srnn_stream_t stream) {
 extern "C" int srnn_gru_backward(const srnn_gru_args* a, srnn_stream_t stream) {
   int rc = check_common(a);
   if (rc) return rc;
-  SRNN_CHECK_ARG(a->batch <= GRU_M, "gru_backward: batch must be <= 64 per launch (got %d)", a->batch);
+
   SRNN_CHECK_ARG(a->dh_out && a->dgi && a->dgh && a->dh0, "gru_backward: null buffer");
   if (a->cell == 1) {
     SRNN_CHECK_ARG(a->c_init && a->dc0, "lstm backward: c_init and dc0 required");

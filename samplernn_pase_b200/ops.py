@@ -328,8 +328,8 @@ def gemm_nll(mode, a, w, bias, target, m, k, lda, ldw, lse=None, logp_target=Non
 # ----------------------------------------------------------------------------------------------
 # recurrence
 # ----------------------------------------------------------------------------------------------
-GRU_MAX_BATCH = 64
-GRU_MAX_STEP_BATCH = 512
+GRU_MAX_BATCH = 64          # rows of one MMA tile (a group)
+GRU_MAX_STEP_BATCH = 512    # rows per launch (8 groups); set to 64 to run every group as its own launch
 GRU_SYNC_WORDS = 8192       # srnn_gru_args.sync: arrival counter, statistics and one release-flag line per CTA
 gru_tuning_flags = 0     # srnn_gru_args.tuning_flags (scripts/gru_microbench.py sweeps them)
 gru_debug_ts = None      # int64 [256, 8] tensor receiving CTA 0's pipeline timestamps
@@ -341,10 +341,11 @@ gru_last_sync = None
 
 
 def _gru_call(name, batch, steps, hidden, cell=0, **bufs):
-    """Runs the persistent kernel over slot groups of <= 64 rows (independent sequences).
+    """Runs the persistent kernel over the batch rows (independent sequences), at most GRU_MAX_STEP_BATCH per launch.
     ``bufs``: field -> (tensor, elements per batch row); time-major buffers advance by one row."""
-    # a single forward timestep (generation) takes all rows in one launch: the kernel walks the 64-row blocks itself
-    group = GRU_MAX_STEP_BATCH if (steps == 1 and name == 'srnn_gru_forward') else GRU_MAX_BATCH
+    # one launch takes up to GRU_MAX_STEP_BATCH rows: the kernel walks groups of 64 rows inside every timestep (one grid
+    # handshake per timestep for all of them, the weight slice fetched once)
+    group = GRU_MAX_STEP_BATCH
     for b0 in range(0, batch, group):
         nb = min(group, batch - b0)
         a = GruArgs()

@@ -734,3 +734,51 @@ def test_gemm_relu_mask_and_gate_mask(ops, m, n, k, batch):
     ops.gemm_nt(g, w, d_msk, m, n, k, k, k, n, batch=batch, a_bs=m * k, c_bs=m * n, gate_mask=mask, colsum=cs_m)
     assert torch.equal(d_act, d_msk)
     assert rel_l2(cs_m, cs_a) < 1e-5
+
+
+@pytest.mark.parametrize('cell', [0, 1])
+@pytest.mark.parametrize('bsz,t,h', [(128, 40, 256), (150, 9, 1024), (70, 33, 64)])
+def test_recurrence_many_rows_per_launch_equals_group_launches(ops, cell, bsz, t, h):
+    """More than 64 rows in ONE multi-timestep launch (groups of 64 walked inside every timestep, state of a row kept in
+    its global buffer between timesteps) must equal the per-group launches bit for bit, forward and backward, GRU and
+    LSTM, with a ragged last group."""
+    ng = 4 if cell else 3
+    gi = rnd(bsz, t, ng * h, seed=cell).to(BF16)
+    w_hh = rnd(ng * h, h, scale=1 / math.sqrt(h), seed=1).to(BF16)
+    b_hh = rnd(ng * h, scale=0.1, seed=2)
+    h0 = rnd(bsz, h, scale=0.5, seed=3)
+    c0 = rnd(bsz, h, scale=0.5, seed=4)
+    dh_out = rnd(bsz, t, h, scale=0.1, seed=5).to(BF16)
+
+    def run(max_rows):
+        old = ops.GRU_MAX_STEP_BATCH
+        ops.GRU_MAX_STEP_BATCH = max_rows
+        try:
+            h_ext = torch.zeros(t + 1, bsz, h, dtype=BF16, device='cuda')
+            h_ext[0] = h0.to(BF16)
+            hall = torch.zeros(bsz * t, h, dtype=BF16, device='cuda')
+            hs, cs = h0.clone(), c0.clone()
+            gates = torch.zeros(bsz * t, (ng + 1) * h, dtype=BF16, device='cuda')
+            dgi = torch.zeros(bsz * t, ng * h, dtype=BF16, device='cuda')
+            dgh = torch.zeros(t * bsz, ng * h, dtype=BF16, device='cuda')
+            dh0 = torch.zeros(bsz, h, dtype=F32, device='cuda')
+            dc0 = torch.zeros(bsz, h, dtype=F32, device='cuda')
+            db_ih = torch.zeros(ng * h, dtype=F32, device='cuda')
+            db_hh = torch.zeros(ng * h, dtype=F32, device='cuda')
+            if cell:
+                ops.lstm_forward(gi.view(bsz * t, ng * h), w_hh, b_hh, h_ext, hall, hs, cs, gates, bsz, t, h)
+                ops.lstm_backward(w_hh.t().contiguous(), h_ext, gates, c0, dh_out.view(bsz * t, h), dgi, dgh, dh0, dc0, bsz, t, h,
+                                  db_ih, db_hh)
+            else:
+                ops.gru_forward(gi.view(bsz * t, ng * h), w_hh, b_hh, h_ext, hall, hs, gates, bsz, t, h)
+                ops.gru_backward(w_hh.t().contiguous(), h_ext, gates, dh_out.view(bsz * t, h), dgi, dgh, dh0, bsz, t, h, db_ih, db_hh)
+            return hall, hs, cs, h_ext, gates, dgi, dgh, dh0, dc0, db_ih, db_hh
+        finally:
+            ops.GRU_MAX_STEP_BATCH = old
+
+    ref = run(64)
+    got = run(512)
+    for i, (a, b) in enumerate(zip(got[:-2], ref[:-2])):
+        assert torch.equal(a, b), (cell, bsz, i)
+    for a, b in zip(got[-2:], ref[-2:]):                # bias gradients: same addends, summed in a different order
+        assert rel_l2(a, b) < 1e-5
