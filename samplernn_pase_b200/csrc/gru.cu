@@ -512,6 +512,9 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
     bool row_ok = lane_ok && grow < B;
     bool io = row_ok && !epilogue_io_skipped(p.flags);
     const bool regs = n_groups == 1;                 // the recurrent state stays in registers across timesteps
+    // (A "quiet window" - the epilogue warps holding their off-critical-path stores and the next step's input loads back for
+    // 512..3 072 cycles after the publish so that this SM's memory pipeline stays free for the polls - measured 3.76-3.99 us
+    // per forward timestep against 3.60 and no change backward: the spinning warps take issue slots from the issuing thread.)
     auto set_group = [&](int g) {
       grow = g * GRU_M + row;
       row_ok = lane_ok && grow < B;

@@ -76,20 +76,21 @@ for flags in [int(f) for f in a.ts_flags.split(',') if f]:
             base = int(t_[s_, 0])
             print(f'{s_:4d}  ' + '  '.join(f'{int(t_[s_, i]) - base:12d}' for i in order) + f'   {int(t_[s_ + 1, 0]) - base:10d}')
 ops.gru_tuning_flags = 0
-# skew between CTAs: global timer (ns) of every CTA at timestep 24 of the forward kernel
-ts = torch.zeros(256, 8, dtype=torch.int64, device='cuda')
-ops.gru_tuning_flags = 128
-ops.gru_debug_ts = ts
-run('fwd')
-torch.cuda.synchronize()
-ops.gru_debug_ts = None
-ops.gru_tuning_flags = 0
-t_ = ts.cpu()
-n_cta = int((t_[:, 0] > 0).sum())
-t0 = int(t_[:n_cta, 0].min())
-print(f'per-CTA global timer at step 24 ({n_cta} CTAs), ns after the first CTA left the grid wait')
-for i, nm in zip(order, names):
-    col = t_[:n_cta, i] - t0
-    print(f'{nm:>14s}: min {int(col.min()):6d}  median {int(col.median()):6d}  max {int(col.max()):6d}')
-print('publish time per CTA (ns):', sorted((t_[:n_cta, 6] - t0).tolist()))
-print('wait_done per CTA (ns):', sorted((t_[:n_cta, 0] - t0).tolist()))
+# skew between CTAs: global timer (ns) of every CTA at timestep 24 of the forward and of the backward kernel
+for kind in ('fwd', 'bwd'):
+    ts = torch.zeros(256, 8, dtype=torch.int64, device='cuda')
+    ops.gru_tuning_flags = 128
+    ops.gru_debug_ts = ts
+    run(kind)
+    torch.cuda.synchronize()
+    ops.gru_debug_ts = None
+    ops.gru_tuning_flags = 0
+    t_ = ts.cpu()
+    n_cta = int((t_[:, 0] > 0).sum())
+    t0 = int(t_[:n_cta, 0].min())
+    print(f'{kind}: per-CTA global timer at step 24 ({n_cta} CTAs), ns after the first CTA left the grid wait')
+    for i, nm in zip(order, names):
+        col = t_[:n_cta, i] - t0
+        if int(t_[:n_cta, i].max()) <= 0:
+            continue
+        print(f'{nm:>14s}: min {int(col.min()):6d}  median {int(col.median()):6d}  max {int(col.max()):6d}')
