@@ -551,15 +551,34 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           static_assert(C != 1 || NCOLS <= 32, "C == 1: one 32-column chunk per partial");
 #pragma unroll
           for (int i = 0; i < NG * U; ++i) out[i] = 0.f;
+          if constexpr (NG * U == 24 && MW == 4) {
+            // GRU forward: the 24 columns of all four partial tiles are requested at once (16 + 8 columns each, 96
+            // registers) and waited for ONCE - one TMEM round trip per timestep instead of two
+            uint32_t va[MW][16], vb[MW][8];
 #pragma unroll
-          for (int pw = 0; pw < MW; pw += 2) {           // two partial tiles in flight per wait
-            if (pw >= KBC * 4) break;                    // fewer K steps than issuers: those partials were never written
-            uint32_t v[2][32];
-            tmem_ld32(t_addr + pw * NCOLS, v[0]);
-            tmem_ld32(t_addr + (pw + 1) * NCOLS, v[1]);
+            for (int pw = 0; pw < MW; ++pw) {
+              tmem_ld16(t_addr + pw * NCOLS, va[pw]);
+              tmem_ld8(t_addr + pw * NCOLS + 16, vb[pw]);
+            }
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < NG * U; ++i) out[i] += __uint_as_float(v[0][i]) + __uint_as_float(v[1][i]);
+            for (int pw = 0; pw < MW; ++pw) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) out[i] += __uint_as_float(va[pw][i]);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) out[16 + i] += __uint_as_float(vb[pw][i]);
+            }
+          } else {
+#pragma unroll
+            for (int pw = 0; pw < MW; pw += 2) {           // two partial tiles in flight per wait
+              if (pw >= KBC * 4) break;                    // fewer K steps than issuers: those partials were never written
+              uint32_t v[2][32];
+              tmem_ld32(t_addr + pw * NCOLS, v[0]);
+              tmem_ld32(t_addr + (pw + 1) * NCOLS, v[1]);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < NG * U; ++i) out[i] += __uint_as_float(v[0][i]) + __uint_as_float(v[1][i]);
+            }
           }
           tc_fence_before();
         } else {
