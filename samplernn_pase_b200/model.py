@@ -176,20 +176,25 @@ class FrameLevelLayer(torch.nn.Module):
 
     def forward(self, x, conds, upper_conditioning, rnn_state):
         """Reference calling convention: ``x`` (B,T,fs) dequantised floats, ``rnn_state`` a list
-        with one (layers,H) tensor or None per slot.  Returns fp32 tensors."""
+        with one (layers,H) tensor or None per slot.  Returns fp32 tensors ``(upsampled, h_n)``.
+        LSTM tiers (extension): a slot's state is a ``(h, c)`` pair of (layers,H) tensors and the second return value
+        is the pair ``(h_n, c_n)``."""
         b = x.shape[0]
         dev = x.device
+        lstm = self.rnn_cell == 'lstm'
         use = torch.tensor([s is not None for s in rnn_state], dtype=torch.uint8).to(dev)
-        carried = None
-        if any(s is not None for s in rnn_state):
+
+        def dense(pick):
+            if not any(s is not None for s in rnn_state):
+                return None
             zero = torch.zeros(self.rnn_layers, self.rnn_hidden_size, device=dev)
-            carried = torch.stack([s if s is not None else zero for s in rnn_state], dim=1).contiguous()
-        h_init = self.initial_state(carried, use)
+            return torch.stack([pick(s) if s is not None else zero for s in rnn_state], dim=1).contiguous()
+
+        h_init = self.initial_state(dense((lambda s: s[0]) if lstm else (lambda s: s)), use)
+        c_init = self.initial_cell(dense(lambda s: s[1]), use) if lstm else None
         upper = upper_conditioning.to(torch.bfloat16) if upper_conditioning is not None else None
-        if self.rnn_cell == 'lstm':
-            raise NotImplementedError('the per-layer list-of-states API exists for GRU tiers (the reference cell)')
-        up, hn, _ = self._tier(None, 0, None, x.float(), conds.float(), upper, h_init)
-        return up.float(), hn
+        up, hn, cn = self._tier(None, 0, None, x.float(), conds.float(), upper, h_init, c_init=c_init)
+        return up.float(), ((hn, cn) if lstm else hn)
 
 
 class SampleLevelLayer(torch.nn.Module):

@@ -492,3 +492,27 @@ def test_single_frame_sequences_forward_backward_vs_cpu_oracle():
             h0r = p_ref[f'frames_layers.{n}.rnn_h0'].grad
             assert rel_l2(h0g, h0r) <= 0.2, (k, n, rel_l2(h0g, h0r))
             assert float((model._state[n].cpu() - state.h[n]).abs().max()) <= 3e-2
+
+
+def test_layer_level_api_with_lstm_tiers():
+    """FrameLevelLayer.forward with the reference's list-of-states convention also works for the LSTM extension: a slot's
+    state is an (h, c) pair; checked against the oracle's LSTM tier (O-C, parity unpinned by the reference)."""
+    from samplernn_pase_b200 import SampleRNNModel
+    spec = O.ModelSpec([4, 4], [1, 1], [64, 64], 5, cell='lstm')
+    params = O.init_params(spec, conds_speaker_n=5, perturb=0.1)
+    model = SampleRNNModel('embedding', 5, 15, 'acoustic', [9, 5, 4, 3], 10, 50, 5, [4, 4], [1, 1], [64, 64], True, 256,
+                           rnn_cell='lstm').cuda()
+    model.load_state_dict(params)
+    bsz, n = 4, 1
+    g = torch.Generator().manual_seed(2)
+    frames = torch.rand(bsz, 5, 16, generator=g) * 0.8
+    conds = torch.randn(bsz, 5, 50, generator=g)
+    h_prev = torch.randn(1, bsz, 64, generator=g) * 0.3
+    c_prev = torch.randn(1, bsz, 64, generator=g) * 0.3
+    states = [(h_prev[:, i].cuda(), c_prev[:, i].cuda()) if i != 2 else None for i in range(bsz)]
+    h_init = torch.stack([h_prev[:, i] if i != 2 else params[f'frames_layers.{n}.rnn_h0'] for i in range(bsz)], 1)
+    c_init = torch.stack([c_prev[:, i] if i != 2 else params[f'frames_layers.{n}.rnn_c0'] for i in range(bsz)], 1)
+    up_ref, hn_ref, cn_ref = O.frame_tier(params, n, frames, conds, None, h_init, cell='lstm', c0=c_init)
+    up, (hn, cn) = model.frames_layers[n](frames.cuda(), conds.cuda(), None, states)
+    assert float((up.cpu() - up_ref).abs().max()) < 5e-2
+    assert float((hn.cpu() - hn_ref).abs().max()) < 3e-2 and float((cn.cpu() - cn_ref).abs().max()) < 5e-2
