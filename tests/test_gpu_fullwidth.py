@@ -237,3 +237,44 @@ def test_full_width_generation_consistent_with_teacher_forcing():
     y3 = model.test(utt.cuda(), info, generator=torch.Generator(device='cuda').manual_seed(6)).cpu()
     assert not torch.equal(y, y3)
     G.GRAPH_FRAMES = 8
+
+
+def test_full_size_config2_size_independent_properties():
+    """BASELINE config 2 at its FULL size (64 slots x L=1000, RF=16 000, H=1024: 1.024 M rows) where no oracle runs:
+    properties that must hold exactly whatever the size -
+      * slot-permutation equivariance: utterance slots are independent, so permuting them permutes log p(target) bit for bit
+        (rows keep their K-order in every contraction; the recurrent kernel treats batch rows independently);
+      * chunked == unchunked: two chunks of L=500 with carry give exactly the log-probabilities of one chunk of L=1000
+        (the carried state is the fp32 state the kernel would have kept in registers);
+      * every log-probability is finite and <= 0, and the mean NLL sits at ln(256) for the random initialisation."""
+    if not torch.cuda.is_available():
+        pytest.skip('needs a GPU')
+    from samplernn_pase_b200 import SampleRNNModel, synthetic
+    kw = dict(conds_speaker_type='embedding', conds_speaker_n=126, conds_speaker_size=15, conds_utterance_type='acoustic',
+              conds_utterance_linguistic_n=[9, 5, 4, 3], conds_utterance_linguistic_emb_size=10, conds_size=50,
+              ratios=[4, 4], rnn_layers=[1, 1], rnn_hidden_size=[1024, 1024], q_type_ulaw=True, q_levels=256, fused_loss=True)
+    torch.manual_seed(1234)
+    full = SampleRNNModel(sequence_length=1000, **kw).cuda()
+    half = SampleRNNModel(sequence_length=500, **kw).cuda()
+    half.load_state_dict(full.state_dict())
+    b, fs = 64, 16
+    wav, conds, spk = synthetic.synthetic_utterances(fs, 16000, 1000, b, 1)
+    info = [{'speaker': {'index': int(s)}} for s in spk]
+    ones = torch.ones(b, dtype=torch.int64)
+    with torch.no_grad():
+        x, y, c = (t.cuda() for t in synthetic.chunk_of(fs, 16000, 1000, wav, conds, 0))
+        lp = full(x, y, c, info, ones)[0][:, :, 0]                               # (64, 16000) log p(target)
+        assert bool(torch.isfinite(lp).all()) and float(lp.max()) <= 0.0
+        assert abs(float(-lp.mean()) - 5.545) < 0.3
+        perm = torch.randperm(b, generator=torch.Generator().manual_seed(3))
+        full.reset_states()
+        lp_p = full(x[perm.cuda()], y[perm.cuda()], c[perm.cuda()], [info[int(i)] for i in perm], ones)[0][:, :, 0]
+        assert torch.equal(lp_p, lp[perm.cuda()])
+        parts = []
+        for k in range(2):
+            xk, yk, ck = (t.cuda() for t in synthetic.chunk_of(fs, 8000, 500, wav, conds, k))
+            parts.append(half(xk, yk, ck, info, ones if k == 0 else torch.zeros(b, dtype=torch.int64))[0][:, :, 0])
+        lp_c = torch.cat(parts, dim=1)
+        d = float((lp_c - lp).abs().max())
+        report(f'full-size config 2 (64 x 16000): permutation equivariance bit-exact; chunked (2 x L=500) vs unchunked max|dlogp| {d:.3e}')
+        assert d <= 1e-5, d
