@@ -259,13 +259,15 @@ def recurrence_report(events, steps_timed, step_ms, b, hidden, lstm, peak_gbs):
         if not tag.startswith('rnn_'):
             continue
         kind, t = tag[4:7], int(tag.split('_T')[1])
+        f32 = '_f32_' in tag                                   # --precision fp32: one split-operand GEMM + one cell kernel per timestep
         ms = [a.elapsed_time(b_) for a, b_ in evs]
         per_step_ms = sum(ms) / steps_timed                    # all launches of this kind in one training step
         groups = max(1, round(len(ms) / steps_timed))          # slot groups (batch > 64) run one after the other
         rows = min(b, 64 * groups) if groups > 1 else b
-        bytes_launch = per[kind] * (b / groups) * t
+        bytes_launch = per[kind] * (b / groups) * t * (2 if f32 else 1)
         avg = sum(ms) / len(ms)
-        out.append(dict(kernel=f'gru_kernel<{kind}> T={t}' + (' (LSTM)' if lstm else ''), launches_per_step=groups,
+        name = f'gru_f32 host loop <{kind}> T={t}' if f32 else f'gru_kernel<{kind}> T={t}' + (' (LSTM)' if lstm else '')
+        out.append(dict(kernel=name, launches_per_step=groups,
                         avg_launch_ms=avg, us_per_timestep=1e3 * avg / t, ms_per_step=per_step_ms,
                         share_of_step=per_step_ms / step_ms, algorithmic_bytes_per_launch=bytes_launch,
                         achieved_gbs=bytes_launch / (avg * 1e-3) / 1e9, frac_of_hbm_peak=bytes_launch / (avg * 1e-3) / 1e9 / peak_gbs))
@@ -288,7 +290,7 @@ def run_gpu(args):
         dist.init_process_group('nccl', device_id=dev)
 
     torch.manual_seed(1234)
-    model = SampleRNNModel(fused_loss=True, **model_kwargs()).to(dev)
+    model = SampleRNNModel(fused_loss=True, precision=args.precision, **model_kwargs()).to(dev)
     trainer = DataParallelTrainer(model, lr=1e-4)
     fs = int(model.frame_size)
     rf = int(model.receptive_field)
@@ -429,11 +431,16 @@ def run_gpu(args):
         line = dict(
             metric=METRIC, value=total / (ms * 1e-3), unit='samples/s', n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=step_ms, higher_is_better=True, scaling=scaling_kind(args), vs_baseline=None,
-            dtype='bf16', data='synthetic',
+            dtype='bf16' if args.precision == 'bf16' else 'f32',
+            data='synthetic',
             config=config_dict(world, b),
             run=dict(samples_per_step_per_gpu=b * rf, parallelism=f'dp{world}', global_batch=b * world,
                      l2_policy='inputs and activations per step (>10 GB) exceed the 126 MB L2; no flush needed',
-                     loss_mode='fused log-softmax+NLL epilogue', final_loss=loss,
+                     loss_mode='fused log-softmax+NLL epilogue' if args.precision == 'bf16' else 'fp32 log-softmax rows',
+                     arithmetic='bf16 operands, fp32 accumulation' if args.precision == 'bf16' else
+                     'fp32-tolerance mode: fp32 activations, split-bf16 (hi+lo) operands into the tcgen05 GEMM (3x K), '
+                     'recurrence as one GEMM + one cell kernel per timestep; NOT the headline configuration',
+                     final_loss=loss,
                      model_train_mflop_per_sample=3 * f_fwd / 1e6,
                      model_tflops_achieved=3 * f_fwd * total / (ms * 1e-3) / 1e12,
                      model_tflops_frac_of_sustained_peak=3 * f_fwd * total / (ms * 1e-3) / 1e12 / peak_tf / world,
@@ -521,6 +528,8 @@ def main():
     ap.add_argument('--global-batch', type=int, default=0,
                     help='fix the GLOBAL number of slots (strong scaling: slots per GPU = global / N) instead of the '
                          'per-GPU slot count of the workload')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
+                    help="fp32: the fp32-tolerance arithmetic mode (validation; ~4x slower; GRU workloads only)")
     ap.add_argument('--no-eager', action='store_true', help='skip the informational GPU-eager leg')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg (profiling runs)')
     args = ap.parse_args()

@@ -29,7 +29,7 @@ extern "C" {
 #define SRNN_ERR_ARG (-1)     /* bad argument (shape, alignment, null pointer) */
 #define SRNN_ERR_DEVICE (-2)  /* not an sm_100 device / driver entry point missing */
 
-#define SRNN_ABI_VERSION 5
+#define SRNN_ABI_VERSION 6
 
 typedef void* srnn_stream_t; /* cudaStream_t */
 
@@ -311,6 +311,74 @@ int srnn_sample_embed(const float* in, int64_t ld, int32_t batch, int32_t q, int
                       int64_t ld_out, const float* u, uint64_t* rng_state, uint8_t* win, int32_t win_len, uint8_t* out,
                       int64_t out_ld, const void* table_bf16, int32_t r0, int32_t hidden, const void* pre_next_bf16,
                       int64_t pre_ld, void* h1_next_bf16, int64_t h1_ld, srnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * fp32-tolerance arithmetic mode (SampleRNNModel(precision='fp32')).  The reference computes in fp32 end to end
+ * (model.py:146-155,192-203; no autocast); this mode reproduces its results to fp32-level tolerances (loss
+ * rel <= 1e-5, per-tensor gradient rel-L2 <= 3e-3) while still contracting on the tcgen05 GEMM: every activation and
+ * gradient is an fp32 tensor, and a product enters srnn_gemm_bf16 on SPLIT operands - x = hi + lo with hi = bf16(x),
+ * lo = bf16(x - hi) - as a.w ~= a_hi.w_hi + a_lo.w_hi + a_hi.w_lo, ONE bf16 GEMM with a 3x longer K.  The entries
+ * below are what the mode needs besides the GEMM.  It is ~4x slower than the bf16 path.
+ * ------------------------------------------------------------------------------------------- */
+/* fp32 (rows, cols) -> bf16 (rows, n_seg * cols_pad), every segment zero padded to cols_pad columns:
+ * role 0: [hi | lo | hi] (first operand of a product), role 1: [hi | hi | lo] (second operand), role 2: [hi | lo]
+ * (against an operand that is exact in bf16, e.g. one-hot rows).  A TN product uses the three column segments of both
+ * operands in three accumulating calls. */
+int srnn_split3_bf16(const float* in, int64_t rows, int32_t cols, int64_t ld_in, void* out_bf16, int32_t cols_pad,
+                     int64_t ld_out, int32_t role, srnn_stream_t stream);
+/* fp32-output variants of srnn_mixer_input / srnn_tier_input / srnn_weight_prep and fp32-input variants of their
+ * adjoints (same argument meaning; leading dimensions in elements) */
+int srnn_mixer_input_f32(const float* utt, const float* spk_table, const int32_t* spk_ids, int32_t batch, int32_t frames,
+                         int32_t U, int32_t S, float* out, int32_t k_pad, srnn_stream_t stream);
+int srnn_mixer_input_bwd_f32(const float* d_in, const int32_t* spk_ids, int32_t batch, int32_t frames, int32_t S,
+                             int32_t k_pad, float* d_table, srnn_stream_t stream);
+int srnn_tier_input_f32(const uint8_t* xq, int64_t xq_ld, int32_t x_off, const float* lut, const float* frames,
+                        const float* conds, int32_t batch, int32_t T, int32_t fs, int32_t L, int32_t C, float* out,
+                        int32_t k_pad, srnn_stream_t stream);
+int srnn_tier_input_bwd_f32(const float* d_in, int32_t batch, int32_t T, int32_t fs, int32_t L, int32_t C, int64_t ld,
+                            float* dconds, srnn_stream_t stream);
+int srnn_weight_prep_f32(const float* v, const float* g, int32_t R, int32_t A, int32_t B, float* out1, const int64_t* s1,
+                         float* out2, const int64_t* s2, float* inv_norm, srnn_stream_t stream);
+/* in place: x[r, c] = act(x[r, c] + aux[r / aux_row_div, c] + aux2[r, c]) (aux, aux2 nullable; relu != 0: max(., 0));
+ * mask (nullable) receives bit (r, c) = result > 0 in the word layout of srnn_gemm_args.relu_mask */
+int srnn_bias_act_f32(float* x, int64_t rows, int32_t cols, int64_t ld, const float* aux, int64_t ldaux,
+                      int32_t aux_row_div, const float* aux2, int64_t ldaux2, int32_t relu, uint32_t* mask,
+                      int64_t ldmask, srnn_stream_t stream);
+/* d_in[r, :] = sum_{i < rep} d_out[r * rep + i, :]  (adjoint of the row repeat, model.py:189-191) */
+int srnn_segment_sum_f32(const float* d_out, int64_t rows, int32_t cols, int64_t ld_dout, int32_t rep, float* d_in,
+                         int64_t ld_din, srnn_stream_t stream);
+int srnn_colsum_f32(const float* in, int64_t rows, int32_t cols, int64_t ld, float* out, srnn_stream_t stream);
+/* log_softmax (model.py:203) in place over rows of q <= 256 fp32 logits + the target pick of nll_loss (runner.py:52):
+ * lse[m] and logp_target[m] (nullable) are written */
+int srnn_logsoftmax_nll_f32(float* logits_inout, int64_t ld, int64_t m, int32_t q, const uint8_t* target, float* lse,
+                            float* logp_target, srnn_stream_t stream);
+/* its backward from the saved log-probabilities: g == NULL: dlogits = row_grad[m] * (onehot(target) - softmax);
+ * else dlogits = g - softmax * sum_n g */
+int srnn_logsoftmax_nll_bwd_f32(const float* logp, int64_t ld, int64_t m, int32_t q, const uint8_t* target,
+                                const float* row_grad, const float* g, int64_t ldg, float* dlogits, int64_t lddlogits,
+                                srnn_stream_t stream);
+/* torch.nn.GRU (model.py:110,152) in the fp32 mode: a host loop over the timesteps, each one split-operand GEMM
+ * (h_{t-1} . W_hh^T, resp. dgh_t . W_hh) and one fp32 cell kernel; batch-major fp32 buffers throughout. */
+typedef struct srnn_gru_f32_args {
+  int32_t batch, steps, hidden;  /* hidden % 8 == 0 */
+  const float* gi;       /* fwd: [batch*steps, 3H] = W_ih x_t + b_ih, row (b,t) = b*steps + t */
+  const void* w3;        /* fwd: srnn_split3_bf16 role 1 of W_hh [3H, H] -> bf16 [3H, 3H]; bwd: role 1 of W_hh^T [H, 3H]
+                            -> bf16 [H, 9H] */
+  const float* b_hh;     /* fwd: [3H] */
+  float* h_state;        /* fwd: [batch, H] in = h_init, out = h_T */
+  float* hall;           /* [batch*steps, H]: fwd out, bwd in */
+  const float* h_init;   /* bwd: [batch, H] the state the forward started from */
+  float* gates;          /* [batch*steps, 4H]: r, z, n, W_hn h + b_hn; fwd out, bwd in */
+  void* a3;              /* workspace, bf16: fwd [batch, 3H], bwd [batch, 9H] */
+  float* ws;             /* workspace: fwd [batch, 3H], bwd [batch, H] */
+  const float* dh_out;   /* bwd: [batch*steps, H] */
+  float* dgi;            /* bwd out: [batch*steps, 3H] */
+  float* dgh;            /* bwd out: [batch*steps, 3H] (batch-major, unlike the bf16 kernels) */
+  float* dh0;            /* bwd out: [batch, H] */
+  float* carry;          /* bwd workspace: [batch, H] */
+} srnn_gru_f32_args;
+int srnn_gru_forward_f32(const srnn_gru_f32_args* args, srnn_stream_t stream);
+int srnn_gru_backward_f32(const srnn_gru_f32_args* args, srnn_stream_t stream);
 
 #ifdef __cplusplus
 }

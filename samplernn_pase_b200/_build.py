@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libsrnn_b200.so')
 STAMP = os.path.join(HERE, '.libsrnn_b200.stamp')
-SOURCES = ['core.cu', 'gemm.cu', 'gru.cu', 'elementwise.cu', 'generate.cu']
+SOURCES = ['core.cu', 'gemm.cu', 'gru.cu', 'elementwise.cu', 'generate.cu', 'precise.cu']
 FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-Xcompiler', '-fPIC',
          '--cudart', 'shared'] + os.environ.get('SRNN_NVCC_EXTRA', '').split()
 

@@ -56,6 +56,15 @@ class GruArgs(C.Structure):
     ]
 
 
+class GruF32Args(C.Structure):
+    _fields_ = [
+        ('batch', C.c_int32), ('steps', C.c_int32), ('hidden', C.c_int32),
+        ('gi', C.c_void_p), ('w3', C.c_void_p), ('b_hh', C.c_void_p), ('h_state', C.c_void_p), ('hall', C.c_void_p),
+        ('h_init', C.c_void_p), ('gates', C.c_void_p), ('a3', C.c_void_p), ('ws', C.c_void_p),
+        ('dh_out', C.c_void_p), ('dgi', C.c_void_p), ('dgh', C.c_void_p), ('dh0', C.c_void_p), ('carry', C.c_void_p),
+    ]
+
+
 P, I32, I64, F64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 
 # name -> argument ctypes (every function returns int unless noted); must mirror include/srnn_b200.h
@@ -91,6 +100,20 @@ SIGNATURES = {
     'srnn_state_select_bwd': [P, P, I32, I32, P, P],
     'srnn_masked_nll_mean': [P, P, I64, I32, P, P],
     'srnn_adam_clipped': [P, P, P, P, I64, F64, F64, F64, F64, I32, F64, P],
+    # fp32-tolerance mode (csrc/precise.cu)
+    'srnn_split3_bf16': [P, I64, I32, I64, P, I32, I64, I32, P],
+    'srnn_mixer_input_f32': [P, P, P, I32, I32, I32, I32, P, I32, P],
+    'srnn_mixer_input_bwd_f32': [P, P, I32, I32, I32, I32, P, P],
+    'srnn_tier_input_f32': [P, I64, I32, P, P, P, I32, I32, I32, I32, I32, P, I32, P],
+    'srnn_tier_input_bwd_f32': [P, I32, I32, I32, I32, I32, I64, P, P],
+    'srnn_weight_prep_f32': [P, P, I32, I32, I32, P, P, P, P, P, P],
+    'srnn_bias_act_f32': [P, I64, I32, I64, P, I64, I32, P, I64, I32, P, I64, P],
+    'srnn_segment_sum_f32': [P, I64, I32, I64, I32, P, I64, P],
+    'srnn_colsum_f32': [P, I64, I32, I64, P, P],
+    'srnn_logsoftmax_nll_f32': [P, I64, I64, I32, P, P, P, P],
+    'srnn_logsoftmax_nll_bwd_f32': [P, I64, I64, I32, P, P, P, I64, P, I64, P],
+    'srnn_gru_forward_f32': [C.POINTER(GruF32Args), P],
+    'srnn_gru_backward_f32': [C.POINTER(GruF32Args), P],
 }
 
 EXPORTS = sorted(list(SIGNATURES) + ['srnn_last_error'])
@@ -113,7 +136,7 @@ def load(path=None):
         fn.restype = C.c_int
     lib.srnn_last_error.argtypes = []
     lib.srnn_last_error.restype = C.c_char_p
-    if lib.srnn_abi_version() != 5:
+    if lib.srnn_abi_version() != 6:
         raise RuntimeError('libsrnn_b200.so ABI version mismatch')
     _lib = lib
     return lib

@@ -6,7 +6,9 @@ Same class names, constructor arguments, attributes, ``forward``/``test`` signat
 all arithmetic runs in the sm_100a kernels of ``csrc/`` through ``functional.py``.
 
 Differences a caller can observe (all documented in DESIGN.md):
-  * arithmetic is bf16 x bf16 -> fp32 (tensor cores) instead of fp32;
+  * arithmetic is bf16 x bf16 -> fp32 (tensor cores) instead of fp32; ``precision='fp32'`` selects the fp32-tolerance
+    mode of ``functional_f32.py`` (split-bf16 operands, fp32 activations; ~4x slower, GRU tiers only, training
+    forward/backward only - generation always runs in bf16);
   * hidden-state carry-over works by default (the reference's ``hasattr(self, 'rnnstates')``
     typo, model.py:256, disables it); ``reference_as_written=True`` reproduces the typo;
   * ``fused_loss=True`` makes ``forward`` return ``(log p(target) as (B_valid, RF, 1), zeros)`` so
@@ -20,6 +22,7 @@ import torch
 
 from . import ops
 from .functional import CondsMixFn, FrameTierFn, SampleLevelFn, StateSelectFn
+from .functional_f32 import CondsMixFn32, FrameTierFn32, SampleLevelFn32
 from .utils import SampleRNNQuantizer
 
 
@@ -110,8 +113,8 @@ class CondsMixer(torch.nn.Module):
         else:
             table = self.speaker_embedding.weight
             ids = self.speaker_ids(info, utt_conds.device)
-        return CondsMixFn.apply(self._expand_linguistic(utt_conds), ids, table, self.conds_mix.weight,
-                                self.conds_mix.bias)
+        fn = CondsMixFn32 if getattr(self, 'precision', 'bf16') == 'fp32' else CondsMixFn
+        return fn.apply(self._expand_linguistic(utt_conds), ids, table, self.conds_mix.weight, self.conds_mix.bias)
 
 
 class _RnnParams(torch.nn.Module):
@@ -162,7 +165,8 @@ class FrameLevelLayer(torch.nn.Module):
 
     def _tier(self, xq_u8, x_off, lut, frames, conds, upper, h_init, into_cat=False, c_init=None):
         """-> (upsampled, h_n, c_n); c_n is an empty tensor for GRU tiers."""
-        return FrameTierFn.apply(
+        fn = FrameTierFn32 if getattr(self, 'precision', 'bf16') == 'fp32' else FrameTierFn
+        return fn.apply(
             xq_u8, x_off, lut, frames, conds, upper, h_init, self.input_samples, self.ratio, into_cat, c_init,
             self.x_expand.weight_g, self.x_expand.weight_v, self.x_expand.bias,
             self.conds_expand.weight_g, self.conds_expand.weight_v, self.conds_expand.bias,
@@ -192,7 +196,8 @@ class FrameLevelLayer(torch.nn.Module):
 
         h_init = self.initial_state(dense((lambda s: s[0]) if lstm else (lambda s: s)), use)
         c_init = self.initial_cell(dense(lambda s: s[1]), use) if lstm else None
-        upper = upper_conditioning.to(torch.bfloat16) if upper_conditioning is not None else None
+        act = torch.float32 if getattr(self, 'precision', 'bf16') == 'fp32' else torch.bfloat16
+        upper = upper_conditioning.to(act) if upper_conditioning is not None else None
         up, hn, cn = self._tier(None, 0, None, x.float(), conds.float(), upper, h_init, c_init=c_init)
         return up.float(), ((hn, cn) if lstm else hn)
 
@@ -218,7 +223,8 @@ class SampleLevelLayer(torch.nn.Module):
         self.adapt = _normed(_lecun_uniform_(torch.empty(q, h, 1)), torch.zeros(q))          # model.py:180-181
 
     def _run(self, xs_u8, conds, upper, target_u8, fused):
-        return SampleLevelFn.apply(
+        fn = SampleLevelFn32 if getattr(self, 'precision', 'bf16') == 'fp32' else SampleLevelFn
+        return fn.apply(
             xs_u8, conds, upper, target_u8, fused, self.emb_layer.weight,
             self.emb_layer_expand.weight_g, self.emb_layer_expand.weight_v,
             self.conds_expand.weight, self.conds_expand.bias, self.comb_layer.weight, self.comb_layer.bias,
@@ -227,8 +233,8 @@ class SampleLevelLayer(torch.nn.Module):
 
     def forward(self, x, conds, upper_tier_conditioning):
         """Reference calling convention: ``x`` (B, RF+r0-1) int64 indices -> (B,RF,Q) log-probs."""
-        return self._run(x.to(torch.uint8).contiguous(), conds.float(),
-                         upper_tier_conditioning.to(torch.bfloat16), None, False)
+        act = torch.float32 if getattr(self, 'precision', 'bf16') == 'fp32' else torch.bfloat16
+        return self._run(x.to(torch.uint8).contiguous(), conds.float(), upper_tier_conditioning.to(act), None, False)
 
 
 class SampleRNNModel(torch.nn.Module):
@@ -237,8 +243,12 @@ class SampleRNNModel(torch.nn.Module):
     def __init__(self, conds_speaker_type, conds_speaker_n, conds_speaker_size, conds_utterance_type,
                  conds_utterance_linguistic_n, conds_utterance_linguistic_emb_size, conds_size, sequence_length, ratios,
                  rnn_layers, rnn_hidden_size, q_type_ulaw, q_levels, fused_loss=False, reference_as_written=False,
-                 rnn_cell='gru'):
+                 rnn_cell='gru', precision='bf16'):
         super().__init__()
+        if precision not in ('bf16', 'fp32'):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if precision == 'fp32' and rnn_cell != 'gru':
+            raise ValueError("precision='fp32' supports GRU tiers only (the reference's cell)")
         self.frame_size = np.prod(ratios)
         self.receptive_field = np.prod(ratios) * sequence_length
         self.quantizer = SampleRNNQuantizer(q_type_ulaw, q_levels)
@@ -252,7 +262,14 @@ class SampleRNNModel(torch.nn.Module):
             self.frames_layers.append(FrameLevelLayer(fs, conds_size, ratios[n], rnn_layers[n], rnn_hidden_size[n],
                                                       rnn_cell))
         self.sample_layer = SampleLevelLayer(ratios[0], conds_size, rnn_hidden_size[0], self.quantizer.q_levels)
+        self.set_precision(precision)
         self._init_rnn_states(0)
+
+    def set_precision(self, precision):
+        """'bf16' (default: bf16 operands, fp32 accumulation) or 'fp32' (fp32-tolerance mode, functional_f32.py)."""
+        self.precision = precision
+        for mod in [self.conds_mixer, self.sample_layer, *self.frames_layers]:
+            mod.precision = precision
 
     # ---- hidden-state store (model.py:236-250), dense: one (layers,B,H) tensor + validity per tier ----
     def _init_rnn_states(self, batch_size):

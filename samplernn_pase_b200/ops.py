@@ -433,3 +433,193 @@ def adam_clipped(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, 
     call('srnn_adam_clipped', ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), float(lr),
          float(beta1), float(beta2), float(eps), int(step), float(grad_scale), stream())
     _count()
+
+
+# ----------------------------------------------------------------------------------------------
+# fp32-tolerance mode (csrc/precise.cu): fp32 tensors everywhere, split-bf16 operands into the tcgen05 GEMM
+# ----------------------------------------------------------------------------------------------
+def _mat(x, name):
+    """2-D fp32 CUDA view with unit column stride -> (tensor, rows, cols, ld)."""
+    _need(x, F32, name)
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise RuntimeError(f'{name}: expected a 2-D matrix with unit column stride, got {tuple(x.shape)} / {x.stride()}')
+    return x, x.shape[0], x.shape[1], x.stride(0)
+
+
+def split3(x, role):
+    """fp32 (rows, cols) -> bf16 (rows, n_seg * cols_pad): role 0 [hi|lo|hi], 1 [hi|hi|lo], 2 [hi|lo]; cols_pad = cols
+    rounded up to 8.  Returns (tensor, cols_pad)."""
+    x, rows, cols, ld = _mat(x, 'split3 x')
+    kp = round_up(cols, 8)
+    seg = 2 if role == 2 else 3
+    out = torch.empty(rows, seg * kp, dtype=BF16, device=x.device)
+    call('srnn_split3_bf16', ptr(x), rows, cols, ld, ptr(out), kp, seg * kp, role, stream())
+    _count()
+    return out, kp
+
+
+def gemm_nt32(a, w, out=None, bias=None, gate_mask=None, colsum=None):
+    """out[m,n] = a[m,k] . w[n,k]^T (+ bias) at fp32-level accuracy: ONE bf16 GEMM over K' = 3k on split operands.
+    ``a``/``w``/``out`` are fp32 matrices (views with a row stride are fine)."""
+    a, m, k, _ = _mat(a, 'gemm_nt32 a')
+    w, n, k2, _ = _mat(w, 'gemm_nt32 w')
+    if k != k2:
+        raise RuntimeError(f'gemm_nt32: inner dimensions differ ({k} vs {k2})')
+    if out is None:
+        out = torch.empty(m, n, dtype=F32, device=a.device)
+    out, _, _, ldc = _mat(out, 'gemm_nt32 out')
+    a3, kp = split3(a, 0)
+    w3, _ = split3(w, 1)
+    gemm_nt(a3, w3, out, m, n, 3 * kp, 3 * kp, 3 * kp, ldc, bias=bias, gate_mask=gate_mask, colsum=colsum)
+    return out
+
+
+def gemm_tn32(a, b, out):
+    """out[m,n] += a[rows,m]^T . b[rows,n] at fp32-level accuracy (three accumulating TN GEMMs on the split segments)."""
+    a, rows, m, _ = _mat(a, 'gemm_tn32 a')
+    b, rows2, n, _ = _mat(b, 'gemm_tn32 b')
+    if rows != rows2:
+        raise RuntimeError(f'gemm_tn32: contraction lengths differ ({rows} vs {rows2})')
+    out, _, _, ldc = _mat(out, 'gemm_tn32 out')
+    a3, mp = split3(a, 0)
+    b3, np_ = split3(b, 1)
+    for i in range(3):
+        gemm_tn(a3[:, i * mp:], b3[:, i * np_:], out, m, n, rows, 3 * mp, 3 * np_, ldc)
+    return out
+
+
+def mixer_input_f32(utt, table, spk_ids, k_pad):
+    b, l, u = utt.shape
+    out = torch.empty(b * l, k_pad, dtype=F32, device=utt.device)
+    call('srnn_mixer_input_f32', ptr(utt), ptr(table), ptr(spk_ids), b, l, u, table.shape[1], ptr(out), k_pad, stream())
+    _count()
+    return out
+
+
+def mixer_input_bwd_f32(d_in, spk_ids, batch, frames, s, k_pad, d_table):
+    _need(d_in, F32, 'mixer_input_bwd_f32 d_in')
+    call('srnn_mixer_input_bwd_f32', ptr(d_in), ptr(spk_ids), batch, frames, s, k_pad, ptr(d_table), stream())
+    _count()
+
+
+def tier_input_f32(xq_u8, x_off, lut, frames, conds, batch, t, fs, k_pad):
+    l, c = conds.shape[1], conds.shape[2]
+    out = torch.empty(batch * t, k_pad, dtype=F32, device=conds.device)
+    call('srnn_tier_input_f32', ptr(xq_u8), xq_u8.shape[1] if xq_u8 is not None else 0, x_off, ptr(lut), ptr(frames),
+         ptr(conds), batch, t, fs, l, c, ptr(out), k_pad, stream())
+    _count()
+    return out
+
+
+def tier_input_bwd_f32(d_in, batch, t, fs, l, c, dconds):
+    d_in, _, _, ld = _mat(d_in, 'tier_input_bwd_f32 d_in')
+    call('srnn_tier_input_bwd_f32', ptr(d_in), batch, t, fs, l, c, ld, ptr(dconds), stream())
+    _count()
+
+
+def weight_prep_f32(v, g, shape3, out1, s1, out2=None, s2=None, inv_norm=None):
+    """``weight_prep`` with fp32 outputs."""
+    _need(v, F32, 'weight_prep_f32 v')
+    _need(out1, F32, 'weight_prep_f32 out1')
+    r, a, b = shape3
+    assert v.is_contiguous() and v.numel() == r * a * b
+    call('srnn_weight_prep_f32', ptr(v), ptr(g), r, a, b, ptr(out1), _strides(s1), ptr(out2),
+         _strides(s2) if s2 is not None else None, ptr(inv_norm), stream())
+    _count()
+
+
+def bias_act_f32(x, aux=None, aux_row_div=1, aux2=None, relu=False, mask=None):
+    """in place: x = act(x + aux[row // aux_row_div] + aux2); ``mask`` (int32 (rows, ceil(cols/32))) receives result > 0."""
+    x, rows, cols, ld = _mat(x, 'bias_act_f32 x')
+    ldaux = ldaux2 = 0
+    if aux is not None:
+        aux, _, _, ldaux = _mat(aux, 'bias_act_f32 aux')
+    if aux2 is not None:
+        aux2, _, _, ldaux2 = _mat(aux2, 'bias_act_f32 aux2')
+    if mask is not None:
+        _need(mask, torch.int32, 'bias_act_f32 mask')
+    call('srnn_bias_act_f32', ptr(x), rows, cols, ld, ptr(aux), ldaux, aux_row_div, ptr(aux2), ldaux2, int(relu),
+         ptr(mask), mask.shape[-1] if mask is not None else 0, stream())
+    _count()
+    return x
+
+
+def segment_sum_f32(dout, rep):
+    dout, rows_out, cols, ld = _mat(dout, 'segment_sum_f32 dout')
+    rows = rows_out // rep
+    din = torch.empty(rows, cols, dtype=F32, device=dout.device)
+    call('srnn_segment_sum_f32', ptr(dout), rows, cols, ld, rep, ptr(din), cols, stream())
+    _count()
+    return din
+
+
+def colsum_f32(x):
+    x, rows, cols, ld = _mat(x, 'colsum_f32 x')
+    out = torch.empty(cols, dtype=F32, device=x.device)
+    call('srnn_colsum_f32', ptr(x), rows, cols, ld, ptr(out), stream())
+    _count(2)
+    return out
+
+
+def logsoftmax_nll_f32(logits, target_u8):
+    """in place: logits -> log-probabilities; returns (lse, logp_target)."""
+    logits, m, q, ld = _mat(logits, 'logsoftmax_nll_f32 logits')
+    lse = torch.empty(m, dtype=F32, device=logits.device)
+    logp_t = torch.empty(m, dtype=F32, device=logits.device)
+    call('srnn_logsoftmax_nll_f32', ptr(logits), ld, m, q, ptr(target_u8), ptr(lse), ptr(logp_t), stream())
+    _count()
+    return lse, logp_t
+
+
+def logsoftmax_nll_bwd_f32(logp, target_u8, row_grad=None, g=None):
+    logp, m, q, ld = _mat(logp, 'logsoftmax_nll_bwd_f32 logp')
+    dl = torch.empty(m, q, dtype=F32, device=logp.device)
+    ldg = 0
+    if g is not None:
+        g, _, _, ldg = _mat(g, 'logsoftmax_nll_bwd_f32 g')
+    call('srnn_logsoftmax_nll_bwd_f32', ptr(logp), ld, m, q, ptr(target_u8), ptr(row_grad), ptr(g), ldg, ptr(dl), q,
+         stream())
+    _count()
+    return dl
+
+
+def gru_forward_f32(gi, w_hh, b_hh, h_state, batch, steps, hidden):
+    """gi fp32 [batch*steps, 3H]; w_hh fp32 [3H, H]; h_state fp32 [batch, H] (in: initial, out: final).
+    Returns (hall [batch*steps, H], gates [batch*steps, 4H])."""
+    h = hidden
+    dev = gi.device
+    w3, _ = split3(w_hh, 1)
+    a = _lib.GruF32Args()
+    a.batch, a.steps, a.hidden = batch, steps, h
+    hall = torch.empty(batch * steps, h, dtype=F32, device=dev)
+    gates = torch.empty(batch * steps, 4 * h, dtype=F32, device=dev)
+    a3 = torch.empty(batch, 3 * h, dtype=BF16, device=dev)
+    ws = torch.empty(batch, 3 * h, dtype=F32, device=dev)
+    a.gi, a.w3, a.b_hh, a.h_state = gi.data_ptr(), w3.data_ptr(), b_hh.data_ptr(), h_state.data_ptr()
+    a.hall, a.gates, a.a3, a.ws = hall.data_ptr(), gates.data_ptr(), a3.data_ptr(), ws.data_ptr()
+    with timed(f'rnn_fwd_f32_T{steps}'):
+        call('srnn_gru_forward_f32', C.byref(a), stream())
+    _count(1 + 2 * steps)
+    return hall, gates
+
+
+def gru_backward_f32(w_hh, gates, hall, h_init, dh_out, batch, steps, hidden):
+    """-> (dgi, dgh) fp32 [batch*steps, 3H] batch-major, dh0 fp32 [batch, H]."""
+    h = hidden
+    dev = gates.device
+    w3, _ = split3(w_hh.t().contiguous(), 1)                 # W_hh^T [H, 3H] -> bf16 [H, 9H]
+    a = _lib.GruF32Args()
+    a.batch, a.steps, a.hidden = batch, steps, h
+    dgi = torch.empty(batch * steps, 3 * h, dtype=F32, device=dev)
+    dgh = torch.empty(batch * steps, 3 * h, dtype=F32, device=dev)
+    dh0 = torch.empty(batch, h, dtype=F32, device=dev)
+    carry = torch.empty(batch, h, dtype=F32, device=dev)
+    a3 = torch.empty(batch, 9 * h, dtype=BF16, device=dev)
+    ws = torch.empty(batch, h, dtype=F32, device=dev)
+    a.w3, a.hall, a.h_init, a.gates = w3.data_ptr(), hall.data_ptr(), h_init.data_ptr(), gates.data_ptr()
+    a.a3, a.ws, a.dh_out, a.dgi, a.dgh = a3.data_ptr(), ws.data_ptr(), dh_out.data_ptr(), dgi.data_ptr(), dgh.data_ptr()
+    a.dh0, a.carry = dh0.data_ptr(), carry.data_ptr()
+    with timed(f'rnn_bwd_f32_T{steps}'):
+        call('srnn_gru_backward_f32', C.byref(a), stream())
+    _count(3 + 2 * steps)
+    return dgi, dgh, dh0
