@@ -320,10 +320,14 @@ int srnn_sample_embed(const float* in, int64_t ld, int32_t batch, int32_t q, int
  * lo = bf16(x - hi) - as a.w ~= a_hi.w_hi + a_lo.w_hi + a_hi.w_lo, ONE bf16 GEMM with a 3x longer K.  The entries
  * below are what the mode needs besides the GEMM.  It is ~4x slower than the bf16 path.
  * ------------------------------------------------------------------------------------------- */
-/* fp32 (rows, cols) -> bf16 (rows, n_seg * cols_pad), every segment zero padded to cols_pad columns:
- * role 0: [hi | lo | hi] (first operand of a product), role 1: [hi | hi | lo] (second operand), role 2: [hi | lo]
- * (against an operand that is exact in bf16, e.g. one-hot rows).  A TN product uses the three column segments of both
- * operands in three accumulating calls. */
+/* fp32 (rows, cols) -> bf16 (rows, n_seg * cols_pad), every segment zero padded to cols_pad columns.
+ * Two pieces (x ~ hi + lo to 2^-18; three products): role 0: [hi | lo | hi] (first operand of a product), role 1:
+ * [hi | hi | lo] (second operand), role 2: [hi | lo] (against an operand that is exact in bf16, e.g. one-hot rows).
+ * Three pieces (x = p0 + p1 + p2 to 2^-24, i.e. all of fp32; the six products down to order 2^-16): role 3:
+ * [p0 | p0 | p1 | p0 | p1 | p2] (first operand), role 4: [q0 | q1 | q0 | q2 | q1 | q0] (second operand).  The tensor core's
+ * fp32 accumulation truncates (~3e-8 relative per K=16 update, measured), so the six-product form only pays for short
+ * K (it reaches 4e-7 at K = 47 but 1e-5 at K = 1024, where the three-product form gives 7e-6); the model path uses
+ * roles 0-2.  A TN product uses the three column segments of roles 0 / 1 in three accumulating calls. */
 int srnn_split3_bf16(const float* in, int64_t rows, int32_t cols, int64_t ld_in, void* out_bf16, int32_t cols_pad,
                      int64_t ld_out, int32_t role, srnn_stream_t stream);
 /* fp32-output variants of srnn_mixer_input / srnn_tier_input / srnn_weight_prep and fp32-input variants of their
@@ -339,6 +343,10 @@ int srnn_tier_input_bwd_f32(const float* d_in, int32_t batch, int32_t T, int32_t
                             float* dconds, srnn_stream_t stream);
 int srnn_weight_prep_f32(const float* v, const float* g, int32_t R, int32_t A, int32_t B, float* out1, const int64_t* s1,
                          float* out2, const int64_t* s2, float* inv_norm, srnn_stream_t stream);
+/* out[(b, j), :] = sum_{k < r0} table[k*q + idx[b*idx_ld + j + k], :]: embedding + conv1d + the embedding block of
+ * comb_layer (model.py:192-200) as a gather-sum over the folded fp32 table (r0*q, hidden) - no rounding beyond fp32 adds */
+int srnn_embed_gather_f32(const float* table, const uint8_t* idx, int64_t idx_ld, int32_t batch, int32_t rows_per_slot,
+                          int32_t r0, int32_t q, int32_t hidden, float* out, srnn_stream_t stream);
 /* in place: x[r, c] = act(x[r, c] + aux[r / aux_row_div, c] + aux2[r, c]) (aux, aux2 nullable; relu != 0: max(., 0));
  * mask (nullable) receives bit (r, c) = result > 0 in the word layout of srnn_gemm_args.relu_mask */
 int srnn_bias_act_f32(float* x, int64_t rows, int32_t cols, int64_t ld, const float* aux, int64_t ldaux,

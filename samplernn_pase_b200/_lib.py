@@ -108,6 +108,7 @@ SIGNATURES = {
     'srnn_tier_input_bwd_f32': [P, I32, I32, I32, I32, I32, I64, P, P],
     'srnn_weight_prep_f32': [P, P, I32, I32, I32, P, P, P, P, P, P],
     'srnn_bias_act_f32': [P, I64, I32, I64, P, I64, I32, P, I64, I32, P, I64, P],
+    'srnn_embed_gather_f32': [P, P, I64, I32, I32, I32, I32, I32, P, P],
     'srnn_segment_sum_f32': [P, I64, I32, I64, I32, P, I64, P],
     'srnn_colsum_f32': [P, I64, I32, I64, P, P],
     'srnn_logsoftmax_nll_f32': [P, I64, I64, I32, P, P, P, P],

@@ -13,8 +13,11 @@ namespace srnn {
 
 static inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
 
-// role 0: [hi | lo | hi]   (the "A" side of a product)      role 1: [hi | hi | lo]   (the "B" side)
-// role 2: [hi | lo]        (against an operand that is exact in bf16, e.g. one-hot rows)
+// Two-piece roles (x ~ hi + lo, 2^-18 relative; products a_hi.w_hi + a_lo.w_hi + a_hi.w_lo):
+//   role 0: [hi | lo | hi]   (the "A" side of a product)      role 1: [hi | hi | lo]   (the "B" side)
+//   role 2: [hi | lo]        (against an operand that is exact in bf16, e.g. one-hot rows)
+// Three-piece roles (x = p0 + p1 + p2 to 2^-24: fp32 exactly; the six products of order <= 2^-16):
+//   role 3: [p0 | p0 | p1 | p0 | p1 | p2]   (A side)          role 4: [q0 | q1 | q0 | q2 | q1 | q0]   (B side)
 __global__ void split3_kernel(const float* __restrict__ in, long long rows, int cols, long long ld_in,
                               __nv_bfloat16* __restrict__ out, int cols_pad, long long ld_out, int role) {
   const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -23,7 +26,8 @@ __global__ void split3_kernel(const float* __restrict__ in, long long rows, int 
   const int c = static_cast<int>(g - r * cols_pad);
   const float x = c < cols ? in[r * ld_in + c] : 0.f;
   const __nv_bfloat16 h = __float2bfloat16_rn(x);
-  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  const float r1 = x - __bfloat162float(h);
+  const __nv_bfloat16 l = __float2bfloat16_rn(r1);
   __nv_bfloat16* o = out + r * ld_out + c;
   o[0] = h;
   if (role == 0) {
@@ -32,9 +36,36 @@ __global__ void split3_kernel(const float* __restrict__ in, long long rows, int 
   } else if (role == 1) {
     o[cols_pad] = h;
     o[2 * cols_pad] = l;
-  } else {
+  } else if (role == 2) {
     o[cols_pad] = l;
+  } else {
+    const __nv_bfloat16 t = __float2bfloat16_rn(r1 - __bfloat162float(l));
+    if (role == 3) {
+      o[cols_pad] = h; o[2 * cols_pad] = l; o[3 * cols_pad] = h; o[4 * cols_pad] = l; o[5 * cols_pad] = t;
+    } else {
+      o[cols_pad] = l; o[2 * cols_pad] = h; o[3 * cols_pad] = t; o[4 * cols_pad] = l; o[5 * cols_pad] = h;
+    }
   }
+}
+
+// out[(b, j), :] = sum_{k < r0} table[k * q + idx[b * idx_ld + j + k], :]   (fp32 rows; the embedding + conv1d + comb_layer
+// embedding block as a gather-sum of the folded table, model.py:192-200 - exact in fp32, no product involved)
+__global__ void embed_gather_f32_kernel(const float* __restrict__ table, const uint8_t* __restrict__ idx, long long idx_ld,
+                                        int batch, int rows_per_slot, int r0, int q, int H, float* __restrict__ out) {
+  const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int per_row = H / 4;
+  const long long row = g / per_row;
+  if (row >= static_cast<long long>(batch) * rows_per_slot) return;
+  const int seg = static_cast<int>(g - row * per_row);
+  const int b = static_cast<int>(row / rows_per_slot);
+  const int j = static_cast<int>(row - static_cast<long long>(b) * rows_per_slot);
+  const uint8_t* win = idx + b * idx_ld + j;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < r0; ++k) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(table + (static_cast<long long>(k) * q + win[k]) * H) + seg);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  reinterpret_cast<float4*>(out + row * H)[seg] = acc;
 }
 
 // conditioning mixer operand (model.py:60-72), fp32
@@ -241,7 +272,7 @@ __global__ void logsoftmax_nll_bwd_f32_kernel(const float* __restrict__ logp, lo
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
 
-__device__ __forceinline__ void store_split(__nv_bfloat16* o, int kp, float x) {
+__device__ __forceinline__ void store_split(__nv_bfloat16* o, int kp, float x) {   // role 0
   const __nv_bfloat16 h = __float2bfloat16_rn(x);
   o[0] = h;
   o[kp] = __float2bfloat16_rn(x - __bfloat162float(h));
@@ -327,9 +358,10 @@ using namespace srnn;
 
 extern "C" int srnn_split3_bf16(const float* in, int64_t rows, int32_t cols, int64_t ld_in, void* out, int32_t cols_pad,
                                 int64_t ld_out, int32_t role, srnn_stream_t s) {
-  SRNN_CHECK_ARG(in && out && rows > 0 && cols > 0 && cols_pad >= cols && cols_pad % 8 == 0 && role >= 0 && role <= 2,
-                 "split3_bf16: cols_pad must be a multiple of 8 and >= cols, role in 0..2");
-  SRNN_CHECK_ARG(ld_out >= (role == 2 ? 2 : 3) * static_cast<int64_t>(cols_pad), "split3_bf16: ld_out too small");
+  SRNN_CHECK_ARG(in && out && rows > 0 && cols > 0 && cols_pad >= cols && cols_pad % 8 == 0 && role >= 0 && role <= 4,
+                 "split3_bf16: cols_pad must be a multiple of 8 and >= cols, role in 0..4");
+  SRNN_CHECK_ARG(ld_out >= (role == 2 ? 2 : role >= 3 ? 6 : 3) * static_cast<int64_t>(cols_pad),
+                 "split3_bf16: ld_out too small");
   split3_kernel<<<blocks_for(rows * cols_pad, 256), 256, 0, ST(s)>>>(in, rows, cols, ld_in,
                                                                      static_cast<__nv_bfloat16*>(out), cols_pad, ld_out, role);
   SRNN_CUDA(cudaGetLastError());
@@ -438,13 +470,24 @@ extern "C" int srnn_logsoftmax_nll_bwd_f32(const float* logp, int64_t ld, int64_
   return SRNN_OK;
 }
 
-// one recurrent product of the fp32 mode: C[batch, n] = A3[batch, 3 kp] . W3[n, 3 kp]^T on the tcgen05 GEMM
-static int split_gemm(const void* a3, const void* w3, float* c, int batch, int n, int kp, srnn_stream_t s) {
+extern "C" int srnn_embed_gather_f32(const float* table, const uint8_t* idx, int64_t idx_ld, int32_t batch,
+                                     int32_t rows_per_slot, int32_t r0, int32_t q, int32_t hidden, float* out,
+                                     srnn_stream_t s) {
+  SRNN_CHECK_ARG(table && idx && out && batch > 0 && rows_per_slot > 0 && r0 > 0 && q > 0 && hidden % 4 == 0,
+                 "embed_gather_f32: hidden must be a multiple of 4");
+  embed_gather_f32_kernel<<<blocks_for(static_cast<long long>(batch) * rows_per_slot * (hidden / 4), 256), 256, 0, ST(s)>>>(
+      table, idx, idx_ld, batch, rows_per_slot, r0, q, hidden, out);
+  SRNN_CUDA(cudaGetLastError());
+  return SRNN_OK;
+}
+
+// one recurrent product of the fp32 mode: C[batch, n] = A[batch, segs kp] . W[n, segs kp]^T on the tcgen05 GEMM
+static int split_gemm(const void* a3, const void* w3, float* c, int batch, int n, int kp, int segs, srnn_stream_t s) {
   srnn_gemm_args g{};
   g.op = 0;
-  g.m = batch; g.n = n; g.k = 3 * kp; g.batch = 1;
-  g.a = a3; g.lda = 3 * kp;
-  g.b = w3; g.ldb = 3 * kp;
+  g.m = batch; g.n = n; g.k = segs * kp; g.batch = 1;
+  g.a = a3; g.lda = segs * kp;
+  g.b = w3; g.ldb = segs * kp;
   g.c = c; g.ldc = n; g.c_dtype = 1;
   g.aux_row_div = 1;
   return srnn_gemm_bf16(&g, s);
@@ -459,7 +502,7 @@ extern "C" int srnn_gru_forward_f32(const srnn_gru_f32_args* a, srnn_stream_t s)
       a->h_state, B, H, kp, static_cast<__nv_bfloat16*>(a->a3));
   SRNN_CUDA(cudaGetLastError());
   for (int t = 0; t < T; ++t) {
-    const int rc = split_gemm(a->a3, a->w3, a->ws, B, 3 * H, kp, s);
+    const int rc = split_gemm(a->a3, a->w3, a->ws, B, 3 * H, kp, 3, s);
     if (rc) return rc;
     gru_f32_cell_kernel<<<blocks_for(static_cast<long long>(B) * H, 256), 256, 0, ST(s)>>>(
         a->gi, a->ws, a->b_hh, a->h_state, a->hall, a->gates, B, T, t, H, kp, static_cast<__nv_bfloat16*>(a->a3));
@@ -481,7 +524,7 @@ extern "C" int srnn_gru_backward_f32(const srnn_gru_f32_args* a, srnn_stream_t s
         a->gates, a->hall, a->h_init, a->dh_out, a->carry, a->ws, a->dgi, a->dgh, B, T, t, H, kp,
         static_cast<__nv_bfloat16*>(a->a3));
     SRNN_CUDA(cudaGetLastError());
-    const int rc = split_gemm(a->a3, a->w3, a->ws, B, H, kp, s);     // rec[b, i] = sum_j dgh[b, j] W_hh[j, i]
+    const int rc = split_gemm(a->a3, a->w3, a->ws, B, H, kp, 3, s);  // rec[b, i] = sum_j dgh[b, j] W_hh[j, i]
     if (rc) return rc;
   }
   add2_f32_kernel<<<blocks_for(static_cast<long long>(B) * H, 256), 256, 0, ST(s)>>>(a->carry, a->ws, a->dh0, B * H);

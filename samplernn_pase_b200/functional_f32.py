@@ -3,9 +3,13 @@ three modules as ``functional.py`` (folded embedding table, conditioning hoisted
 passes; model.py:28-203), but every activation, gate and gradient is an fp32 tensor and every contraction enters the
 tcgen05 GEMM on split-bf16 operands (``ops.gemm_nt32`` / ``ops.gemm_tn32``: a.w ~= a_hi.w_hi + a_lo.w_hi + a_hi.w_lo in
 one GEMM with a 3x longer K, fp32 accumulation), so the results agree with the reference's fp32 arithmetic to fp32-level
-tolerances (loss rel <= 1e-5, per-tensor gradient rel-L2 <= 3e-3).  The recurrence runs as one split-operand
-GEMM and one fp32 cell kernel per timestep (``srnn_gru_forward_f32``).  GRU tiers only.  About 4x slower than the bf16
-path; it exists for validation, not for throughput.
+tolerances (loss rel <= 1e-5, per-tensor gradient rel-L2 <= 3e-3).  Products are accurate to ~4-7e-6: 2^-18
+from the two-piece split plus ~3e-8 per K=16 accumulator update (the tensor core's fp32 accumulation truncates; measured
+in tests/test_gpu_fp32_mode.py) - which is why the three-piece / six-product variant (``ops.gemm_nt32(terms=6)``, operands
+exact to fp32) is NOT used here: at K >= 1024 its twice-longer accumulation chain costs more accuracy than the extra
+pieces bring.  The recurrence runs as one split-operand GEMM and one fp32 cell kernel per timestep
+(``srnn_gru_forward_f32``).  GRU tiers only.  About 5x slower than the bf16 path; it exists for validation, not for
+throughput.
 """
 import torch
 
@@ -185,18 +189,14 @@ class SampleLevelFn32(torch.autograd.Function):
             ops.gemm_nt32(e32, we[:, k * q:(k + 1) * q], out=tt[k * q:(k + 1) * q])
         cwc = cw.contiguous()
         w_e, w_c, w_u = cwc[:, :h], cwc[:, h:2 * h], cwc[:, 2 * h:]
-        tprime = ops.gemm_nt32(w_e, tt)                                            # T'[o', k*Q+q]
-        t2, _ = ops.split3(tprime, 2)                                              # bf16 (H, 2*r0*Q): [hi | lo]
+        tprime_t = ops.gemm_nt32(tt, w_e)                                 # T'^T[k*Q+q, o'] = sum_o tt[k*Q+q,o] W_e[o',o]
 
         conds2 = conds.contiguous().view(b * l, c)
         c_frame = ops.gemm_nt32(conds2, csw.contiguous().view(h, c), bias=csb.contiguous())
-        cterm = ops.gemm_nt32(c_frame, w_c, bias=cbias.contiguous())               # (B*L, H)
+        cterm = ops.gemm_nt32(c_frame, w_c, bias=cbias.contiguous())      # (B*L, H)
 
-        # [one-hot windows | one-hot windows] . [T'_hi | T'_lo]^T: the one-hot operand is exact in bf16
-        p_e = _empty(m, h, device=dev)
-        kq = r0 * q
-        ops.gemm_nt(onehot, t2, p_e, rf, h, 2 * kq, q, 2 * kq, h, batch=b, a_bs=w * q, c_bs=rf * h,
-                    a2=onehot, lda2=q, a2_bs=w * q, k1=kq)
+        # the one-hot x table product is a gather-sum of r0 table rows per sample: exact in fp32
+        p_e = ops.embed_gather_f32(tprime_t, xs_u8.contiguous(), rf, r0, q)        # (m, H)
         upper_c = upper.reshape(m, h).contiguous()
         h1 = ops.gemm_nt32(upper_c, w_u)
         mk1 = torch.empty(m, (h + 31) // 32, dtype=torch.int32, device=dev)
@@ -214,7 +214,7 @@ class SampleLevelFn32(torch.autograd.Function):
         w3_t = _empty(h, q, device=dev)
         inv_3 = _empty(q, device=dev)
         ops.weight_prep_f32(w3v, w3g, (q, h, 1), w3, (h, 1, 0), w3_t, (1, q, 0), inv_norm=inv_3)
-        logp = ops.gemm_nt32(h2, w3, bias=b3.contiguous())                         # logits, then log-probabilities in place
+        logp = ops.gemm_nt32(h2, w3, bias=b3.contiguous())                # logits, then log-probabilities in place
         if target_u8 is None:
             target_u8 = torch.zeros(m, dtype=torch.uint8, device=dev)
         target_u8 = target_u8.contiguous()

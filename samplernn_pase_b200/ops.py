@@ -446,20 +446,27 @@ def _mat(x, name):
     return x, x.shape[0], x.shape[1], x.stride(0)
 
 
+SPLIT_SEGMENTS = {0: 3, 1: 3, 2: 2, 3: 6, 4: 6}
+
+
 def split3(x, role):
-    """fp32 (rows, cols) -> bf16 (rows, n_seg * cols_pad): role 0 [hi|lo|hi], 1 [hi|hi|lo], 2 [hi|lo]; cols_pad = cols
+    """fp32 (rows, cols) -> bf16 (rows, n_seg * cols_pad): role 0 [hi|lo|hi], 1 [hi|hi|lo], 2 [hi|lo] (two pieces, 2^-18);
+    role 3 [p0|p0|p1|p0|p1|p2], 4 [q0|q1|q0|q2|q1|q0] (three pieces, fp32-exact operands, six products); cols_pad = cols
     rounded up to 8.  Returns (tensor, cols_pad)."""
     x, rows, cols, ld = _mat(x, 'split3 x')
     kp = round_up(cols, 8)
-    seg = 2 if role == 2 else 3
+    seg = SPLIT_SEGMENTS[role]
     out = torch.empty(rows, seg * kp, dtype=BF16, device=x.device)
     call('srnn_split3_bf16', ptr(x), rows, cols, ld, ptr(out), kp, seg * kp, role, stream())
     _count()
     return out, kp
 
 
-def gemm_nt32(a, w, out=None, bias=None, gate_mask=None, colsum=None):
-    """out[m,n] = a[m,k] . w[n,k]^T (+ bias) at fp32-level accuracy: ONE bf16 GEMM over K' = 3k on split operands.
+def gemm_nt32(a, w, out=None, bias=None, gate_mask=None, colsum=None, terms=3):
+    """out[m,n] = a[m,k] . w[n,k]^T (+ bias) at fp32-level accuracy: ONE bf16 GEMM over K' = terms * k on split operands.
+    terms = 3: two pieces per operand, products accurate to 4e-6 (short K) .. 7e-6 (K = 1024); terms = 6: three pieces,
+    4e-7 at short K but 1e-5 at K = 1024 - the tensor core's truncating fp32 accumulation costs ~3e-8 per K=16 update, so
+    the longer chain loses more than the extra pieces gain; the model path uses terms = 3.
     ``a``/``w``/``out`` are fp32 matrices (views with a row stride are fine)."""
     a, m, k, _ = _mat(a, 'gemm_nt32 a')
     w, n, k2, _ = _mat(w, 'gemm_nt32 w')
@@ -468,9 +475,21 @@ def gemm_nt32(a, w, out=None, bias=None, gate_mask=None, colsum=None):
     if out is None:
         out = torch.empty(m, n, dtype=F32, device=a.device)
     out, _, _, ldc = _mat(out, 'gemm_nt32 out')
-    a3, kp = split3(a, 0)
-    w3, _ = split3(w, 1)
-    gemm_nt(a3, w3, out, m, n, 3 * kp, 3 * kp, 3 * kp, ldc, bias=bias, gate_mask=gate_mask, colsum=colsum)
+    a3, kp = split3(a, 0 if terms == 3 else 3)
+    w3, _ = split3(w, 1 if terms == 3 else 4)
+    gemm_nt(a3, w3, out, m, n, terms * kp, terms * kp, terms * kp, ldc, bias=bias, gate_mask=gate_mask, colsum=colsum)
+    return out
+
+
+def embed_gather_f32(table, idx_u8, rows_per_slot, r0, q):
+    """out[(b,j), :] = sum_k table[k*q + idx[b, j+k], :]; table fp32 (r0*q, H) contiguous, idx uint8 (B, W)."""
+    _need(table, F32, 'embed_gather_f32 table')
+    _need(idx_u8, torch.uint8, 'embed_gather_f32 idx')
+    b, w = idx_u8.shape
+    h = table.shape[1]
+    out = torch.empty(b * rows_per_slot, h, dtype=F32, device=table.device)
+    call('srnn_embed_gather_f32', ptr(table), ptr(idx_u8), w, b, rows_per_slot, r0, q, h, ptr(out), stream())
+    _count()
     return out
 
 

@@ -66,10 +66,11 @@ def test_split_operand_gemms_vs_float64():
         bias = torch.randn(n, generator=gen)
         ref = a.double() @ w.double().t() + bias.double()
         got = ops.gemm_nt32(a.cuda(), w.cuda(), bias=bias.cuda()).cpu()
+        got6 = ops.gemm_nt32(a.cuda(), w.cuda(), bias=bias.cuda(), terms=6).cpu()
         fp32 = (a @ w.t() + bias)
-        e, e32 = rel_l2(got, ref), rel_l2(fp32, ref)
-        report(f'gemm_nt32 {m}x{n}x{k}: rel-L2 {e:.2e} (torch fp32 on the CPU: {e32:.2e})')
-        assert e <= 2e-5, (m, n, k, e)
+        e, e6, e32 = rel_l2(got, ref), rel_l2(got6, ref), rel_l2(fp32, ref)
+        report(f'gemm_nt32 {m}x{n}x{k}: rel-L2 3 products {e:.2e}, 6 products {e6:.2e} (torch fp32 on the CPU: {e32:.2e})')
+        assert e <= 2e-5 and e6 <= (1e-6 if k <= 64 else 3e-5), (m, n, k, e, e6)
     for rows, m, n in ((300, 96, 47), (4096, 256, 128), (8, 1024, 64)):
         a = torch.randn(rows, m, generator=gen)
         b = torch.randn(rows, n, generator=gen)
@@ -165,8 +166,9 @@ def test_fp32_mode_full_width_config2_vs_cpu_oracle(monkeypatch):
     pre-activations of h1/h2 a handful (|x| < 4e-6 |row|) land on the other side of zero than in exact arithmetic; each
     flipped gate is a full-size error in one element of dh2/dh1, i.e. rel-L2 ~ sqrt(flips / active) ~ 2-3e-3 (the fp32
     reference, 50x more accurate per product, flips none here).  The learned initial states, reached only through 64
-    recurrent steps, show 0.7-1.5e-2.  Bounds at this width: 5e-3 per tensor (SURVEY 8(d) says 3e-3; the goldens meet it
-    100x over), 2.5e-2 for rnn_h0, cosine >= 0.9998."""
+    recurrent steps, show 0.7-1.5e-2.  In the second chunk the fp32 reference itself shows 1.2-1.7e-3 on the same tensors
+    (it flips a few gates too).  Bounds at this width: 5e-3 per tensor (SURVEY 8(d) says 3e-3; the goldens meet it 100x
+    over), 2.5e-2 for rnn_h0, cosine >= 0.9998."""
     need_gpu()
     from samplernn_pase_b200 import SampleRNNModel
     ratios, layers, seq, hidden = [4, 4], [1, 1], 16, [1024, 1024]
