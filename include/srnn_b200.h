@@ -221,7 +221,8 @@ typedef struct srnn_gru_args {
                             per-step operand as one TMA box per K block instead of ONE box, 64 = two MMA-issuing warps, bits 12-13 = polls of the arrival
                             counter kept in flight (0: 1, 1: 2, 2: 4), bits 14-15 = their spacing ((n+1)*64 cycles),
                             bits 16-19 = n*32 cycles to hold the TMA read back after the wait, bits 20-23 = cycles before the first
-                            poll of a wait (0: 256, n: (n-1)*128), 1 << 24 = the last arriver releases the others
+                            poll of a wait (0: 256, n: (n-1)*128), 1 << 25 = speculative landing (the first attempt of a timestep
+                            skips the counter and relies on the validation; measured no faster), 1 << 24 = the last arriver releases the others
                             through per-CTA flag lines (default: every CTA polls the arrival counter; measured faster), 128 = debug_ts receives the global
                             timer of every CTA at timestep 24, bits 8-11 = force a cluster size.  Bits 1 and 4 exist only
                             in instrumented (-DSRNN_DEBUG) builds and are rejected with SRNN_ERR_ARG otherwise. */

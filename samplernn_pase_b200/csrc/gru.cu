@@ -413,16 +413,28 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       int s = BWD ? 1 : 0;                           // backward: the last timestep (round 0) has no recurrent input
       int grp = 0;                                   // group of 64 batch rows inside timestep s
       bool fresh = true;                             // first attempt of (s, grp)
+      // Tuning flag 1 << 25, SPECULATIVE landing: the first attempt of a timestep does not wait for the arrival counter at
+      // all - it issues the TMA read `pre_poll` cycles after this CTA's own publish and lets the validation decide; only a
+      // rejected attempt falls back to the counter.  (The counter's round trip - RED to a hot L2 line + a poll - is longer
+      // than the time the data stores themselves need to reach L2.)
+      const bool speculate = !strict && (p.flags & (1 << 25)) != 0;
+      bool waited = false;                           // this timestep's counter wait has been done
       for (;;) {
         if (mw == 0) {
-          if (fresh && grp == 0 && s > 0 && !grid_wait_skipped(p.flags)) {
-            if (pre_poll) spin_cycles(pre_poll);
+          if (fresh && grp == 0) waited = false;
+          const bool first = fresh && grp == 0 && s > 0;
+          if (s > 0 && !waited && !grid_wait_skipped(p.flags) && (speculate ? !fresh : first)) {
+            if (pre_poll && first) spin_cycles(pre_poll);
             if (!(p.flags & (1 << 24)))
               grid_wait(p.sync, G * static_cast<uint32_t>(s), strict, poll_depth, poll_gap);
             else                                     // experiment: own flag line, written by the last arriver of round s
               grid_wait(p.sync + GRU_FLAG_BASE + GRU_FLAG_STRIDE * blockIdx.x, static_cast<uint32_t>(s), strict, poll_depth,
                         poll_gap);
             if (hold) spin_cycles(hold);
+            waited = true;
+            GRU_TS(0, s);
+          } else if (speculate && first) {
+            if (pre_poll) spin_cycles(pre_poll);
             GRU_TS(0, s);
           }
           asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy writes -> TMA reads (free: measured)
