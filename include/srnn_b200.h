@@ -213,7 +213,7 @@ typedef struct srnn_gru_args {
   void* dgh;             /* bf16 [steps, ext_batch, 3H] TIME-major, out (also the per-step exchange buffer) */
   float* dh0;            /* fp32 [batch, H] out: dL/dh_init */
   uint32_t* sync;        /* >= 32 KB (8192 uint32), zeroed by the caller before every launch: [0] grid-wide arrival
-                            counter, [64 + 32 j] release flag of CTA j; on return [32] holds the number of exchange
+                            counter, [64 + 32 j] release flag of CTA j, [4160 + 32 g] arrival counter of row group g; on return [32] holds the number of exchange
                             attempts the kernel rejected and repeated (see below) */
   int32_t tuning_flags;  /* 0 = defaults.  Every documented bit leaves the results unchanged:
                             2 = force a cooperative launch for steps == 1, 16 = strict exchange protocol (release
@@ -221,7 +221,10 @@ typedef struct srnn_gru_args {
                             per-step operand as one TMA box per K block instead of ONE box, 64 = two MMA-issuing warps, bits 12-13 = polls of the arrival
                             counter kept in flight (0: 1, 1: 2, 2: 4), bits 14-15 = their spacing ((n+1)*64 cycles),
                             bits 16-19 = n*32 cycles to hold the TMA read back after the wait, bits 20-23 = cycles before the first
-                            poll of a wait (0: 256, n: (n-1)*128), 1 << 25 = speculative landing (the first attempt of a timestep
+                            poll of a wait (0: 256, n: (n-1)*128), 1 << 26 = forward multi-group launches (batch > 64) use ONE arrival counter per timestep instead of one
+                            per 64-row group (default forward: per group - a group's handshake then overlaps the other groups' work;
+                            default backward: per timestep, 1 << 28 = per group there too), 1 << 27 =
+                            32-row groups for 32 < batch <= 64 (measured slower), 1 << 25 = speculative landing (the first attempt of a timestep
                             skips the counter and relies on the validation; measured no faster), 1 << 24 = the last arriver releases the others
                             through per-CTA flag lines (default: every CTA polls the arrival counter; measured faster), 128 = debug_ts receives the global
                             timer of every CTA at timestep 24, bits 8-11 = force a cluster size.  Bits 1 and 4 exist only

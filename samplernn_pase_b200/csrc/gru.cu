@@ -51,7 +51,9 @@ struct GruParams {
   int hslot;                       // bytes between K blocks of the staged [batch, K slice] operand
   int one_box;                     // the whole slice arrives as ONE 4-D TMA box (else one box per K block)
   int groups;                      // > 1: single-timestep forward over `groups` blocks of 64 rows in ONE launch (generation)
-  int box_rows;                    // rows of one TMA box of the exchanged operand (min(batch, 64))
+  int box_rows;                    // rows of one TMA box of the exchanged operand (min(batch, group_rows))
+  int group_rows;                  // batch rows per group: 64 (one full MMA tile), or 32 (tuning flag 1 << 27, batch <= 64)
+  int group_sync;                  // groups > 1: every group has its own arrival counter, published and awaited per group
   const __nv_bfloat16* gi;
   const float* b_hh;
   __nv_bfloat16* h_ext;
@@ -213,6 +215,14 @@ __device__ __forceinline__ void grid_wait(const uint32_t* counter, uint32_t targ
 // arriver's return + flag stores + a second poll round trip cost more than the reader queue they remove.
 // Called by the whole of epilogue warp 2 (converged); `round` = publishes of this CTA so far, this one included.
 constexpr int GRU_FLAG_BASE = 64, GRU_FLAG_STRIDE = 32;            // in uint32 words of the sync buffer
+// Per-group arrival counters (multi-group launches): group g of timestep t only needs group g's rows of h_{t-1}, so each
+// group publishes to and waits on ITS OWN counter.  A CTA walks the groups of a timestep one after the other, so by the
+// time it returns to group g for the next timestep, the other CTAs' publishes of group g are a whole group phase old:
+// the grid handshake (~2 300 cycles) of one group hides behind the landing + MMAs + gate math of the others.
+constexpr int GRU_GROUP_BASE = GRU_FLAG_BASE + GRU_FLAG_STRIDE * 128, GRU_GROUP_STRIDE = 32;
+__device__ __forceinline__ uint32_t* group_counter(uint32_t* sync, int group_sync, int grp) {
+  return group_sync ? sync + GRU_GROUP_BASE + GRU_GROUP_STRIDE * grp : sync;
+}
 __device__ __forceinline__ void publish(uint32_t* sync, int flags, uint32_t round, uint32_t n_ctas, int lane) {
   const bool strict = (flags & 16) != 0;
   if (!(flags & (1 << 24))) {                                    // default: plain counter, polled by everyone
@@ -421,12 +431,14 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
       bool waited = false;                           // this timestep's counter wait has been done
       for (;;) {
         if (mw == 0) {
-          if (fresh && grp == 0) waited = false;
-          const bool first = fresh && grp == 0 && s > 0;
+          // one wait per timestep (before its first group), or - with per-group counters - one per group
+          const bool head = fresh && (grp == 0 || p.group_sync);
+          if (head) waited = false;
+          const bool first = head && s > 0;
           if (s > 0 && !waited && !grid_wait_skipped(p.flags) && (speculate ? !fresh : first)) {
-            if (pre_poll && first) spin_cycles(pre_poll);
+            if (pre_poll && first && grp == 0) spin_cycles(pre_poll);
             if (!(p.flags & (1 << 24)))
-              grid_wait(p.sync, G * static_cast<uint32_t>(s), strict, poll_depth, poll_gap);
+              grid_wait(group_counter(p.sync, p.group_sync, grp), G * static_cast<uint32_t>(s), strict, poll_depth, poll_gap);
             else                                     // experiment: own flag line, written by the last arriver of round s
               grid_wait(p.sync + GRU_FLAG_BASE + GRU_FLAG_STRIDE * blockIdx.x, static_cast<uint32_t>(s), strict, poll_depth,
                         poll_gap);
@@ -439,7 +451,7 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
           }
           asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy writes -> TMA reads (free: measured)
           const int slot = BWD ? (T - s) : s;                     // time slot of the exchange buffer
-          const int row0 = grp * GRU_M;                           // first batch row of this group
+          const int row0 = grp * p.group_rows;                    // first batch row of this group
           if (one_box) {
             mbar_expect_tx(full, bytes);
             tma_load_4d(hbuf, &tma_x, full, 0, row0, kb0, slot);
@@ -528,8 +540,8 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
     // 512..3 072 cycles after the publish so that this SM's memory pipeline stays free for the polls - measured 3.76-3.99 us
     // per forward timestep against 3.60 and no change backward: the spinning warps take issue slots from the issuing thread.)
     auto set_group = [&](int g) {
-      grow = g * GRU_M + row;
-      row_ok = lane_ok && grow < B;
+      grow = g * p.group_rows + row;
+      row_ok = lane_ok && row < p.group_rows && grow < B;
       io = row_ok && !epilogue_io_skipped(p.flags);
     };
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -725,9 +737,9 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
               p.c_state[static_cast<long long>(grow) * H + u0 + i] = c[i];
             }
           }
-          if (grp == n_groups - 1) {                   // every group's h_t is stored: one arrival per CTA and timestep
+          if (p.group_sync || grp == n_groups - 1) {                   // every group's h_t is stored: one arrival per CTA and timestep
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (warp == 2 && T > 1) publish(p.sync, p.flags, static_cast<uint32_t>(t + 1), G, lane);   // T == 1: nobody waits
+            if (warp == 2 && T > 1) publish(group_counter(p.sync, p.group_sync, grp), p.flags, static_cast<uint32_t>(t + 1), G, lane);   // T == 1: nobody waits
           }
           if (p.hall && io) store_units<U>(p.hall + rt * H + u0, h);
           if (p.gates && io) {                           // saved for backward: i, f, g, o, c_t  (5H per row)
@@ -820,9 +832,9 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < U; ++i) p.dc0[static_cast<long long>(grow) * H + u0 + i] = carry_c[i];
           }
-          if (grp == n_groups - 1) {
+          if (p.group_sync || grp == n_groups - 1) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (warp == 2) publish(p.sync, p.flags, static_cast<uint32_t>(s + 1), G, lane);
+            if (warp == 2) publish(group_counter(p.sync, p.group_sync, grp), p.flags, static_cast<uint32_t>(s + 1), G, lane);
           }
           if (io) {                                               // same values, batch-major, for the GEMMs
             __nv_bfloat16* gip = p.dgi + rt * 4 * H + u0;
@@ -897,12 +909,12 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < U; ++i) p.h_state[static_cast<long long>(grow) * H + u0 + i] = h[i];
           }
-          if (grp == n_groups - 1) {
+          if (p.group_sync || grp == n_groups - 1) {
             // publish h_t: all epilogue threads' stores (of every group) -> one arrival per CTA
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (warp == 2) {
               if (lane == 0) GRU_TS(6, t);
-              if (T > 1) publish(p.sync, p.flags, static_cast<uint32_t>(t + 1), G, lane);   // T == 1: nobody waits
+              if (T > 1) publish(group_counter(p.sync, p.group_sync, grp), p.flags, static_cast<uint32_t>(t + 1), G, lane);   // T == 1: nobody waits
             }
           }
           // the batch-major copy of h_t (GEMM operand) and the saved gates are off the critical path
@@ -984,11 +996,11 @@ gru_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < U; ++i) p.dh0[static_cast<long long>(grow) * H + u0 + i] = carry[i];
           }
-          if (grp == n_groups - 1) {
+          if (p.group_sync || grp == n_groups - 1) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (warp == 2) {
               if (lane == 0) GRU_TS(6, s);
-              publish(p.sync, p.flags, static_cast<uint32_t>(s + 1), G, lane);
+              publish(group_counter(p.sync, p.group_sync, grp), p.flags, static_cast<uint32_t>(s + 1), G, lane);
             }
           }
           if (io) {                                               // dgi is only read after the kernel
@@ -1117,8 +1129,12 @@ static int launch_gru_mw(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   // lands it as one box + one barrier per K block instead so that the MMAs of block i could start while later blocks
   // are in flight - measured slower (16 issues cost 1 500 cycles and the FIRST 8 KB box still takes ~1 700 cycles to
   // land, as long as the whole 128 KB box: the landing is latency-, not bandwidth-bound; profiles/r02_gru_pipelined.txt).
-  const int rows = B < GRU_M ? B : GRU_M;              // rows of one MMA tile / TMA box (B > 64: multi-group mode)
-  const int groups = (B + GRU_M - 1) / GRU_M;
+  // Groups: B > 64 rows are walked in groups of 64 inside every timestep.  Tuning flag 1 << 27: groups of 32 rows for
+  // 32 < B <= 64 (half the landing bytes per group, and with per-group counters the two groups hide each other's
+  // handshake; each group still costs a full M = 64 MMA pass).
+  const int group_rows = ((a->tuning_flags & (1 << 27)) && B > 32 && B <= GRU_M) ? 32 : GRU_M;
+  const int rows = B < group_rows ? B : group_rows;    // rows of one TMA box (B > group_rows: multi-group mode)
+  const int groups = (B + group_rows - 1) / group_rows;
   const bool one_box = !(a->tuning_flags & 32) && K % 64 == 0 && B % 8 == 0 && kbc * rows * 128 <= 160 * 1024;
   {
     const uint64_t slots = BWD ? (uint64_t)T : (uint64_t)T + 1;
@@ -1142,6 +1158,12 @@ static int launch_gru_mw(const srnn_gru_args* a, int kbc, cudaStream_t stream) {
   p.one_box = one_box ? 1 : 0;
   p.groups = groups;
   p.box_rows = rows;
+  p.group_rows = group_rows;
+  // Per-group arrival counters: default for FORWARD multi-group launches (measured B=128, T=4000: 6.77 us per timestep
+  // against 7.73 with one counter per timestep); the backward kernel keeps one counter per timestep (9.12 against 9.50:
+  // its cluster reduction already staggers the groups).  1 << 26 forces one counter per timestep, 1 << 28 per-group
+  // counters in the backward kernel too; never combined with the fan-out experiment (which owns the flag lines).
+  p.group_sync = (groups > 1 && !(a->tuning_flags & ((1 << 26) | (1 << 24))) && (!BWD || (a->tuning_flags & (1 << 28)))) ? 1 : 0;
   p.hslot = one_box ? rows * 128 : GRU_SLOT;
   p.gi = static_cast<const __nv_bfloat16*>(a->gi);
   p.b_hh = a->b_hh;

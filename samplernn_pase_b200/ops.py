@@ -5,6 +5,7 @@ All matrices are row-major.  ``bf16`` operands must have 16-byte aligned bases a
 dimensions that are multiples of 8 elements (TMA).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -329,9 +330,9 @@ def gemm_nll(mode, a, w, bias, target, m, k, lda, ldw, lse=None, logp_target=Non
 # recurrence
 # ----------------------------------------------------------------------------------------------
 GRU_MAX_BATCH = 64          # rows of one MMA tile (a group)
-GRU_MAX_STEP_BATCH = 512    # rows per launch (8 groups); set to 64 to run every group as its own launch
+GRU_MAX_STEP_BATCH = int(os.environ.get('SRNN_GRU_MAX_STEP_BATCH', '512'))    # rows per launch (8 groups); 64: every group its own launch
 GRU_SYNC_WORDS = 8192       # srnn_gru_args.sync: arrival counter, statistics and one release-flag line per CTA
-gru_tuning_flags = 0     # srnn_gru_args.tuning_flags (scripts/gru_microbench.py sweeps them)
+gru_tuning_flags = int(os.environ.get('SRNN_GRU_TUNING_FLAGS', '0'))     # srnn_gru_args.tuning_flags (scripts/gru_microbench.py sweeps them)
 gru_debug_ts = None      # int64 [256, 8] tensor receiving CTA 0's pipeline timestamps
 gru_units_per_cta = 8    # 16 halves the recurrent kernels' CTA count (SMs left free for concurrent GEMMs)
 
