@@ -339,6 +339,11 @@ gru_units_per_cta = 8    # 16 halves the recurrent kernels' CTA count (SMs left 
 
 _gru_scratch = {}
 gru_last_sync = None
+#: callables invoked (host side) right after a recurrent BACKWARD launch has been enqueued.  The data-parallel trainer uses it
+#: to enqueue its gradient all-reduces BEHIND that launch: a cooperative launch does not start while another stream's kernel
+#: (an NCCL all-reduce waiting for a slower rank) is resident, so an all-reduce enqueued just before it delays the recurrence
+#: by however long the slowest rank is late (profiles/r02_dp_trace_n8.txt)
+rnn_backward_listeners = []
 
 
 def _gru_call(name, batch, steps, hidden, cell=0, **bufs):
@@ -375,6 +380,9 @@ def _gru_call(name, batch, steps, hidden, cell=0, **bufs):
         with timed(f"{'rnn_fwd' if name == 'srnn_gru_forward' else 'rnn_bwd'}_T{steps}"):
             call(name, C.byref(a), stream())
         _count(1 if steps == 1 else 2)
+    if name == 'srnn_gru_backward':
+        for fn in rnn_backward_listeners:
+            fn()
 
 
 def gru_forward(gi, w_hh, b_hh, h_ext, hall, h_state, gates, batch, steps, hidden):

@@ -13,6 +13,8 @@ Clipping (optimizer.py:12) is applied after averaging, inside the fused AdamClip
 Parameters and gradients live in two flat fp32 buffers (views are handed back to the modules), so
 the optimizer is one kernel launch and each bucket is one contiguous NCCL call.
 """
+import os
+import weakref
 from typing import List, Optional
 
 import torch
@@ -127,7 +129,7 @@ class DataParallelTrainer:
     ``group=None`` with an uninitialised process group runs single-process (no collectives).
     Works with any backend; tests drive it with gloo on CPU tensors through ``reduce_only``."""
 
-    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, group=None):
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, group=None, defer_buckets=None):
         self.model = model
         self.flat = FlatBuffers(model)
         self.group = group
@@ -135,6 +137,17 @@ class DataParallelTrainer:
         self.optimizer = FlatAdamClipped(self.flat, lr=lr, betas=betas, eps=eps)
         self._pending: List = []
         self._ready = None
+        # A bucket whose gradients are complete is not all-reduced at once but right AFTER the next recurrent backward launch
+        # has been enqueued (torch orders the NCCL stream behind the work enqueued so far, so the all-reduce then runs after
+        # that recurrence, next to the GEMMs that follow it).  Launched immediately it would still be resident - spinning for
+        # the slowest rank - when the next persistent recurrent kernel is launched, and a cooperative launch waits for it:
+        # 2 ms per step at 8 GPUs (profiles/r02_dp_trace_n8.txt).  Buckets that complete after the last recurrent launch
+        # go out at the end of backward as before.
+        if defer_buckets is None:
+            defer_buckets = os.environ.get('SRNN_DP_DEFER', '1') != '0'
+        self.defer_buckets = defer_buckets
+        self._deferred: List[int] = []
+        self._active = False
         self._install_hooks()
 
     def _install_hooks(self):
@@ -147,11 +160,32 @@ class DataParallelTrainer:
                 owner[i] = bi
         for i, p in enumerate(self.flat.params):
             p.register_post_accumulate_grad_hook(lambda _p, bi=owner[i]: self._param_ready(bi))
+        from . import ops
+        ref = weakref.WeakMethod(self._after_recurrent_launch)       # a dropped trainer must not keep receiving calls
+
+        def listener():
+            fn = ref()
+            if fn is not None:
+                fn()
+        ops.rnn_backward_listeners.append(listener)
 
     def _param_ready(self, bi):
         self._remaining[bi] -= 1
         if self._remaining[bi] == 0:
+            if self.defer_buckets:
+                self._deferred.append(bi)
+            else:
+                self._launch_bucket(bi)
+
+    def _after_recurrent_launch(self):
+        """ops.rnn_backward_listeners callback: a recurrent backward kernel has just been enqueued."""
+        if self._active:
+            self._flush_deferred()
+
+    def _flush_deferred(self):
+        for bi in self._deferred:
             self._launch_bucket(bi)
+        self._deferred = []
 
     def _launch_bucket(self, bi):
         _, start, end, _ = self.flat.buckets[bi]
@@ -162,12 +196,16 @@ class DataParallelTrainer:
     def _begin(self):
         self._pending = []
         self._launched = set()
+        self._deferred = []
+        self._active = True
         if self.world > 1:
             self._remaining = {bi: len(b[3]) for bi, b in enumerate(self.flat.buckets)}
 
     def _finish_reduce(self):
+        self._active = False
         if self.world == 1:
             return
+        self._flush_deferred()
         for bi in range(len(self.flat.buckets)):                               # parameters that got no gradient
             if bi not in self._launched:
                 self._launch_bucket(bi)
