@@ -171,3 +171,58 @@ def test_flat_adam_clipped_state_dict_uses_torch_adam_layout():
     for i, (p, off) in enumerate(zip(flat.params, flat.offsets)):
         assert bool((opt.exp_avg[off: off + p.numel()] == i + 1).all())
         assert opt.state[p]['exp_avg'].data_ptr() == opt.exp_avg[off: off + p.numel()].data_ptr()
+
+
+def _worker_deferred(rank, world, port, results):
+    """Deferred buckets: a completed bucket is held back until a recurrent backward launch has been enqueued
+    (``ops.rnn_backward_listeners``) or backward ends; with ``defer_buckets=False`` it goes out from the hook."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from samplernn_pase_b200 import ops
+    torch.manual_seed(0)
+    m = Tiny()
+    trainer = DataParallelTrainer(m, defer_buckets=True)
+    x = torch.randn(4, 5, generator=torch.Generator().manual_seed(rank))
+    seen = {}
+    # a "recurrent backward launch" in the middle of backward: when the gradient of frames_layers[1]'s input is computed
+    def mid(_grad):
+        seen['before'] = (sorted(trainer._launched), list(trainer._deferred))
+        for fn in ops.rnn_backward_listeners:
+            fn()
+        seen['after'] = (sorted(trainer._launched), list(trainer._deferred))
+    trainer._begin()
+    trainer.flat.zero_grad()
+    h = torch.tanh(m.frames_layers[0](m.conds_mixer(x)))
+    h.register_hook(mid)
+    m.sample_layer(torch.tanh(m.frames_layers[1](h))).pow(2).sum().backward()
+    end = (sorted(trainer._launched), list(trainer._deferred))
+    trainer._finish_reduce()
+    deferred_grad = trainer.flat.flat_grad.clone()
+    # the same step with immediate launches gives the same reduced gradient
+    torch.manual_seed(0)
+    m2 = Tiny()
+    t2 = DataParallelTrainer(m2, defer_buckets=False)
+    t2._begin()
+    t2.flat.zero_grad()
+    m2(x).pow(2).sum().backward()
+    immediate = sorted(t2._launched)
+    t2._finish_reduce()
+    results[rank] = (seen, end, sorted(trainer._launched), immediate, bool(torch.allclose(deferred_grad, t2.flat.flat_grad, atol=1e-6)))
+    dist.destroy_process_group()
+
+
+def test_deferred_buckets_go_out_behind_a_recurrent_launch():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker_deferred, args=(2, port, results), nprocs=2, join=True)
+    for rank in range(2):
+        seen, end, launched, immediate, same = results[rank]
+        # buckets in FlatBuffers order: conds_mixer 0, frames_layers.0 1, frames_layers.1 2, sample_layer 3
+        assert seen['before'] == ([], [3, 2])            # sample layer and the upper tier are complete but held back
+        assert seen['after'] == ([2, 3], [])             # the "recurrent launch" releases them
+        assert end == ([2, 3], [1, 0])                   # the rest waits for the end of backward
+        assert launched == [0, 1, 2, 3] and immediate == [0, 1, 2, 3] and same
