@@ -230,3 +230,49 @@ def test_fp32_mode_full_width_config2_vs_cpu_oracle(monkeypatch):
         for n in range(len(ratios)):
             rows = [i for i, v in enumerate(state64.valid[n]) if v]
             assert float((model._state[n].cpu()[:, rows] - state64.h[n][:, rows]).abs().max()) <= STATE_ABS
+
+
+def test_fp32_mode_layer_level_api_matches_oracle():
+    """CondsMixer / FrameLevelLayer / SampleLevelLayer called with the reference's own conventions (model.py:60,140,188) in
+    the fp32-tolerance mode, against the oracle: 1e-4 where the bf16 path is held to 3e-2 .. 8e-2."""
+    g = Golden('gru2_single')
+    model = build_model(g)
+    sd = g.state_dict()
+    spec = O.ModelSpec(**g.spec_kwargs())
+    c = g.chunk(0)
+    conds_ref = O.conds_mixer(sd, c['conds'], c['speakers'])
+    conds = model.conds_mixer(c['conds'].cuda(), infos(c))
+    assert float((conds.cpu() - conds_ref).abs().max()) < 1e-4
+    xq = O.quantize(c['x'])
+    n = len(spec.ratios) - 1
+    fs = spec.frame_sizes[n]
+    frames = O.dequantize(xq[:, :c['y'].shape[1]]).reshape(xq.shape[0], -1, fs)
+    h0 = sd[f'frames_layers.{n}.rnn_h0'][:, None].expand(-1, xq.shape[0], -1)
+    up_ref, hn_ref = O.frame_tier(sd, n, frames, conds_ref, None, h0)
+    up, hn = model.frames_layers[n](frames.cuda(), conds_ref.cuda(), None, [None] * xq.shape[0])
+    assert float((up.cpu() - up_ref).abs().max()) < 1e-4 and float((hn.cpu() - hn_ref).abs().max()) < 1e-4
+    # a lower tier takes the upper tier's output as conditioning (model.py:148)
+    fs0 = spec.frame_sizes[0]
+    frames0 = O.dequantize(xq[:, spec.frame_size - fs0: spec.frame_size - fs0 + c['y'].shape[1]]).reshape(xq.shape[0], -1, fs0)
+    h00 = sd['frames_layers.0.rnn_h0'][:, None].expand(-1, xq.shape[0], -1)
+    low_ref, _ = O.frame_tier(sd, 0, frames0, conds_ref, up_ref, h00)
+    low, _ = model.frames_layers[0](frames0.cuda(), conds_ref.cuda(), up_ref.cuda(), [None] * xq.shape[0])
+    assert float((low.cpu() - low_ref).abs().max()) < 1e-4
+    r0 = spec.ratios[0]
+    xs = xq[:, spec.frame_size - r0:]
+    upper = torch.randn(xq.shape[0], c['y'].shape[1], spec.hidden[0], generator=torch.Generator().manual_seed(1)) * 0.3
+    lp_ref = O.sample_level(sd, xs, conds_ref, upper)
+    lp = model.sample_layer(xs.cuda(), conds_ref.cuda(), upper.cuda())
+    assert lp.shape == lp_ref.shape and float((lp.cpu() - lp_ref).abs().max()) < 2e-4
+    assert float(torch.logsumexp(lp, 2).abs().max()) < 1e-5
+
+
+def test_fp32_mode_rejects_what_it_does_not_cover():
+    need_gpu()
+    from samplernn_pase_b200 import SampleRNNModel
+    with pytest.raises(ValueError):
+        SampleRNNModel('embedding', 5, 15, 'acoustic', [9, 5, 4, 3], 10, 50, 4, [4, 4], [1, 1], [32, 32], True, 256,
+                       precision='fp32', rnn_cell='lstm')
+    with pytest.raises(ValueError):
+        SampleRNNModel('embedding', 5, 15, 'acoustic', [9, 5, 4, 3], 10, 50, 4, [4, 4], [1, 1], [32, 32], True, 256,
+                       precision='tf32')
