@@ -325,13 +325,13 @@ int srnn_sample_embed(const float* in, int64_t ld, int32_t batch, int32_t q, int
  * below are what the mode needs besides the GEMM.  It is ~4x slower than the bf16 path.
  * ------------------------------------------------------------------------------------------- */
 /* fp32 (rows, cols) -> bf16 (rows, n_seg * cols_pad), every segment zero padded to cols_pad columns.
- * Two pieces (x ~ hi + lo to 2^-18; three products): role 0: [hi | lo | hi] (first operand of a product), role 1:
- * [hi | hi | lo] (second operand), role 2: [hi | lo] (against an operand that is exact in bf16, e.g. one-hot rows).
+ * Two pieces (x ~ hi + lo to 2^-18; three products): role 0: [lo | hi | hi] (first operand of a product), role 1:
+ * [hi | lo | hi] (second operand), role 2: [lo | hi] (against an operand that is exact in bf16, e.g. one-hot rows).
  * Three pieces (x = p0 + p1 + p2 to 2^-24, i.e. all of fp32; the six products down to order 2^-16): role 3:
- * [p0 | p0 | p1 | p0 | p1 | p2] (first operand), role 4: [q0 | q1 | q0 | q2 | q1 | q0] (second operand).  The tensor core's
- * fp32 accumulation truncates (~3e-8 relative per K=16 update, measured), so the six-product form only pays for short
- * K (it reaches 4e-7 at K = 47 but 1e-5 at K = 1024, where the three-product form gives 7e-6); the model path uses
- * roles 0-2.  A TN product uses the three column segments of roles 0 / 1 in three accumulating calls. */
+ * [p2 | p1 | p0 | p1 | p0 | p0] (first operand), role 4: [q0 | q1 | q2 | q0 | q1 | q0] (second operand).  The SMALLEST
+ * products come first along K: the tensor core's fp32 accumulation truncates (~3e-8 relative to the accumulator per
+ * K=16 update, measured), so with the leading product last the accumulator is small during all the other updates.
+ * A TN product uses the three column segments of roles 0 / 1 in three accumulating calls. */
 int srnn_split3_bf16(const float* in, int64_t rows, int32_t cols, int64_t ld_in, void* out_bf16, int32_t cols_pad,
                      int64_t ld_out, int32_t role, srnn_stream_t stream);
 /* fp32-output variants of srnn_mixer_input / srnn_tier_input / srnn_weight_prep and fp32-input variants of their
@@ -374,14 +374,14 @@ int srnn_logsoftmax_nll_bwd_f32(const float* logp, int64_t ld, int64_t m, int32_
 typedef struct srnn_gru_f32_args {
   int32_t batch, steps, hidden;  /* hidden % 8 == 0 */
   const float* gi;       /* fwd: [batch*steps, 3H] = W_ih x_t + b_ih, row (b,t) = b*steps + t */
-  const void* w3;        /* fwd: srnn_split3_bf16 role 1 of W_hh [3H, H] -> bf16 [3H, 3H]; bwd: role 1 of W_hh^T [H, 3H]
+  const void* w3;        /* fwd: srnn_split3_bf16 role 4 of W_hh [3H, H] -> bf16 [3H, 6H]; bwd: role 1 of W_hh^T [H, 3H]
                             -> bf16 [H, 9H] */
   const float* b_hh;     /* fwd: [3H] */
   float* h_state;        /* fwd: [batch, H] in = h_init, out = h_T */
   float* hall;           /* [batch*steps, H]: fwd out, bwd in */
   const float* h_init;   /* bwd: [batch, H] the state the forward started from */
   float* gates;          /* [batch*steps, 4H]: r, z, n, W_hn h + b_hn; fwd out, bwd in */
-  void* a3;              /* workspace, bf16: fwd [batch, 3H], bwd [batch, 9H] */
+  void* a3;              /* workspace, bf16: fwd [batch, 6H], bwd [batch, 9H] */
   float* ws;             /* workspace: fwd [batch, 3H], bwd [batch, H] */
   const float* dh_out;   /* bwd: [batch*steps, H] */
   float* dgi;            /* bwd out: [batch*steps, 3H] */

@@ -13,11 +13,14 @@ namespace srnn {
 
 static inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
 
-// Two-piece roles (x ~ hi + lo, 2^-18 relative; products a_hi.w_hi + a_lo.w_hi + a_hi.w_lo):
-//   role 0: [hi | lo | hi]   (the "A" side of a product)      role 1: [hi | hi | lo]   (the "B" side)
-//   role 2: [hi | lo]        (against an operand that is exact in bf16, e.g. one-hot rows)
+// Two-piece roles (x ~ hi + lo, 2^-18 relative; products a_lo.w_hi + a_hi.w_lo + a_hi.w_hi):
+//   role 0: [lo | hi | hi]   (the "A" side of a product)      role 1: [hi | lo | hi]   (the "B" side)
+//   role 2: [lo | hi]        (against an operand that is exact in bf16, e.g. one-hot rows: [x | x] . [lo | hi])
 // Three-piece roles (x = p0 + p1 + p2 to 2^-24: fp32 exactly; the six products of order <= 2^-16):
-//   role 3: [p0 | p0 | p1 | p0 | p1 | p2]   (A side)          role 4: [q0 | q1 | q0 | q2 | q1 | q0]   (B side)
+//   role 3: [p2 | p1 | p0 | p1 | p0 | p0]   (A side)          role 4: [q0 | q1 | q2 | q0 | q1 | q0]   (B side)
+// SMALLEST PRODUCTS FIRST: the tensor core's fp32 accumulator truncates (~3e-8 relative to the accumulator per K=16
+// update, measured), so the order of the segments along K matters - with the leading product hi.hi LAST the accumulator
+// is small (2^-8 of the result) during all the other updates and only the last K/16 updates truncate at full magnitude.
 __global__ void split3_kernel(const float* __restrict__ in, long long rows, int cols, long long ld_in,
                               __nv_bfloat16* __restrict__ out, int cols_pad, long long ld_out, int role) {
   const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -29,21 +32,18 @@ __global__ void split3_kernel(const float* __restrict__ in, long long rows, int 
   const float r1 = x - __bfloat162float(h);
   const __nv_bfloat16 l = __float2bfloat16_rn(r1);
   __nv_bfloat16* o = out + r * ld_out + c;
-  o[0] = h;
   if (role == 0) {
-    o[cols_pad] = l;
-    o[2 * cols_pad] = h;
+    o[0] = l; o[cols_pad] = h; o[2 * cols_pad] = h;
   } else if (role == 1) {
-    o[cols_pad] = h;
-    o[2 * cols_pad] = l;
+    o[0] = h; o[cols_pad] = l; o[2 * cols_pad] = h;
   } else if (role == 2) {
-    o[cols_pad] = l;
+    o[0] = l; o[cols_pad] = h;
   } else {
     const __nv_bfloat16 t = __float2bfloat16_rn(r1 - __bfloat162float(l));
     if (role == 3) {
-      o[cols_pad] = h; o[2 * cols_pad] = l; o[3 * cols_pad] = h; o[4 * cols_pad] = l; o[5 * cols_pad] = t;
+      o[0] = t; o[cols_pad] = l; o[2 * cols_pad] = h; o[3 * cols_pad] = l; o[4 * cols_pad] = h; o[5 * cols_pad] = h;
     } else {
-      o[cols_pad] = l; o[2 * cols_pad] = h; o[3 * cols_pad] = t; o[4 * cols_pad] = l; o[5 * cols_pad] = h;
+      o[0] = h; o[cols_pad] = l; o[2 * cols_pad] = t; o[3 * cols_pad] = h; o[4 * cols_pad] = l; o[5 * cols_pad] = h;
     }
   }
 }
@@ -272,10 +272,18 @@ __global__ void logsoftmax_nll_bwd_f32_kernel(const float* __restrict__ logp, lo
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
 
-__device__ __forceinline__ void store_split(__nv_bfloat16* o, int kp, float x) {   // role 0
+__device__ __forceinline__ void store_split6(__nv_bfloat16* o, int kp, float x) {   // role 3: [p2 | p1 | p0 | p1 | p0 | p0]
   const __nv_bfloat16 h = __float2bfloat16_rn(x);
-  o[0] = h;
-  o[kp] = __float2bfloat16_rn(x - __bfloat162float(h));
+  const float r1 = x - __bfloat162float(h);
+  const __nv_bfloat16 l = __float2bfloat16_rn(r1);
+  o[0] = __float2bfloat16_rn(r1 - __bfloat162float(l));
+  o[kp] = l; o[2 * kp] = h; o[3 * kp] = l; o[4 * kp] = h; o[5 * kp] = h;
+}
+
+__device__ __forceinline__ void store_split(__nv_bfloat16* o, int kp, float x) {   // role 0: [lo | hi | hi]
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  o[0] = __float2bfloat16_rn(x - __bfloat162float(h));
+  o[kp] = h;
   o[2 * kp] = h;
 }
 
@@ -285,7 +293,7 @@ __global__ void gru_f32_prime_kernel(const float* __restrict__ h_state, int batc
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= batch * kp) return;
   const int b = g / kp, j = g - b * kp;
-  store_split(a3 + static_cast<long long>(b) * 3 * kp + j, kp, j < H ? h_state[b * H + j] : 0.f);
+  store_split6(a3 + static_cast<long long>(b) * 6 * kp + j, kp, j < H ? h_state[b * H + j] : 0.f);
 }
 
 __global__ void gru_f32_cell_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
@@ -311,7 +319,7 @@ __global__ void gru_f32_cell_kernel(const float* __restrict__ gi, const float* _
   gr[H + j] = z;
   gr[2 * H + j] = n;
   gr[3 * H + j] = hn;
-  store_split(a3 + static_cast<long long>(b) * 3 * kp + j, kp, h);
+  store_split6(a3 + static_cast<long long>(b) * 6 * kp + j, kp, h);
 }
 
 // one backward timestep: dh = dh_out[t] + carry + rec; writes dgi[t], dgh[t] (+ its split operand) and the new carry dh*z
@@ -502,7 +510,7 @@ extern "C" int srnn_gru_forward_f32(const srnn_gru_f32_args* a, srnn_stream_t s)
       a->h_state, B, H, kp, static_cast<__nv_bfloat16*>(a->a3));
   SRNN_CUDA(cudaGetLastError());
   for (int t = 0; t < T; ++t) {
-    const int rc = split_gemm(a->a3, a->w3, a->ws, B, 3 * H, kp, 3, s);
+    const int rc = split_gemm(a->a3, a->w3, a->ws, B, 3 * H, kp, 6, s);
     if (rc) return rc;
     gru_f32_cell_kernel<<<blocks_for(static_cast<long long>(B) * H, 256), 256, 0, ST(s)>>>(
         a->gi, a->ws, a->b_hh, a->h_state, a->hall, a->gates, B, T, t, H, kp, static_cast<__nv_bfloat16*>(a->a3));

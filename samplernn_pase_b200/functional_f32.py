@@ -3,13 +3,15 @@ three modules as ``functional.py`` (folded embedding table, conditioning hoisted
 passes; model.py:28-203), but every activation, gate and gradient is an fp32 tensor and every contraction enters the
 tcgen05 GEMM on split-bf16 operands (``ops.gemm_nt32`` / ``ops.gemm_tn32``: a.w ~= a_hi.w_hi + a_lo.w_hi + a_hi.w_lo in
 one GEMM with a 3x longer K, fp32 accumulation), so the results agree with the reference's fp32 arithmetic to fp32-level
-tolerances (loss rel <= 1e-5, per-tensor gradient rel-L2 <= 3e-3).  Products are accurate to ~4-7e-6: 2^-18
-from the two-piece split plus ~3e-8 per K=16 accumulator update (the tensor core's fp32 accumulation truncates; measured
-in tests/test_gpu_fp32_mode.py) - which is why the three-piece / six-product variant (``ops.gemm_nt32(terms=6)``, operands
-exact to fp32) is NOT used here: at K >= 1024 its twice-longer accumulation chain costs more accuracy than the extra
-pieces bring.  The recurrence runs as one split-operand GEMM and one fp32 cell kernel per timestep
-(``srnn_gru_forward_f32``).  GRU tiers only.  About 5x slower than the bf16 path; it exists for validation, not for
-throughput.
+tolerances (loss rel <= 1e-5, per-tensor gradient rel-L2 <= 3e-3).  The tensor core's fp32 accumulator
+truncates (~3e-8 relative to the accumulator per K=16 update, measured in tests/test_gpu_fp32_mode.py), so the segments are
+concatenated SMALLEST PRODUCT FIRST: the leading hi.hi product comes last and only its K/16 updates truncate at full
+magnitude.  FORWARD contractions use three pieces per operand and six products (``terms=6``: ~1e-6 at K = 1024, 8e-8 at
+short K), because what a forward error costs is not linear: a pre-activation that lands on the other side of zero flips a
+ReLU gate, and every flipped gate is a full-size error in the gradients behind it.  Backward contractions (linear in the
+error) use two pieces and three products (4.5e-6).  The recurrence runs as one split-operand GEMM (six products forward,
+three backward) and one fp32 cell kernel per timestep (``srnn_gru_forward_f32``).  GRU tiers only.  About 5-6x slower than
+the bf16 path; it exists for validation, not for throughput.
 """
 import torch
 
@@ -38,7 +40,7 @@ class CondsMixFn32(torch.autograd.Function):
         utt = utt.contiguous()
         mixin = ops.mixer_input_f32(utt, table.contiguous(), spk_ids, kp)          # (B*L, kp)
         w = weight.contiguous()                                                    # (C, S+U): already K-major
-        conds = ops.gemm_nt32(mixin[:, :s + u], w, bias=bias.contiguous())
+        conds = ops.gemm_nt32(mixin[:, :s + u], w, bias=bias.contiguous(), terms=6)
         ctx.save_for_backward(mixin, w, spk_ids)
         ctx.dims = (b, l, u, s, c, kp)
         ctx.table_rows = table.shape[0]
@@ -88,7 +90,7 @@ class FrameTierFn32(torch.autograd.Function):
         inv_c = _empty(h, device=dev)
         ops.weight_prep_f32(xv, xg, (h, fs, 1), wcat, (kp, 1, 0), inv_norm=inv_x)
         ops.weight_prep_f32(cv, cg, (h, c, 1), wcat[:, fs:], (kp, 1, 0), inv_norm=inv_c)
-        u = ops.gemm_nt32(ain, wcat, bias=(xb + cb))
+        u = ops.gemm_nt32(ain, wcat, bias=(xb + cb), terms=6)
         if upper is not None:
             ops.bias_act_f32(u, aux2=upper.reshape(b * t, h))
 
@@ -97,7 +99,7 @@ class FrameTierFn32(torch.autograd.Function):
         hn = _empty(layers, b, h, device=dev)
         for i in range(layers):
             w_ih, w_hh, b_ih, b_hh = (p.contiguous() for p in rnn[4 * i: 4 * i + 4])
-            gi = ops.gemm_nt32(x_l, w_ih, bias=b_ih)
+            gi = ops.gemm_nt32(x_l, w_ih, bias=b_ih, terms=6)
             h0_i = h_init[i].contiguous()
             h_state = h0_i.clone()
             hall, gates = ops.gru_forward_f32(gi, w_hh, b_hh, h_state, b, t, h)
@@ -109,7 +111,7 @@ class FrameTierFn32(torch.autograd.Function):
         wu_t = _empty(h, r * h, device=dev)
         inv_u = _empty(h, device=dev)
         ops.weight_prep_f32(uv, ug, (h, h, r), wu, (1, h, h * h), wu_t, (r * h, 1, h), inv_norm=inv_u)
-        up = ops.gemm_nt32(x_l, wu, bias=ub.t().contiguous().view(-1)).view(b, t * r, h)
+        up = ops.gemm_nt32(x_l, wu, bias=ub.t().contiguous().view(-1), terms=6).view(b, t * r, h)
 
         ctx.dims = (b, t, l, c, h, fs, r, kp, layers, upper is not None)
         ctx.saved_layers = saved_layers
@@ -186,19 +188,19 @@ class SampleLevelFn32(torch.autograd.Function):
         ops.weight_prep_f32(ev, eg, (h, q, r0), we, (r0 * q, 1, q), we_t, (1, r0 * h, h), inv_norm=inv_e)
         tt = _empty(r0 * q, h, device=dev)                                         # tt[k*Q+q, o] = sum_q' E[q,q'] We[o,q',k]
         for k in range(r0):
-            ops.gemm_nt32(e32, we[:, k * q:(k + 1) * q], out=tt[k * q:(k + 1) * q])
+            ops.gemm_nt32(e32, we[:, k * q:(k + 1) * q], out=tt[k * q:(k + 1) * q], terms=6)
         cwc = cw.contiguous()
         w_e, w_c, w_u = cwc[:, :h], cwc[:, h:2 * h], cwc[:, 2 * h:]
-        tprime_t = ops.gemm_nt32(tt, w_e)                                 # T'^T[k*Q+q, o'] = sum_o tt[k*Q+q,o] W_e[o',o]
+        tprime_t = ops.gemm_nt32(tt, w_e, terms=6)                                 # T'^T[k*Q+q, o'] = sum_o tt[k*Q+q,o] W_e[o',o]
 
         conds2 = conds.contiguous().view(b * l, c)
-        c_frame = ops.gemm_nt32(conds2, csw.contiguous().view(h, c), bias=csb.contiguous())
-        cterm = ops.gemm_nt32(c_frame, w_c, bias=cbias.contiguous())      # (B*L, H)
+        c_frame = ops.gemm_nt32(conds2, csw.contiguous().view(h, c), bias=csb.contiguous(), terms=6)
+        cterm = ops.gemm_nt32(c_frame, w_c, bias=cbias.contiguous(), terms=6)      # (B*L, H)
 
         # the one-hot x table product is a gather-sum of r0 table rows per sample: exact in fp32
         p_e = ops.embed_gather_f32(tprime_t, xs_u8.contiguous(), rf, r0, q)        # (m, H)
         upper_c = upper.reshape(m, h).contiguous()
-        h1 = ops.gemm_nt32(upper_c, w_u)
+        h1 = ops.gemm_nt32(upper_c, w_u, terms=6)
         mk1 = torch.empty(m, (h + 31) // 32, dtype=torch.int32, device=dev)
         mk2 = torch.empty(m, (h + 31) // 32, dtype=torch.int32, device=dev)
         ops.bias_act_f32(h1, aux=cterm, aux_row_div=fsz, aux2=p_e, relu=True, mask=mk1)
@@ -208,13 +210,13 @@ class SampleLevelFn32(torch.autograd.Function):
         w2_t = _empty(h, h, device=dev)
         inv_2 = _empty(h, device=dev)
         ops.weight_prep_f32(w2v, w2g, (h, h, 1), w2, (h, 1, 0), w2_t, (1, h, 0), inv_norm=inv_2)
-        h2 = ops.gemm_nt32(h1, w2, bias=b2.contiguous())
+        h2 = ops.gemm_nt32(h1, w2, bias=b2.contiguous(), terms=6)
         ops.bias_act_f32(h2, relu=True, mask=mk2)
         w3 = _empty(q, h, device=dev)
         w3_t = _empty(h, q, device=dev)
         inv_3 = _empty(q, device=dev)
         ops.weight_prep_f32(w3v, w3g, (q, h, 1), w3, (h, 1, 0), w3_t, (1, q, 0), inv_norm=inv_3)
-        logp = ops.gemm_nt32(h2, w3, bias=b3.contiguous())                # logits, then log-probabilities in place
+        logp = ops.gemm_nt32(h2, w3, bias=b3.contiguous(), terms=6)                # logits, then log-probabilities in place
         if target_u8 is None:
             target_u8 = torch.zeros(m, dtype=torch.uint8, device=dev)
         target_u8 = target_u8.contiguous()

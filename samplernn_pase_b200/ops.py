@@ -459,9 +459,10 @@ SPLIT_SEGMENTS = {0: 3, 1: 3, 2: 2, 3: 6, 4: 6}
 
 
 def split3(x, role):
-    """fp32 (rows, cols) -> bf16 (rows, n_seg * cols_pad): role 0 [hi|lo|hi], 1 [hi|hi|lo], 2 [hi|lo] (two pieces, 2^-18);
-    role 3 [p0|p0|p1|p0|p1|p2], 4 [q0|q1|q0|q2|q1|q0] (three pieces, fp32-exact operands, six products); cols_pad = cols
-    rounded up to 8.  Returns (tensor, cols_pad)."""
+    """fp32 (rows, cols) -> bf16 (rows, n_seg * cols_pad): role 0 [lo|hi|hi], 1 [hi|lo|hi], 2 [lo|hi] (two pieces, 2^-18);
+    role 3 [p2|p1|p0|p1|p0|p0], 4 [q0|q1|q2|q0|q1|q0] (three pieces, fp32-exact operands, six products) - the smallest
+    products come first along K because the tensor core's accumulator truncates; cols_pad = cols rounded up to 8.
+    Returns (tensor, cols_pad)."""
     x, rows, cols, ld = _mat(x, 'split3 x')
     kp = round_up(cols, 8)
     seg = SPLIT_SEGMENTS[role]
@@ -473,9 +474,10 @@ def split3(x, role):
 
 def gemm_nt32(a, w, out=None, bias=None, gate_mask=None, colsum=None, terms=3):
     """out[m,n] = a[m,k] . w[n,k]^T (+ bias) at fp32-level accuracy: ONE bf16 GEMM over K' = terms * k on split operands.
-    terms = 3: two pieces per operand, products accurate to 4e-6 (short K) .. 7e-6 (K = 1024); terms = 6: three pieces,
-    4e-7 at short K but 1e-5 at K = 1024 - the tensor core's truncating fp32 accumulation costs ~3e-8 per K=16 update, so
-    the longer chain loses more than the extra pieces gain; the model path uses terms = 3.
+    terms = 3: two pieces per operand, products accurate to 4.5e-6 (the 2^-18 of the split); terms = 6: three pieces,
+    8e-8 at short K, 1e-6 at K = 1024 (what is left is the tensor core's truncating fp32 accumulation, ~3e-8 per K=16
+    update of the LAST segment - the segments are ordered smallest product first).  The model path uses 6 forward (ReLU
+    gates flip on pre-activation errors) and 3 backward.
     ``a``/``w``/``out`` are fp32 matrices (views with a row stride are fine)."""
     a, m, k, _ = _mat(a, 'gemm_nt32 a')
     w, n, k2, _ = _mat(w, 'gemm_nt32 w')
@@ -616,12 +618,12 @@ def gru_forward_f32(gi, w_hh, b_hh, h_state, batch, steps, hidden):
     Returns (hall [batch*steps, H], gates [batch*steps, 4H])."""
     h = hidden
     dev = gi.device
-    w3, _ = split3(w_hh, 1)
+    w3, _ = split3(w_hh, 4)                                  # forward: three pieces, six products (see gemm_nt32)
     a = _lib.GruF32Args()
     a.batch, a.steps, a.hidden = batch, steps, h
     hall = torch.empty(batch * steps, h, dtype=F32, device=dev)
     gates = torch.empty(batch * steps, 4 * h, dtype=F32, device=dev)
-    a3 = torch.empty(batch, 3 * h, dtype=BF16, device=dev)
+    a3 = torch.empty(batch, 6 * h, dtype=BF16, device=dev)
     ws = torch.empty(batch, 3 * h, dtype=F32, device=dev)
     a.gi, a.w3, a.b_hh, a.h_state = gi.data_ptr(), w3.data_ptr(), b_hh.data_ptr(), h_state.data_ptr()
     a.hall, a.gates, a.a3, a.ws = hall.data_ptr(), gates.data_ptr(), a3.data_ptr(), ws.data_ptr()
