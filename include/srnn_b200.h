@@ -319,10 +319,11 @@ int srnn_sample_embed(const float* in, int64_t ld, int32_t batch, int32_t q, int
 /* ---------------------------------------------------------------------------------------------
  * fp32-tolerance arithmetic mode (SampleRNNModel(precision='fp32')).  The reference computes in fp32 end to end
  * (model.py:146-155,192-203; no autocast); this mode reproduces its results to fp32-level tolerances (loss
- * rel <= 1e-5, per-tensor gradient rel-L2 <= 3e-3) while still contracting on the tcgen05 GEMM: every activation and
- * gradient is an fp32 tensor, and a product enters srnn_gemm_bf16 on SPLIT operands - x = hi + lo with hi = bf16(x),
- * lo = bf16(x - hi) - as a.w ~= a_hi.w_hi + a_lo.w_hi + a_hi.w_lo, ONE bf16 GEMM with a 3x longer K.  The entries
- * below are what the mode needs besides the GEMM.  It is ~4x slower than the bf16 path.
+ * rel <= 1e-5, per-tensor gradient rel-L2 <= 3e-3; measured 6e-8 / 9.3e-4 at H = 1024) while still contracting on the
+ * tcgen05 GEMM: every activation and gradient is an fp32 tensor, and a product enters srnn_gemm_bf16 on SPLIT operands
+ * concatenated along K - three products of two bf16 pieces (backward) or six products of three pieces (forward), ONE
+ * bf16 GEMM with a 3x / 6x longer K.  The entries below are what the mode needs besides the GEMM.  It is ~5.7x slower
+ * than the bf16 path.
  * ------------------------------------------------------------------------------------------- */
 /* fp32 (rows, cols) -> bf16 (rows, n_seg * cols_pad), every segment zero padded to cols_pad columns.
  * Two pieces (x ~ hi + lo to 2^-18; three products): role 0: [lo | hi | hi] (first operand of a product), role 1:

@@ -1,12 +1,13 @@
 // The fp32-tolerance arithmetic mode (SampleRNNModel(precision='fp32')): every activation, gate and gradient is an fp32
-// tensor; the contractions still run on the tcgen05 GEMM of gemm.cu, but on SPLIT operands - an fp32 value x enters as
-// the bf16 pair hi = bf16(x), lo = bf16(x - hi) and a product a.w is evaluated as a_hi.w_hi + a_lo.w_hi + a_hi.w_lo in
-// ONE bf16 GEMM whose K is three times as long (operands [hi|lo|hi] and [hi|hi|lo] concatenated along K, fp32
-// accumulation): the dropped lo.lo term and the split residue are both ~2^-16 relative, i.e. close to fp32.  This file
-// holds what that mode needs besides the GEMM: the split, fp32 variants of the operand-assembly kernels, the
-// elementwise epilogue (aux add / ReLU / mask), the log-softmax + NLL rows, and the recurrence as a host loop of
-// (split-operand GEMM, cell kernel) per timestep.  The mode exists for parity at the reference's own (fp32) tolerances
-// (SURVEY 8(d)); it is ~4x slower than the bf16 path and is not what bench.py measures by default.
+// tensor; the contractions still run on the tcgen05 GEMM of gemm.cu, but on SPLIT operands concatenated along K into ONE
+// bf16 GEMM with fp32 accumulation: two pieces per operand and three products (a_lo.w_hi + a_hi.w_lo + a_hi.w_hi, ~4.5e-6)
+// for the backward contractions, three pieces and six products (~1e-6 at K = 1024) for the forward ones.  The segments
+// are ordered SMALLEST PRODUCT FIRST because the tensor core's fp32 accumulator truncates (see split3_kernel).  This file
+// holds what the mode needs besides the GEMM: the split, fp32 variants of the operand-assembly kernels, the elementwise
+// epilogue (aux add / ReLU / mask), an exact gather-sum for the folded embedding table, the log-softmax + NLL rows, and
+// the recurrence as a host loop of (split-operand GEMM, fp32 cell kernel) per timestep.  The mode exists for parity at the
+// reference's own (fp32) tolerances; it is ~5.7x slower than the bf16 path and is not what bench.py
+// measures by default.
 #include "common.cuh"
 
 namespace srnn {
