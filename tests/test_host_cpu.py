@@ -108,3 +108,23 @@ def test_carry_state_dict_round_trip_keeps_reference_keys():
     for n in range(len(a.frames_layers)):
         assert torch.equal(b._state[n], a._state[n]) and b._state_valid[n] == [True, False, True]
     assert [st is None for st in b.rnn_states[b.frames_layers[0]]] == [False, True, False]
+
+
+def test_precision_switch_is_validated_and_has_no_cpu_path():
+    """``precision`` accepts 'bf16' / 'fp32' only, the fp32-tolerance mode is GRU-only, it keeps the reference's state-dict
+    keys, and like the bf16 path it refuses CPU tensors (no fallback)."""
+    from samplernn_pase_b200 import SampleRNNModel, ops
+    args = ('embedding', 5, 15, 'acoustic', [9, 5, 4, 3], 10, 50, 4, [4, 4], [1, 1], [32, 32], True, 256)
+    with pytest.raises(ValueError):
+        SampleRNNModel(*args, precision='tf32')
+    with pytest.raises(ValueError):
+        SampleRNNModel(*args, precision='fp32', rnn_cell='lstm')
+    a, b = SampleRNNModel(*args), SampleRNNModel(*args, precision='fp32')
+    assert list(a.state_dict().keys()) == list(b.state_dict().keys())
+    assert all(m.precision == 'fp32' for m in [b.conds_mixer, b.sample_layer, *b.frames_layers])
+    b.set_precision('bf16')
+    assert all(m.precision == 'bf16' for m in [b.conds_mixer, b.sample_layer, *b.frames_layers])
+    with pytest.raises(RuntimeError):
+        ops.gemm_nt32(torch.zeros(8, 8), torch.zeros(8, 8))
+    with pytest.raises(RuntimeError):
+        ops.split3(torch.zeros(8, 8), 0)
